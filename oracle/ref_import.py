@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE ONLY — loader for the *unmodified* reference (115dkk/Impulcifer-pip313).
+
+Imports the reference's own hot-path modules from ``/root/reference`` so that golden vectors can be
+generated from the real implementation (``tests/golden/make_golden.py``) and so that the oracle
+restatement in ``oracle/impulcifer_oracle.py`` can be pinned against it.
+
+``/root/reference`` exists only in the build container, never on the GPU box, so nothing under
+``tests/ -m gpu``, ``bench.py`` or ``__graft_entry__.smoke()`` may import this module.
+
+Only plotting / audio-device / WAV-container modules are stubbed.  No arithmetic is restated here:
+  * ``matplotlib*``, ``seaborn``, ``bokeh*``, ``sounddevice``  -> MagicMock (imported at module top by
+    core/impulse_response_estimator.py:10, core/plotting/*.py)
+  * ``soundfile`` -> 20-line shim over ``scipy.io.wavfile`` (PCM_32 -> float64 via /2**31, exactly what
+    libsndfile does for ``dtype='float64'``); write() quantises with ``np.round(x * 2**31)`` + clip.
+  * ``nnresample`` -> the restatement in ``oracle/nnresample_port.py`` (package absent from the image;
+    parity for that one step is therefore UNPINNED).
+"""
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("IMPULCIFER_REFERENCE_ROOT", "/root/reference")
+
+_STUBS = [
+    'matplotlib', 'matplotlib.pyplot', 'matplotlib.ticker', 'matplotlib.font_manager', 'matplotlib.figure',
+    'matplotlib.axes', 'matplotlib.colors', 'matplotlib.cm', 'matplotlib.mlab', 'matplotlib.gridspec',
+    'mpl_toolkits', 'mpl_toolkits.mplot3d', 'mpl_toolkits.axes_grid1', 'seaborn', 'bokeh', 'bokeh.plotting',
+    'bokeh.models', 'bokeh.layouts', 'bokeh.palettes', 'bokeh.io', 'bokeh.embed', 'bokeh.resources',
+    'sounddevice',
+]
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "core"))
+
+
+def _soundfile_shim():
+    sf = types.ModuleType('soundfile')
+
+    def _read(path, dtype='float64', always_2d=False, **kw):
+        from scipy.io import wavfile
+        fs, d = wavfile.read(path)
+        if d.dtype == np.int32:
+            d = d.astype(np.float64) / 2 ** 31
+        elif d.dtype == np.int16:
+            d = d.astype(np.float64) / 2 ** 15
+        else:
+            d = d.astype(np.float64)
+        if always_2d and d.ndim == 1:
+            d = d[:, None]
+        return d, fs
+
+    def _write(path, data, samplerate=48000, subtype="PCM_32", **kw):
+        from scipy.io import wavfile
+        data = np.asarray(data, dtype=np.float64)
+        if subtype == "PCM_32":
+            q = np.clip(np.round(data * 2 ** 31), -2 ** 31, 2 ** 31 - 1).astype(np.int32)
+        elif subtype == "PCM_16":
+            q = np.clip(np.round(data * 2 ** 15), -2 ** 15, 2 ** 15 - 1).astype(np.int16)
+        else:
+            raise ValueError("shim supports PCM_16/PCM_32 only")
+        wavfile.write(path, int(samplerate), q)
+
+    class _Info:
+        def __init__(self, path):
+            from scipy.io import wavfile
+            fs, d = wavfile.read(path, mmap=True)
+            self.samplerate = fs
+            self.frames = d.shape[0]
+            self.channels = 1 if d.ndim == 1 else d.shape[1]
+            self.subtype = {np.dtype('int32'): 'PCM_32', np.dtype('int16'): 'PCM_16'}.get(d.dtype, 'FLOAT')
+
+    sf.read, sf.write, sf.info = _read, _write, _Info
+    return sf
+
+
+_loaded = False
+
+
+def load():
+    """Make ``core.*`` and ``autoeq.*`` of the reference importable. Idempotent."""
+    global _loaded
+    if _loaded:
+        return
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    for m in _STUBS:
+        sys.modules.setdefault(m, MagicMock())
+    sys.modules.setdefault('soundfile', _soundfile_shim())
+    if 'nnresample' not in sys.modules:
+        here = os.path.dirname(os.path.abspath(__file__))
+        if here not in sys.path:
+            sys.path.insert(0, here)
+        import nnresample_port
+        sys.modules['nnresample'] = nnresample_port
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    _loaded = True
+
+
+def modules():
+    """Return the reference's hot-path modules as a namespace."""
+    load()
+    ns = types.SimpleNamespace()
+    from core import impulse_response_estimator, impulse_response, hrir, decay, constants, audio_io
+    from core import parallel_utils, parallel_processing, parallel_workers
+    from autoeq import frequency_response
+    ns.impulse_response_estimator = impulse_response_estimator
+    ns.impulse_response = impulse_response
+    ns.hrir = hrir
+    ns.decay = decay
+    ns.constants = constants
+    ns.audio_io = audio_io
+    ns.parallel_utils = parallel_utils
+    ns.parallel_processing = parallel_processing
+    ns.parallel_workers = parallel_workers
+    ns.frequency_response = frequency_response
+    return ns

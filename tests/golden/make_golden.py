@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports 115dkk/Impulcifer-pip313 from /root/reference through ``oracle/ref_import.py`` (plot / audio-IO
+stubs only, no arithmetic restated) and records what the reference itself computes for the hot path:
+
+  demo_room_inputs.npz   the eight ``data/demo/room-*.wav`` recordings + ``FC.wav`` as int32 PCM
+  demo_room_golden.npz   ``data/demo/room-responses.wav`` (the reference's own committed output,
+                         32 x 21600 int32) + per-IR peak / knee / crop integers + FC.wav HRIR chain
+  synth71_golden.npz     reference results on the seeded synthetic 7.1 set (``synth.recording_set(seed=1234)``):
+                         all integers, checksums of every IR, slices, FR / smoothing / min-phase vectors
+  small_cases.npz        tiny estimators from the reference's own tests (fs=2000/0.05 s, fs=48000/1 s)
+"""
+import os
+import sys
+
+import numpy as np
+from scipy.io import wavfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, ROOT)
+
+import ref_import  # noqa: E402
+
+ref = ref_import.modules()
+from impulcifer_pip313_b200 import synth  # noqa: E402
+
+IRE = ref.impulse_response_estimator.ImpulseResponseEstimator
+HRIR = ref.hrir.HRIR
+ImpulseResponse = ref.impulse_response.ImpulseResponse
+FrequencyResponse = ref.frequency_response.FrequencyResponse
+DEMO = os.path.join(ref_import.REFERENCE_ROOT, 'data', 'demo')
+SWEEP = os.path.join(ref_import.REFERENCE_ROOT, 'data', 'sweep-6.15s-48000Hz-32bit-2.93Hz-24000Hz.wav')
+
+
+def checksums(x):
+    """Order-insensitive-enough fingerprints of a float64 vector (compared at 1e-12 relative)."""
+    x = np.asarray(x, dtype=np.float64)
+    k = np.arange(len(x), dtype=np.float64)
+    probe = np.cos(0.37 * k) + 0.5 * np.sin(0.011 * k * 1.0)
+    return np.array([x.sum(), np.dot(x, x), np.dot(x, probe), np.abs(x).max()])
+
+
+def demo_room():
+    est = IRE.from_wav(SWEEP)
+    files = [('room-FL,FR-left.wav', ['FL', 'FR'], 'left'), ('room-FL,FR-right.wav', ['FL', 'FR'], 'right'),
+             ('room-FC-left.wav', ['FC'], 'left'), ('room-FC-right.wav', ['FC'], 'right'),
+             ('room-BL,SL-left.wav', ['BL', 'SL'], 'left'), ('room-BL,SL-right.wav', ['BL', 'SL'], 'right'),
+             ('room-SR,BR-left.wav', ['SR', 'BR'], 'left'), ('room-SR,BR-right.wav', ['SR', 'BR'], 'right')]
+    inputs = {}
+    rir = HRIR(est)
+    for name, speakers, side in files:
+        fs, d = wavfile.read(os.path.join(DEMO, name))
+        assert fs == 48000 and d.dtype == np.int32
+        inputs[name] = d
+        rir.open_recording(os.path.join(DEMO, name), speakers, side=side)
+    fs, fc = wavfile.read(os.path.join(DEMO, 'FC.wav'))
+    inputs['FC.wav'] = fc.T.copy()
+    fs, sweep = wavfile.read(SWEEP)
+    inputs['sweep'] = sweep
+    np.savez_compressed(os.path.join(HERE, 'demo_room_inputs.npz'), **inputs)
+
+    gold = {}
+    names, peaks, knees, noise, wins, crops, lens = [], [], [], [], [], [], []
+    for spk, pair in rir.irs.items():
+        for side, ir in pair.items():
+            names.append(f'{spk}-{side}')
+            gold[f'est_ck_{spk}-{side}'] = checksums(ir.data)
+            pk = ir.peak_index()
+            peaks.append(pk)
+            crops.append(max(pk - 48, 0))
+            ir.crop_head()
+            p, k, nf, w = ir.decay_params()
+            knees.append(k)
+            noise.append(nf)
+            wins.append(w)
+            lens.append(len(ir.data))
+    tail = rir.crop_tails()
+    _, golden_wav = wavfile.read(os.path.join(DEMO, 'room-responses.wav'))
+    mat = np.vstack([rir.irs[s][e].data if s in rir.irs and e in rir.irs[s] else np.zeros(tail)
+                     for s, e in (n.split('-') for n in ref.constants.HEXADECAGONAL_TRACK_ORDER)])
+    q = np.clip(np.rint(mat * 2 ** 31), -2 ** 31, 2 ** 31 - 1).astype(np.int32)
+    assert np.array_equal(q, golden_wav.T), "reference no longer reproduces room-responses.wav"
+    gold.update(room_responses=golden_wav.T.copy(), names=np.array(names), peaks=np.array(peaks),
+                crops=np.array(crops), knees=np.array(knees), noise=np.array(noise), wins=np.array(wins),
+                lens=np.array(lens), tail=np.array(tail))
+
+    # binaural chain on FC.wav (the only complete HRIR recording in the demo set)
+    h = HRIR(est)
+    h.open_recording(os.path.join(DEMO, 'FC.wav'), ['FC'])
+    gold['fc_peaks'] = np.array([h.irs['FC']['left'].peak_index(), h.irs['FC']['right'].peak_index()])
+    h.crop_heads()
+    gold['fc_len_after_heads'] = np.array([len(h.irs['FC']['left'].data), len(h.irs['FC']['right'].data)])
+    h.align_ipsilateral_all()
+    gold['fc_tail'] = np.array(h.crop_tails())
+    gold['fc_left'] = h.irs['FC']['left'].data.copy()
+    gold['fc_right'] = h.irs['FC']['right'].data.copy()
+    fr = h.irs['FC']['left'].frequency_response()
+    gold['fc_fr_frequency'] = fr.frequency.copy()
+    gold['fc_fr_raw'] = fr.raw.copy()
+    fr.smoothen_fractional_octave(window_size=1 / 3)
+    gold['fc_fr_smoothed'] = fr.smoothed.copy()
+    np.savez_compressed(os.path.join(HERE, 'demo_room_golden.npz'), **gold)
+    print('demo_room: tail', tail, 'peaks', peaks)
+
+
+def synth71():
+    est = IRE(min_duration=5.0, fs=48000)
+    rec = synth.recording_set(est.test_signal, est.fs, synth.LAYOUT_71, seed=1234)
+    import tempfile
+    gold = {'sweep_len': np.array(len(est)), 'n_octaves': np.array(est.n_octaves),
+            'inv_ck': checksums(est.inverse_filter), 'sweep_ck': checksums(est.test_signal),
+            'rec_ck': np.array([checksums(rec[0]), checksums(rec[1])])}
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, 'FL,FR,FC,SL,SR,BL,BR.wav')
+        wavfile.write(path, est.fs, np.rint(rec.T * 2 ** 31).astype(np.int32))
+        h = HRIR(est)
+        h.open_recording(path, synth.LAYOUT_71)
+    names = [f'{s}-{e}' for s in h.irs for e in ('left', 'right')]
+    gold['names'] = np.array(names)
+    gold['est_ck'] = np.array([checksums(h.irs[s][e].data) for s in h.irs for e in ('left', 'right')])
+    gold['est_peaks'] = np.array([h.irs[s][e].peak_index() for s in h.irs for e in ('left', 'right')])
+    # a window of the raw estimate around each peak (pins float values, not just checksums)
+    gold['est_slices'] = np.array([h.irs[s][e].data[pk - 64:pk + 1984]
+                                   for (s, e), pk in zip(((s, e) for s in h.irs for e in ('left', 'right')),
+                                                         gold['est_peaks'])])
+    dp = [h.irs[s][e].decay_params() for s in h.irs for e in ('left', 'right')]
+    gold['est_knees'] = np.array([d[1] for d in dp])
+    gold['est_noise'] = np.array([d[2] for d in dp])
+    gold['est_wins'] = np.array([d[3] for d in dp])
+    h.crop_heads()
+    gold['len_after_heads'] = np.array([len(h.irs[s][e].data) for s in h.irs for e in ('left', 'right')])
+    h.align_ipsilateral_all()
+    gold['ck_after_ipsi'] = np.array([checksums(h.irs[s][e].data) for s in h.irs for e in ('left', 'right')])
+    h.align_onset_groups_peak_leftref()
+    gold['peaks_after_align'] = np.array([h.irs[s][e].peak_index() for s in h.irs for e in ('left', 'right')])
+    dp = [h.irs[s][e].decay_params() for s in h.irs for e in ('left', 'right')]
+    gold['knees_after_align'] = np.array([d[1] for d in dp])
+    tail = h.crop_tails()
+    gold['tail'] = np.array(tail)
+    gold['final_ck'] = np.array([checksums(h.irs[s][e].data) for s in h.irs for e in ('left', 'right')])
+    gold['final_FL_left'] = h.irs['FL']['left'].data.copy()
+    gold['final_BR_left'] = h.irs['BR']['left'].data.copy()
+    # FR post-processing on four IRs
+    fr_names = [('FL', 'left'), ('FL', 'right'), ('FC', 'left'), ('BR', 'right')]
+    raws, sm13, hl_s, hl_e, mp5, mp10, sm_custom = [], [], [], [], [], [], []
+    for s, e in fr_names:
+        fr = h.irs[s][e].frequency_response()
+        gold['fr_frequency'] = fr.frequency.copy()
+        raws.append(fr.raw.copy())
+        fr.smoothen_fractional_octave(window_size=1 / 3)
+        sm13.append(fr.smoothed.copy())
+        fr2 = fr.copy()
+        fr2.error = fr2.raw - np.mean(fr2.raw)
+        fr2.smoothen_heavy_light()
+        hl_s.append(fr2.smoothed.copy())
+        hl_e.append(fr2.error_smoothed.copy())
+        fr3 = fr.copy()
+        fr3.smoothen_fractional_octave(window_size=2, iterations=2, treble_window_size=1 / 12, treble_iterations=3,
+                                       treble_f_lower=2000, treble_f_upper=12000)
+        sm_custom.append(fr3.smoothed.copy())
+        fr.equalization = -(fr.smoothed - np.mean(fr.smoothed))
+        mp5.append(fr.minimum_phase_impulse_response(fs=est.fs, f_res=5, normalize=False))
+        mp10.append(fr.minimum_phase_impulse_response(fs=est.fs, f_res=10, normalize=True))
+    gold.update(fr_names=np.array([f'{s}-{e}' for s, e in fr_names]), fr_raw=np.array(raws),
+                fr_smoothed=np.array(sm13), fr_hl_smoothed=np.array(hl_s), fr_hl_error=np.array(hl_e),
+                fr_custom=np.array(sm_custom), minphase_f5=np.array(mp5), minphase_f10=np.array(mp10))
+    # resample 48k -> 44.1k through the reference method (nnresample = restated port: UNPINNED)
+    ir = ImpulseResponse(h.irs['FL']['left'].data.copy(), est.fs)
+    ir.resample(44100)
+    gold['resampled_FL_left_44100'] = ir.data.copy()
+    np.savez_compressed(os.path.join(HERE, 'synth71_golden.npz'), **gold)
+    print('synth71: tail', tail, 'peaks', gold['est_peaks'])
+
+
+def small_cases():
+    gold = {}
+    rng = np.random.default_rng(7)
+    for tag, (dur, fs) in {'fs2000': (0.05, 2000), 'fs48000_1s': (1.0, 48000), 'fs44100_2s': (2.0, 44100)}.items():
+        est = IRE(min_duration=dur, fs=fs)
+        full = fs <= 4000  # large cases keep checksums only (recordings are re-synthesised by the test)
+        gold[f'{tag}_n_octaves'] = np.array(est.n_octaves)
+        gold[f'{tag}_len'] = np.array(len(est))
+        gold[f'{tag}_test_signal_ck'] = checksums(est.test_signal)
+        gold[f'{tag}_inverse_filter_ck'] = checksums(est.inverse_filter)
+        if full:
+            gold[f'{tag}_test_signal'] = est.test_signal.copy()
+            gold[f'{tag}_inverse_filter'] = est.inverse_filter.copy()
+        # delayed-impulse recordings, as in tests/test_estimator_roundtrip.py
+        for delay in (0, 1, 127, 1000):
+            if delay >= fs:
+                continue
+            rec = np.concatenate([np.zeros(delay), est.test_signal, np.zeros(int(0.2 * fs))])
+            y = est.estimate(rec)
+            gold[f'{tag}_d{delay}_est_ck'] = checksums(y)
+            gold[f'{tag}_d{delay}_peak'] = np.array(ImpulseResponse(y, fs).peak_index())
+            if full:
+                gold[f'{tag}_d{delay}_est'] = y
+        noise = np.random.default_rng(11).standard_normal(len(est) + fs // 2) * 0.1
+        y = est.estimate(noise)
+        gold[f'{tag}_noise_est_ck'] = checksums(y)
+        if full:
+            gold[f'{tag}_noise_est'] = y
+    # peak_index edge cases (plateaus, negative first, nothing above threshold, silence)
+    cases = {
+        'plateau': np.array([0, 0.2, 1.0, 1.0, 1.0, 0.3, 0, -0.5, 0]),
+        'neg_first': np.array([0, -0.1, -0.9, -0.2, 0.0, 1.0, 0.1]),
+        'monotone': np.linspace(0, 1, 50),
+        'silence': np.zeros(32),
+        'tiny': np.array([0.0, 1e-21, 0.0]),
+        'edge_peak': np.array([1.0, 0.5, 0.2, 0.1]),
+        'plateau_to_end': np.array([0, 0.5, 1.0, 1.0]),
+        'even_plateau': np.array([0, 1.0, 1.0, 0]),
+        'imp1000': np.concatenate([np.zeros(1000), [1.0], np.zeros(500)]),
+    }
+    for k, v in cases.items():
+        gold[f'pk_{k}_x'] = v.astype(np.float64)
+        gold[f'pk_{k}_idx'] = np.array(ImpulseResponse(v.astype(np.float64).copy(), 48000).peak_index())
+    # decay_params degenerate inputs (tests/test_impulse_response_decay.py)
+    dcases = {
+        'short': np.array([1.0, 0.5, 0.2]),
+        'delta': np.concatenate([[1.0], np.zeros(4799)]),
+        'exp': np.exp(-np.arange(48000) / 3000.0) * np.cos(np.arange(48000) * 0.3) + 1e-4 * rng.standard_normal(48000),
+        'noise_only': 1e-3 * rng.standard_normal(20000),
+        'lt30ms': np.concatenate([[1.0], 0.01 * rng.standard_normal(1000)]),
+    }
+    for k, v in dcases.items():
+        gold[f'dc_{k}_x'] = v.astype(np.float64)
+        gold[f'dc_{k}_out'] = np.array([float(t) for t in ref.decay.decay_params(v.astype(np.float64), 48000)])
+    np.savez_compressed(os.path.join(HERE, 'small_cases.npz'), **gold)
+    print('small_cases written')
+
+
+if __name__ == '__main__':
+    demo_room()
+    synth71()
+    small_cases()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
