@@ -1,0 +1,411 @@
+// K1 — batched sweep deconvolution (ImpulseResponseEstimator.estimate, reference
+// core/impulse_response_estimator.py:149-151).
+//
+//   out[r] = convolve(rec[r], inverse_filter, mode='same')          for a whole batch of recordings
+//
+// Two recordings (typically the two ears of one speaker) are packed as re + i*im of ONE complex
+// transform: the inverse filter is real, so (a + i b) * h = (a*h) + i (b*h) and no real-FFT
+// untangling pass exists.  Only the len(rec) centred samples of the full linear convolution are
+// wanted, so the circular length only has to satisfy N >= L + ceil((M-1)/2) (wrap-around lands in
+// samples that are discarded); for the 6.15 s / 48 kHz sweep that is 538 905 -> N = 768 x 768 instead
+// of SciPy's 691 200-point real transforms.
+//
+// Three launches per chunk of pairs (chunks sized so the complex workspace stays inside the 126 MB L2):
+//   A  column pass: load 2 real rows (zero-padded, any sample format) -> DIF over n1 -> x W_N^(n2 k1) -> ws
+//   BC row pass   : ws row -> DIF over n2 -> x H (inverse-sweep spectrum, pre-permuted, pre-scaled)
+//                   -> DIT over k2 -> x conj(W_N^(n2 k1)) -> ws           (in place)
+//   D  column pass: ws -> DIT over k1 -> write the wanted slice of re / im to the two output rows
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <mutex>
+#include <set>
+#include <utility>
+#include <vector>
+
+#include "fft2d.cuh"
+#include "fft_fixed.cuh"
+
+using namespace impb;
+
+namespace {
+
+template <typename T> struct DeconvArgs {
+  cx_t<T>* ws;
+  const cx_t<T>* tw;
+  const cx_t<T>* hs;
+  int64_t N;
+  int N1, N2;
+  // input
+  const void* rec;
+  int64_t ld_in, len, nrows, row0;
+  int in_fmt;
+  // output
+  void* out;
+  int64_t ld_out, out_start, out_len;
+  int out_f64;
+};
+
+__device__ __forceinline__ double load_sample(const void* p, int fmt, int64_t i) {
+  switch (fmt) {
+    case IMPB_FMT_F64: return __ldg(reinterpret_cast<const double*>(p) + i);
+    case IMPB_FMT_F32: return (double)__ldg(reinterpret_cast<const float*>(p) + i);
+    default: return (double)__ldg(reinterpret_cast<const int32_t*>(p) + i) * (1.0 / 2147483648.0);
+  }
+}
+
+// A: real pair -> column DIF
+template <typename T, int TILE> struct DeconvColIn {
+  DeconvArgs<T> a;
+  __device__ __forceinline__ cx_t<T> load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    const int64_t n = (int64_t)e * a.N2 + n2;
+    if (n2 >= a.N2 || n >= a.len) return mkc<T>(0, 0);
+    const int64_t ra = a.row0 + 2 * (int64_t)b, rb = ra + 1;
+    const T re = (T)load_sample(a.rec, a.in_fmt, ra * a.ld_in + n);
+    const T im = rb < a.nrows ? (T)load_sample(a.rec, a.in_fmt, rb * a.ld_in + n) : (T)0;
+    return mkc<T>(re, im);
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= a.N2) return;
+    const size_t idx = (size_t)e * a.N2 + n2;
+    a.ws[(size_t)b * a.N + idx] = cmul(v, __ldg(a.tw + idx));
+  }
+};
+
+// BC: row DIF x H x row DIT, in place
+template <typename T, int TILE> struct DeconvRow {
+  DeconvArgs<T> a;
+  __device__ __forceinline__ cx_t<T> load(int b, int t, int e, int c) const {
+    const int row = t * TILE + c;
+    if (row >= a.N1) return mkc<T>(0, 0);
+    return a.ws[(size_t)b * a.N + (size_t)row * a.N2 + e];
+  }
+  __device__ __forceinline__ cx_t<T> pw(int t, int R, int items, int q, int w) const {
+    return __ldg(a.hs + ((size_t)t * R + q) * items + w);
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v) const {
+    const int row = t * TILE + c;
+    if (row >= a.N1) return;
+    const size_t idx = (size_t)row * a.N2 + e;
+    a.ws[(size_t)b * a.N + idx] = cmul(v, cconj(__ldg(a.tw + idx)));
+  }
+};
+
+// D: column DIT -> real pair out
+template <typename T, int TILE> struct DeconvColOut {
+  DeconvArgs<T> a;
+  __device__ __forceinline__ cx_t<T> load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= a.N2) return mkc<T>(0, 0);
+    return a.ws[(size_t)b * a.N + (size_t)e * a.N2 + n2];
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v) const {
+    const int n2 = t * TILE + c;
+    const int64_t j = (int64_t)e * a.N2 + n2 - a.out_start;
+    if (n2 >= a.N2 || j < 0 || j >= a.out_len) return;
+    const int64_t ra = a.row0 + 2 * (int64_t)b, rb = ra + 1;
+    if (a.out_f64) {
+      double* o = reinterpret_cast<double*>(a.out);
+      o[ra * a.ld_out + j] = (double)v.x;
+      if (rb < a.nrows) o[rb * a.ld_out + j] = (double)v.y;
+    } else {
+      float* o = reinterpret_cast<float*>(a.out);
+      o[ra * a.ld_out + j] = (float)v.x;
+      if (rb < a.nrows) o[rb * a.ld_out + j] = (float)v.y;
+    }
+  }
+};
+
+// spectrum of the inverse filter: scrambled [p1][p2] -> natural order
+__global__ void k_spec_to_natural(const double2* __restrict__ ws, double2* __restrict__ nat, const int* __restrict__ perm1,
+                                  const int* __restrict__ perm2, int N1, int N2) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N1 * N2) return;
+  const int p1 = (int)(i / N2), p2 = (int)(i % N2);
+  nat[(size_t)perm1[p1] + (size_t)N1 * perm2[p2]] = ws[i];
+}
+
+// natural order -> the register/lane order of the fused row kernel:  hs[(tile*R + q)*items + w]
+template <typename T>
+__global__ void k_spec_layout(const double2* __restrict__ nat, cx_t<T>* __restrict__ hs, const int* __restrict__ perm1,
+                              const int* __restrict__ perm2, int N1, int N2, int TILE, int R, double scale) {
+  const int items = (N2 / R) * TILE;
+  const int64_t total = (int64_t)((N1 + TILE - 1) / TILE) * R * items;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int w = (int)(i % items);
+  const int q = (int)((i / items) % R);
+  const int t = (int)(i / ((int64_t)items * R));
+  const int c = w % TILE, j = w / TILE;
+  const int row = t * TILE + c, p2 = j * R + q;
+  double2 v = make_double2(0.0, 0.0);
+  if (row < N1) v = nat[(size_t)perm1[row] + (size_t)N1 * perm2[p2]];
+  hs[i] = mkc<T>((T)(v.x * scale), (T)(v.y * scale));
+}
+
+// ---- compile-time specialised launches (fft_fixed.cuh); sizes must match plan.cu:fixed_radices ----
+template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
+  // the opt-in shared-memory size is a per-kernel, per-device attribute: set it once
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  const std::pair<const void*, int> key((const void*)kernel, device);
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(key)) return IMPB_OK;
+  IMPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  done.insert(key);
+  return IMPB_OK;
+}
+
+#define IMPB_FX_CASE(KERNEL, S_, R0_, R1_, R2_)                                                 \
+  case S_: {                                                                                    \
+    auto k = KERNEL<T, TILE, 256, Radix3<R0_, R1_, R2_>, F>;                                     \
+    const size_t smem = (size_t)S_ * (TILE + 1) * sizeof(cx_t<T>);                               \
+    int rc = fx_prepare(k, smem, device);                                                        \
+    if (rc) return rc;                                                                           \
+    k<<<grid, 256, smem, st>>>(tw0, tw1, f);                                                     \
+    IMPB_CUDA(cudaGetLastError());                                                               \
+    return IMPB_OK;                                                                              \
+  }
+
+#define IMPB_FX_DISPATCH(NAME, KERNEL)                                                                        \
+  template <typename T, int TILE, class F>                                                                   \
+  static int NAME(int S, dim3 grid, cudaStream_t st, int device, const cx_t<T>* tw0, const cx_t<T>* tw1,     \
+                  const F& f) {                                                                              \
+    switch (S) {                                                                                             \
+      IMPB_FX_CASE(KERNEL, 768, 12, 8, 8)                                                                    \
+      default: set_error("no specialised kernel for S=%d", S); return IMPB_EUNSUPPORTED;                    \
+    }                                                                                                        \
+  }
+IMPB_FX_DISPATCH(fx_fwd, k_fx_fwd)
+IMPB_FX_DISPATCH(fx_inv, k_fx_inv)
+IMPB_FX_DISPATCH(fx_conv, k_fx_conv)
+
+template <typename T, int TILE> struct DeconvEngine {
+  Fft2D<T> fft;
+  cx_t<T>* hs = nullptr;
+  int device = 0;
+
+  int launch(const DeconvArgs<T>& a, int pairs, cudaStream_t st) const {
+    int rc;
+    static const bool no_fixed = getenv("IMPB_NO_FIXED") != nullptr;
+    if (fft.col_fixed && fft.row_fixed && !no_fixed) {
+      const Plan2D& p = fft.p;
+      if ((rc = fx_fwd<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
+                                DeconvColIn<T, TILE>{a})))
+        return rc;
+      if ((rc = fx_conv<T, TILE>(p.N2, dim3(fft.row_tiles(), pairs), st, device, fft.fx_row[0], fft.fx_row[1],
+                                 DeconvRow<T, TILE>{a})))
+        return rc;
+      return fx_inv<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
+                             DeconvColOut<T, TILE>{a});
+    }
+    if ((rc = fft.template col_fwd<TILE>(DeconvColIn<T, TILE>{a}, pairs, st))) return rc;
+    if ((rc = fft.template row_conv<TILE>(DeconvRow<T, TILE>{a}, pairs, st))) return rc;
+    return fft.template col_inv<TILE>(DeconvColOut<T, TILE>{a}, pairs, st);
+  }
+};
+
+}  // namespace
+
+struct impb_plan {
+  impb_ctx* ctx = nullptr;
+  int precision = 64;
+  int64_t M = 0, L = 0, s = 0;  // s = (M-1)/2: start of the 'same' slice in the full convolution
+  DeconvEngine<double, 8> e64;
+  DeconvEngine<float, 16> e32;
+  int64_t chunk_pairs = 1;
+  bool has64 = false, has32 = false;
+};
+
+static int build_spectrum(impb_plan* pl, const double* inv_host) {
+  // FP64 transform of the zero-padded filter with a double plan of the same (N1, N2)
+  const Plan2D& target = pl->precision == 64 ? pl->e64.fft.p : pl->e32.fft.p;
+  const int N1 = target.N1, N2 = target.N2;
+  const size_t N = (size_t)target.N;
+  Fft2D<double> tmp;
+  Fft2D<double>* f64 = nullptr;
+  if (pl->precision == 64) {
+    f64 = &pl->e64.fft;
+  } else {
+    Plan2D pd = target;
+    pd.tile = 8;
+    pd.threads = 512;
+    if (!make_subplan(N1, 8, 512, &pd.col) || !make_subplan(N2, 8, 512, &pd.row)) return IMPB_EUNSUPPORTED;
+    pd.smem_col = tile_smem_bytes<double>(pd.col, 8);
+    pd.smem_row = tile_smem_bytes<double>(pd.row, 8);
+    if (std::max(pd.smem_col, pd.smem_row) > pl->ctx->smem_optin) {
+      set_error("FP32 plan %dx%d does not fit the FP64 spectrum builder", N1, N2);
+      return IMPB_EUNSUPPORTED;
+    }
+    int rc = tmp.init(pd);
+    if (rc) return rc;
+    f64 = &tmp;
+  }
+  double *d_h = nullptr;
+  double2 *ws = nullptr, *nat = nullptr;
+  IMPB_CUDA(cudaMalloc(&d_h, pl->M * sizeof(double)));
+  IMPB_CUDA(cudaMalloc(&ws, N * sizeof(double2)));
+  IMPB_CUDA(cudaMalloc(&nat, N * sizeof(double2)));
+  IMPB_CUDA(cudaMemcpy(d_h, inv_host, pl->M * sizeof(double), cudaMemcpyHostToDevice));
+  DeconvArgs<double> a{};
+  a.ws = ws; a.tw = f64->tw; a.hs = nullptr; a.N = (int64_t)N; a.N1 = N1; a.N2 = N2;
+  a.rec = d_h; a.ld_in = pl->M; a.len = pl->M; a.nrows = 1; a.row0 = 0; a.in_fmt = IMPB_FMT_F64;
+  int rc = f64->col_fwd<8>(DeconvColIn<double, 8>{a}, 1, 0);
+  if (!rc) {
+    RowPlain<double, 8> rp{ws, ws, nullptr, (int64_t)N, N1, N2, 0, 0};
+    rc = f64->row_fwd<8>(rp, 1, 0);
+  }
+  if (!rc) {
+    const int thr = 256;
+    k_spec_to_natural<<<(unsigned)((N + thr - 1) / thr), thr>>>(ws, nat, f64->perm_col, f64->perm_row, N1, N2);
+    const double scale = 1.0 / (double)N;
+    if (pl->precision == 64) {
+      const int R = target.row.radix[target.row.nst - 1];
+      const size_t total = (size_t)((N1 + 7) / 8) * 8 * N2;
+      IMPB_CUDA(cudaMalloc(&pl->e64.hs, total * sizeof(double2)));
+      k_spec_layout<double><<<(unsigned)((total + thr - 1) / thr), thr>>>(nat, pl->e64.hs, pl->e64.fft.perm_col,
+                                                                       pl->e64.fft.perm_row, N1, N2, 8, R, scale);
+    } else {
+      const int R = target.row.radix[target.row.nst - 1];
+      const size_t total = (size_t)((N1 + 15) / 16) * 16 * N2;
+      IMPB_CUDA(cudaMalloc(&pl->e32.hs, total * sizeof(float2)));
+      k_spec_layout<float><<<(unsigned)((total + thr - 1) / thr), thr>>>(nat, pl->e32.hs, pl->e32.fft.perm_col,
+                                                                      pl->e32.fft.perm_row, N1, N2, 16, R, scale);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = cuda_fail(e, "inverse-filter spectrum build");
+  }
+  cudaFree(d_h); cudaFree(ws); cudaFree(nat);
+  if (pl->precision != 64) tmp.release();
+  return rc;
+}
+
+extern "C" {
+
+int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, int64_t M, int64_t L,
+                                int32_t precision, impb_plan** out) {
+  if (!ctx || !inv_filter_host || !out || M < 1 || L < 1 || (precision != 64 && precision != 32)) {
+    set_error("impb_deconv_plan_create: bad argument");
+    return IMPB_EINVAL;
+  }
+  DeviceGuard g(ctx->device);
+  impb_plan* pl = new impb_plan();
+  pl->ctx = ctx;
+  pl->e64.device = pl->e32.device = ctx->device;
+  pl->precision = precision;
+  pl->M = M;
+  pl->L = L;
+  pl->s = (M - 1) / 2;
+  // circular length: wanted full-convolution indices [s, s+L) must not be hit by wrap-around
+  const int64_t n_min = std::max<int64_t>(std::max(L + (M - 1) - pl->s, pl->s + L), 16);
+  Plan2D p;
+  // both precisions are planned against the FP64 shared-memory limit (the spectrum is built in FP64)
+  if (!plan_2d(ctx, n_min, false, 8, &p)) {
+    set_error("no 2-pass FFT plan for n >= %lld", (long long)n_min);
+    delete pl;
+    return IMPB_EUNSUPPORTED;
+  }
+  int rc;
+  if (precision == 64) {
+    rc = pl->e64.fft.init(p);
+    pl->has64 = true;
+  } else {
+    Plan2D pf = p;
+    pf.tile = 16;
+    pf.threads = p.threads;
+    if (!make_subplan(p.N1, 16, pf.threads, &pf.col) || !make_subplan(p.N2, 16, pf.threads, &pf.row)) {
+      delete pl;
+      return IMPB_EUNSUPPORTED;
+    }
+    pf.smem_col = tile_smem_bytes<float>(pf.col, 16);
+    pf.smem_row = tile_smem_bytes<float>(pf.row, 16);
+    rc = pl->e32.fft.init(pf);
+    pl->has32 = true;
+  }
+  if (!rc) rc = build_spectrum(pl, inv_filter_host);
+  if (rc) {
+    impb_deconv_plan_destroy(pl);
+    return rc;
+  }
+  const size_t cx = precision == 64 ? sizeof(double2) : sizeof(float2);
+  // pairs per launch triple: measured on B200, fewer/larger launches beat L2-resident chunks at the
+  // current kernel speed (tools/quick_bench.py, IMPB_CHUNK_PAIRS sweep); cap the workspace at 1 GiB
+  int64_t chunk = (int64_t)((size_t)1 << 30) / (int64_t)(p.N * cx);
+  if (const char* e = getenv("IMPB_CHUNK_PAIRS")) chunk = atoll(e);
+  pl->chunk_pairs = std::max<int64_t>(1, std::min<int64_t>(chunk, 32768));
+  *out = pl;
+  return IMPB_OK;
+}
+
+void impb_deconv_plan_destroy(impb_plan* pl) {
+  if (!pl) return;
+  DeviceGuard g(pl->ctx->device);
+  if (pl->has64) { pl->e64.fft.release(); cudaFree(pl->e64.hs); }
+  if (pl->has32) { pl->e32.fft.release(); cudaFree(pl->e32.hs); }
+  delete pl;
+}
+
+int32_t impb_deconv_plan_info(const impb_plan* pl, int64_t* nfft, int64_t* n1, int64_t* n2) {
+  if (!pl) return IMPB_EINVAL;
+  const Plan2D& p = pl->precision == 64 ? pl->e64.fft.p : pl->e32.fft.p;
+  if (nfft) *nfft = p.N;
+  if (n1) *n1 = p.N1;
+  if (n2) *n2 = p.N2;
+  return IMPB_OK;
+}
+
+int64_t impb_deconv_workspace_bytes(const impb_plan* pl, int64_t batch) {
+  if (!pl || batch < 1) return 0;
+  const Plan2D& p = pl->precision == 64 ? pl->e64.fft.p : pl->e32.fft.p;
+  const int64_t pairs = std::min<int64_t>((batch + 1) / 2, pl->chunk_pairs);
+  return pairs * p.N * (int64_t)(pl->precision == 64 ? sizeof(double2) : sizeof(float2));
+}
+
+int32_t impb_deconv_launches_per_execute(const impb_plan* pl, int64_t batch) {
+  if (!pl || batch < 1) return 0;
+  const int64_t pairs = (batch + 1) / 2;
+  return (int32_t)(3 * ((pairs + pl->chunk_pairs - 1) / pl->chunk_pairs));
+}
+
+int32_t impb_deconv_execute(impb_plan* pl, const void* rec, int64_t ld_in, int32_t in_fmt, int64_t len, void* out,
+                            int64_t ld_out, int32_t out_f64, int64_t out_offset, int64_t out_len, int64_t batch,
+                            void* workspace, void* stream) {
+  if (!pl || !rec || !out || !workspace || batch < 0 || len < 0 || len > pl->L || ld_in < len || out_offset < 0 ||
+      out_len < 0 || out_offset + out_len > len || ld_out < out_len || in_fmt < 0 || in_fmt > 2) {
+    set_error("impb_deconv_execute: bad argument (len=%lld L=%lld out_offset=%lld out_len=%lld)", (long long)len,
+              pl ? (long long)pl->L : 0LL, (long long)out_offset, (long long)out_len);
+    return IMPB_EINVAL;
+  }
+  if (batch == 0 || out_len == 0) return IMPB_OK;
+  DeviceGuard g(pl->ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t pairs = (batch + 1) / 2;
+  for (int64_t p0 = 0; p0 < pairs; p0 += pl->chunk_pairs) {
+    const int np = (int)std::min<int64_t>(pl->chunk_pairs, pairs - p0);
+    int rc;
+    if (pl->precision == 64) {
+      DeconvArgs<double> a{};
+      const Plan2D& p = pl->e64.fft.p;
+      a.ws = (double2*)workspace; a.tw = pl->e64.fft.tw; a.hs = pl->e64.hs;
+      a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
+      a.rec = rec; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
+      a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = 1;
+      rc = pl->e64.launch(a, np, st);
+    } else {
+      DeconvArgs<float> a{};
+      const Plan2D& p = pl->e32.fft.p;
+      a.ws = (float2*)workspace; a.tw = pl->e32.fft.tw; a.hs = pl->e32.hs;
+      a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
+      a.rec = rec; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
+      a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = out_f64 ? 1 : 0;
+      rc = pl->e32.launch(a, np, st);
+    }
+    if (rc) return rc;
+  }
+  return IMPB_OK;
+}
+
+}  // extern "C"

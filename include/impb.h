@@ -1,0 +1,162 @@
+/* impb.h — C ABI of libimpulcifer_b200.so (B200 / sm_100a hot path of 115dkk/Impulcifer-pip313).
+ *
+ * The reference is pure Python: its "plugin interface" for this path is the Python class API
+ * (SURVEY.md §8b).  This header is the boundary a maintainer binds with ctypes/cffi from those classes;
+ * INTEGRATION.md shows the stub.  Each entry point names the reference code it replaces (file:line,
+ * relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns int32 status: 0 = IMPB_OK, negative = error; text via impb_last_error()
+ *   - all data pointers are DEVICE pointers owned by the caller unless the name ends in _host
+ *   - every launch takes the cudaStream_t (as void*) it must be ordered on; nothing synchronises
+ *   - arrays are row-major [batch, ld]; int64 index arrays live on the device
+ *   - a context is bound to one device; calls on different streams may come from different host threads
+ *   - no CPU fallback exists anywhere: if the device or the kernel image is missing, calls fail
+ */
+#ifndef IMPB_H
+#define IMPB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define IMPB_API __attribute__((visibility("default")))
+#else
+#define IMPB_API
+#endif
+
+#define IMPB_OK 0
+#define IMPB_EINVAL (-1)    /* bad argument */
+#define IMPB_ECUDA (-2)     /* CUDA runtime error (text in impb_last_error) */
+#define IMPB_ENOMEM (-3)
+#define IMPB_EUNSUPPORTED (-4) /* size that the planner cannot factor */
+
+/* sample formats of impb_deconv_execute input */
+#define IMPB_FMT_F64 0
+#define IMPB_FMT_F32 1
+#define IMPB_FMT_I32PCM 2   /* int32 PCM, scaled by 2^-31 on load (libsndfile PCM_32 -> float64) */
+
+typedef struct impb_ctx impb_ctx;
+typedef struct impb_plan impb_plan;
+typedef struct impb_fft impb_fft;
+
+IMPB_API uint32_t impb_version(void);
+IMPB_API int32_t impb_ctx_create(int32_t device, impb_ctx** out);
+IMPB_API void impb_ctx_destroy(impb_ctx* ctx);
+IMPB_API const char* impb_last_error(void); /* thread-local */
+
+/* ---- K1: sweep deconvolution ---------------------------------------------------------------------
+ * Replaces ImpulseResponseEstimator.estimate(), core/impulse_response_estimator.py:149-151
+ * (scipy.signal.convolve(recording, inverse_filter, mode='same', method='auto')), and the serial
+ * per-column loop that calls it in core/hrir.py:307-355.
+ *
+ * A plan caches the spectrum of the inverse filter for recordings of up to L samples.  precision is
+ * 64 (FP64 arithmetic) or 32 (FP32 fast path, FP64-computed spectrum rounded to FP32).
+ * execute(): rec is [batch, ld_in] in in_fmt, every row holds `len` valid samples (len <= L).  Row r of
+ * out ([batch, ld_out] f64 for precision 64, f32 for precision 32 unless out_f64 != 0) receives
+ *   convolve(rec[r, :len], inverse_filter, 'same')[out_offset : out_offset + out_len].
+ */
+IMPB_API int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, int64_t M, int64_t L,
+                                int32_t precision, impb_plan** out);
+IMPB_API void impb_deconv_plan_destroy(impb_plan* plan);
+IMPB_API int64_t impb_deconv_workspace_bytes(const impb_plan* plan, int64_t batch);
+IMPB_API int32_t impb_deconv_plan_info(const impb_plan* plan, int64_t* nfft, int64_t* n1, int64_t* n2);
+IMPB_API int32_t impb_deconv_execute(impb_plan* plan, const void* rec, int64_t ld_in, int32_t in_fmt, int64_t len,
+                            void* out, int64_t ld_out, int32_t out_f64, int64_t out_offset, int64_t out_len,
+                            int64_t batch, void* workspace, void* stream);
+/* name and launch count of the kernels one execute() issues (bench.py gpu_launches accounting) */
+IMPB_API int32_t impb_deconv_launches_per_execute(const impb_plan* plan, int64_t batch);
+
+/* ---- K2: first-peak search -----------------------------------------------------------------------
+ * Replaces ImpulseResponse.peak_index(), core/impulse_response.py:32-70 and its twin
+ * core/decay.py:12-41: m = max|x|; if m < 1e-20 -> start; first strict local maximum (plateau midpoint,
+ * scipy _local_maxima_1d) of x/m or -x/m that is >= height; else argmax|x|.  Segment r is
+ * x[offsets[r] : offsets[r] + lengths[r]]; peak_out[r] is relative to the segment start.  Bit-exact. */
+IMPB_API int32_t impb_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,
+                        double height, int64_t* peak_out, int64_t batch, void* stream);
+
+/* ---- K4: Lundeby decay parameters ----------------------------------------------------------------
+ * Replaces decay.decay_params(), core/decay.py:44-260 (called by HRIR.crop_tails, core/hrir.py:627-636).
+ * peak_out / knee_out are relative to the segment start. */
+IMPB_API int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths, int32_t fs,
+                     int64_t* peak_out, int64_t* knee_out, double* noise_db_out, int64_t* win_out,
+                     int64_t batch, void* stream);
+
+/* ---- K6: onset cross-correlation lag ---------------------------------------------------------------
+ * Replaces the scipy.signal.correlate(..., 'full') + argmax of HRIR.align_ipsilateral_all,
+ * core/hrir.py:932-948.  a, b: [batch] segments given by offsets/lengths (zero-extended to seg_len);
+ * lag_out[r] = argmax_k sum_n a[n+k] b[n] - (len-1) semantics of `lags[np.argmax(corr)]`. */
+IMPB_API int32_t impb_xcorr_lag(impb_ctx* ctx, const double* x, const int64_t* a_offsets, const int64_t* a_lengths,
+                       const int64_t* b_offsets, const int64_t* b_lengths, int64_t* lag_out, int64_t batch,
+                       void* stream);
+
+/* ---- K3+K5+K7+K16: fused gather / window --------------------------------------------------------------
+ * Replaces the slicing, ImpulseResponse.shift (core/impulse_response.py:92-108), Hann fade-in of
+ * HRIR.crop_heads (core/hrir.py:591-612), the tail crop + Hann fade-out of HRIR.crop_tails
+ * (core/hrir.py:642-651) and the gain multiply of HRIR.normalize (core/hrir.py:527-544).
+ *   dst[r, j] = gain * fade_out(j) * S(j),  j in [0, out_len)
+ *   S(j)      = fade_in(j - shift[r]) * src[src_start[r] + j - shift[r]]   if valid_lo[r] <= j < valid_hi[r]
+ *             = 0                                                            otherwise
+ * fade_in(m) = hann(2*fade_in_len)[m] for m < fade_in_len (1 otherwise); fade_out is the second half of
+ * hann(fade_out_len) laid over the last fade_out_len/2... samples exactly as np.concatenate([ones, win]). */
+IMPB_API int32_t impb_gather_window(impb_ctx* ctx, const double* src, const int64_t* src_start, const int64_t* shift,
+                           const int64_t* valid_lo, const int64_t* valid_hi, int64_t out_len,
+                           int64_t fade_in_len, int64_t fade_out_len, double gain, double* dst, int64_t ld_dst,
+                           int64_t batch, void* stream);
+
+/* ---- generic batched complex FFT plan (used by K8 / K12 / K13 and the host-side shim) -------------- */
+IMPB_API int32_t impb_fft_create(impb_ctx* ctx, int64_t n, int32_t precision, impb_fft** out);
+IMPB_API void impb_fft_destroy(impb_fft* fft);
+
+/* ---- K8: magnitude response -------------------------------------------------------------------------
+ * Replaces audio_io.magnitude_response(), core/audio_io.py:100-113: 20*log10(|rfft(x)|) for the first
+ * ceil(n/2) bins.  x: [batch, ld_x] rows of n samples; mag_out: [batch, ld_out]. */
+IMPB_API int32_t impb_magnitude_db(impb_fft* fft, const double* x, int64_t ld_x, double* mag_out, int64_t ld_out,
+                          int64_t batch, void* workspace, void* stream);
+IMPB_API int64_t impb_fft_workspace_bytes(const impb_fft* fft, int64_t batch);
+
+/* ---- K10: log-frequency linear interpolation ----------------------------------------------------------
+ * Replaces InterpolatedUnivariateSpline(log10 f, y, k=1)(log10 f_out) of FrequencyResponse.interpolate,
+ * autoeq/frequency_response.py:874-894 (shared f_in/f_out grids, y: [batch, n_in]). */
+IMPB_API int32_t impb_loglerp(impb_ctx* ctx, const double* logf_in, const double* y_in, int64_t n_in, int64_t ld_in,
+                     const double* logf_out, int64_t n_out, double* y_out, int64_t ld_out, int64_t batch,
+                     void* stream);
+
+/* ---- K11: fractional-octave smoothing -------------------------------------------------------------------
+ * Replaces FrequencyResponse._smoothen_fractional_octave, autoeq/frequency_response.py:1060-1105:
+ * `it_normal` passes of savgol_filter(y, w_normal, 2) and `it_treble` passes of savgol_filter(y, w_treble, 2)
+ * (mode='interp' edge fit), blended by k_treble[n] (the log-frequency sigmoid, computed by the host shim).
+ * coef_*: [w] convolution weights; edge_*: [w/2, w] edge-fit weights (host: savgol_coeffs / polyfit). */
+IMPB_API int32_t impb_savgol_blend(impb_ctx* ctx, const double* y, int64_t n, int64_t ld, int32_t w_normal,
+                          int32_t it_normal, const double* coef_normal, const double* edge_normal,
+                          int32_t w_treble, int32_t it_treble, const double* coef_treble,
+                          const double* edge_treble, const double* k_treble, double* out, int64_t ld_out,
+                          int64_t batch, void* stream);
+
+/* ---- K12+K13: minimum-phase FIR ---------------------------------------------------------------------------
+ * Replaces scipy firwin2 + minimum_phase(method='homomorphic', half=True) as called by
+ * FrequencyResponse.minimum_phase_impulse_response, autoeq/frequency_response.py:672-680.
+ * gain: [batch, n] linear amplitude on linspace(0, fs/2, n) (last sample 0); fir_out: [batch, n]. */
+typedef struct impb_minphase impb_minphase;
+IMPB_API int32_t impb_minphase_create(impb_ctx* ctx, int64_t n, impb_minphase** out);
+IMPB_API void impb_minphase_destroy(impb_minphase* mp);
+IMPB_API int64_t impb_minphase_workspace_bytes(const impb_minphase* mp, int64_t batch);
+IMPB_API int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_t ld_gain, double* fir_out, int64_t ld_out,
+                          int64_t batch, void* workspace, void* stream);
+
+/* ---- K15+K9: decay window + polyphase resampling ------------------------------------------------------------
+ * Replaces decay.apply_decay_window (core/decay.py:383-403) followed by ImpulseResponse.resample,
+ * core/impulse_response.py:121-124 (nnresample -> scipy.signal.resample_poly -> upfirdn).
+ * taps: the resample_poly window already scaled by `up` ([ntaps], odd).  decay: [batch,4] doubles
+ * (window_start, half_window, knee_index, window_level_dB) or NULL.  dst row length = ceil(n*up/down). */
+IMPB_API int32_t impb_window_resample(impb_ctx* ctx, const double* src, int64_t ld_src, int64_t n, const double* decay,
+                             const double* taps, int64_t ntaps, int32_t up, int32_t down, double* dst,
+                             int64_t ld_dst, int64_t batch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMPB_H */
