@@ -34,11 +34,11 @@ SIGNATURES = {
     "impb_deconv_execute": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64,
                                     c_vp, c_vp]),
     "impb_deconv_launches_per_execute": (c_i32, [c_vp, c_i64]),
-    "impb_peak_index": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_i64, c_vp]),
-    "impb_lundeby": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "impb_xcorr_lag": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "impb_gather_window": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_dbl, c_vp, c_i64,
-                                   c_i64, c_vp]),
+    "impb_peak_index": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_i64, c_i64, c_vp]),
+    "impb_lundeby": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "impb_xcorr_lag": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "impb_gather_window": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp,
+                                   c_i64, c_i64, c_vp]),
     "impb_fft_create": (c_i32, [c_vp, c_i64, c_i32, C.POINTER(c_vp)]),
     "impb_fft_destroy": (None, [c_vp]),
     "impb_fft_workspace_bytes": (c_i64, [c_vp, c_i64]),
@@ -46,10 +46,13 @@ SIGNATURES = {
     "impb_loglerp": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "impb_savgol_blend": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp,
                                   c_vp, c_vp, c_i64, c_i64, c_vp]),
-    "impb_minphase_create": (c_i32, [c_vp, c_i64, C.POINTER(c_vp)]),
+    "impb_minphase_create": (c_i32, [c_vp, c_i64, c_vp, C.POINTER(c_vp)]),
     "impb_minphase_destroy": (None, [c_vp]),
     "impb_minphase_workspace_bytes": (c_i64, [c_vp, c_i64]),
-    "impb_minphase_fir": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "impb_minphase_fir": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "impb_resample_out_len": (c_i64, [c_i64, c_i32, c_i32]),
+    "impb_plan_probe": (c_i32, [c_i64, c_i32, c_i32, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i32 * 6),
+                                C.POINTER(c_i32 * 6)]),
     "impb_window_resample": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_i64,
                                      c_i64, c_vp]),
 }

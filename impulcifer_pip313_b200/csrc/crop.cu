@@ -1,0 +1,576 @@
+// K2 / K4 / K6 / K3+K5+K7+K16: integer logic of the crop / align path on the device.
+//   impb_peak_index    ImpulseResponse.peak_index      core/impulse_response.py:32-70 (twin core/decay.py:12-41)
+//   impb_lundeby       decay.decay_params              core/decay.py:44-260
+//   impb_xcorr_lag     correlate + argmax              core/hrir.py:932-948
+//   impb_gather_window crop / shift / fade / gain      core/hrir.py:591-612, 642-651, 527-544;
+//                                                      core/impulse_response.py:92-108
+// All index results are exact integers: comparisons are done on the same IEEE operations the reference
+// performs (x / max|x| by true division, no FMA contraction on the values that are compared).
+#include <float.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace impb;
+
+namespace {
+
+constexpr double kEps = 1e-20;
+constexpr unsigned long long kNoIndex = 0xFFFFFFFFFFFFFFFFull;
+
+struct PeakScratch {
+  unsigned long long max_bits;  // bits of max |x| (non-negative doubles order like integers)
+  unsigned long long first_peak;
+  unsigned long long first_argmax;
+};
+
+__global__ void k_peak_init(PeakScratch* s, int64_t batch) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < batch) {
+    s[i].max_bits = 0ull;
+    s[i].first_peak = kNoIndex;
+    s[i].first_argmax = kNoIndex;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_absmax(const double* __restrict__ x, const int64_t* __restrict__ offsets,
+                                                const int64_t* __restrict__ lengths, PeakScratch* __restrict__ s) {
+  const int r = blockIdx.y;
+  const int64_t n = lengths[r];
+  const double* p = x + offsets[r];
+  double m = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmax(m, fabs(p[i]));
+  for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmax(m, sm[w]);
+    atomicMax(&s[r].max_bits, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+// candidate test for sample i of the normalised signal q = sign * x / m (scipy _local_maxima_1d semantics)
+__device__ __forceinline__ bool peak_at(const double* p, int64_t n, int64_t i, double m, double sign, double height,
+                                        int64_t* mid) {
+  const double qi = sign * __ddiv_rn(p[i], m);
+  if (!(qi >= height)) return false;
+  const double qp = sign * __ddiv_rn(p[i - 1], m);
+  if (!(qp < qi)) return false;
+  int64_t j = i + 1;
+  const int64_t i_max = n - 1;
+  double qj = sign * __ddiv_rn(p[j], m);
+  while (j < i_max && qj == qi) {
+    ++j;
+    qj = sign * __ddiv_rn(p[j], m);
+  }
+  if (!(qj < qi)) return false;
+  *mid = (i + (j - 1)) / 2;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_first_peak(const double* __restrict__ x, const int64_t* __restrict__ offsets,
+                                                    const int64_t* __restrict__ lengths, double height,
+                                                    PeakScratch* __restrict__ s) {
+  const int r = blockIdx.y;
+  const int64_t n = lengths[r];
+  const double* p = x + offsets[r];
+  const double m = __longlong_as_double((long long)s[r].max_bits);
+  if (!(m >= kEps)) return;
+  const double guard = 0.999 * height * m;
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+    // nothing at or after `base` can beat an already published earlier peak
+    // (first_argmax is only consulted when no peak exists at all, so it need not be complete then)
+    const unsigned long long cur = *((volatile unsigned long long*)&s[r].first_peak);
+    if (cur != kNoIndex && cur < (unsigned long long)base) return;
+    const int64_t i = base + threadIdx.x;
+    if (i >= n) continue;
+    const double v = p[i];
+    const double av = fabs(v);
+    if (av == m) atomicMin(&s[r].first_argmax, (unsigned long long)i);
+    if (i < 1 || i > n - 2 || av < guard) continue;
+    int64_t mid;
+    if (peak_at(p, n, i, m, v > 0 ? 1.0 : -1.0, height, &mid)) atomicMin(&s[r].first_peak, (unsigned long long)mid);
+  }
+}
+
+__global__ void k_peak_final(const PeakScratch* __restrict__ s, int64_t* __restrict__ out, int64_t batch) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const double m = __longlong_as_double((long long)s[i].max_bits);
+  int64_t r = 0;
+  if (m >= kEps) r = s[i].first_peak != kNoIndex ? (int64_t)s[i].first_peak : (int64_t)s[i].first_argmax;
+  out[i] = r;
+}
+
+int run_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths, double height,
+                   int64_t* peak_out, int64_t batch, int64_t max_len_hint, cudaStream_t st) {
+  PeakScratch* scratch = nullptr;
+  IMPB_CUDA(cudaMallocAsync(&scratch, sizeof(PeakScratch) * batch, st));
+  const int thr = 256;
+  k_peak_init<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, batch);
+  // enough blocks per segment to fill the machine for small batches, few for large ones
+  int64_t per_seg = (4 * (int64_t)ctx->sm_count + batch - 1) / batch;
+  per_seg = std::max<int64_t>(1, std::min<int64_t>(per_seg, (max_len_hint + thr * 8 - 1) / (thr * 8)));
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = (int)std::min<int64_t>(65535, batch - b0);
+    dim3 grid((unsigned)per_seg, nb);
+    k_absmax<<<grid, thr, 0, st>>>(x, offsets + b0, lengths + b0, scratch + b0);
+    k_first_peak<<<grid, thr, 0, st>>>(x, offsets + b0, lengths + b0, height, scratch + b0);
+  }
+  k_peak_final<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, peak_out, batch);
+  IMPB_CUDA(cudaGetLastError());
+  IMPB_CUDA(cudaFreeAsync(scratch, st));
+  return IMPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lundeby: one CTA per impulse response
+// ------------------------------------------------------------------------------------------------
+constexpr int LB_THREADS = 512;
+constexpr int LB_MAXWIN = 4096;
+
+struct LundebyShared {
+  double red[LB_THREADS / 32];
+  double bcast[4];
+  long long ibcast[4];
+  double win[LB_MAXWIN];
+};
+
+__device__ __forceinline__ double block_sum(double v, LundebyShared& sh) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < LB_THREADS / 32; ++w) t += sh.red[w];
+  return t;
+}
+
+__device__ __forceinline__ double block_max(double v, LundebyShared& sh) {
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < LB_THREADS / 32; ++w) t = fmax(t, sh.red[w]);
+  return t;
+}
+
+struct SqView {  // squared, peak-normalised analysis segment  sq[i] = (x[pk+i] / mx)^2
+  const double* p;
+  double mx;
+  bool norm;
+  __device__ __forceinline__ double operator()(int64_t i) const {
+    const double v = norm ? __ddiv_rn(p[i], mx) : p[i];
+    return __dmul_rn(v, v);
+  }
+};
+
+__device__ __forceinline__ double range_mean(const SqView& sq, int64_t a, int64_t b, LundebyShared& sh) {
+  double acc = 0.0;
+  for (int64_t i = a + threadIdx.x; i < b; i += LB_THREADS) acc += sq(i);
+  return block_sum(acc, sh) / (double)(b - a);
+}
+
+__device__ __forceinline__ double db10(double v) { return 10.0 * log10(fmax(v, kEps)); }
+
+// block means of `nwin` windows of `w` samples, in dB, into sh.win (nwin <= LB_MAXWIN): one warp per window
+__device__ void fill_windows(const SqView& sq, int nwin, int64_t w, LundebyShared& sh) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < nwin; k += LB_THREADS / 32) {
+    double acc = 0.0;
+    const int64_t a = (int64_t)k * w;
+    for (int64_t i = lane; i < w; i += 32) acc += sq(a + i);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sh.win[k] = db10(acc / (double)w);
+  }
+  __syncthreads();
+}
+
+struct Regress { double slope, icpt; };
+__device__ Regress linregress_dev(const double* y, double wd, int s, int e) {
+  // x[k] = k*wd + wd/2 ; scipy: slope = cov(x,y)/var(x) (bias=1), intercept = ymean - slope*xmean
+  const int n = e - s;
+  double xm = 0.0, ym = 0.0;
+  for (int k = s; k < e; ++k) { xm += (double)k * wd + wd / 2; ym += y[k]; }
+  xm /= n; ym /= n;
+  double sxx = 0.0, sxy = 0.0;
+  for (int k = s; k < e; ++k) {
+    const double dx = ((double)k * wd + wd / 2) - xm;
+    sxx += dx * dx;
+    sxy += dx * (y[k] - ym);
+  }
+  Regress r;
+  r.slope = (sxy / n) / (sxx / n);
+  r.icpt = ym - r.slope * xm;
+  return r;
+}
+
+__device__ __forceinline__ int first_le(const double* w, int n, double thr) {
+  for (int k = 0; k < n; ++k)
+    if (w[k] <= thr) return k;
+  return -1;
+}
+
+// argmin_i |i*step - t| over i in [0, ns), first index on ties (np.argmin(np.abs(t_squared - t)))
+__device__ int64_t nearest_t(double t, double step, int64_t ns) {
+  if (ns <= 1 || !(step > 0.0)) return 0;
+  int64_t i0 = (int64_t)floor(t / step);
+  i0 = max((int64_t)0, min(i0, ns - 1));
+  int64_t best = i0;
+  double bd = fabs((double)i0 * step - t);
+  for (int64_t c = max((int64_t)0, i0 - 2); c <= min(ns - 1, i0 + 2); ++c) {
+    const double d = fabs((double)c * step - t);
+    if (d < bd || (d == bd && c < best)) { bd = d; best = c; }
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict__ x, const int64_t* __restrict__ offsets,
+                                                        const int64_t* __restrict__ lengths, int fs,
+                                                        const int64_t* __restrict__ peaks, int64_t* __restrict__ peak_out,
+                                                        int64_t* __restrict__ knee_out, double* __restrict__ noise_out,
+                                                        int64_t* __restrict__ win_out) {
+  __shared__ LundebyShared sh;
+  const int r = blockIdx.x;
+  const int64_t n_ir = lengths[r];
+  const double* ir = x + offsets[r];
+  const bool lead = threadIdx.x == 0;
+#define LB_RETURN(pk_, knee_, noise_, w_)                                                    \
+  do {                                                                                       \
+    if (lead) { peak_out[r] = (pk_); knee_out[r] = (knee_); noise_out[r] = (noise_); win_out[r] = (w_); } \
+    return;                                                                                  \
+  } while (0)
+
+  if (n_ir < 10) LB_RETURN(0, n_ir, -200.0, n_ir > 0 ? n_ir : 1);
+  const int64_t pk = peaks[r];
+  const int64_t stop = min(pk + (int64_t)(2 * fs), n_ir);
+  const int64_t ns = stop - pk;  // >= 1 because pk <= n_ir - 1
+  const double* seg = ir + pk;
+  double mx = 0.0;
+  for (int64_t i = threadIdx.x; i < ns; i += LB_THREADS) mx = fmax(mx, fabs(seg[i]));
+  mx = block_max(mx, sh);
+  SqView sq{seg, mx, mx >= kEps};
+  const double step = ns > 1 ? ((double)ns / (double)fs) / (double)(ns - 1) : 0.0;  // linspace(0, ns/fs, ns)
+  const double t_last = (double)(ns - 1) * step;
+
+  // ---- pass 1: 30 ms windows ---------------------------------------------------------------
+  double wd = 0.03;
+  int64_t nwin = (int64_t)((double)ns / (double)fs / wd);
+  if (nwin == 0) {
+    const double nf = 10.0 * log10(fmax(range_mean(sq, 0, ns, sh), kEps));
+    LB_RETURN(pk, pk + ns, nf, max((int64_t)1, ns));
+  }
+  int64_t w = max((int64_t)((double)ns / (double)nwin), (int64_t)1);
+  const int64_t w_first = w;
+  if (nwin > LB_MAXWIN) nwin = LB_MAXWIN;  // cannot happen for 30 ms windows of <= 2 s
+  fill_windows(sq, (int)nwin, w, sh);
+
+  int64_t tail0 = (int64_t)((double)ns * 0.9);
+  if (tail0 >= ns) tail0 = 0;
+  const double noise = 10.0 * log10(fmax(range_mean(sq, tail0, ns, sh), kEps));
+
+  // scalar section (thread 0), results broadcast through shared memory
+  if (lead) {
+    int status = 0;  // 0 continue, 1 return full-length
+    int slope_end = (int)nwin;
+    const int c0 = first_le(sh.win, (int)nwin, noise + 10.0);
+    if (c0 > 0) slope_end = c0;
+    double slope = 0.0, icpt = 0.0;
+    if (slope_end < 2) {
+      if (nwin >= 2) slope_end = (int)nwin; else status = 1;
+    }
+    if (!status) {
+      const Regress rg = linregress_dev(sh.win, wd, 0, slope_end);
+      slope = rg.slope; icpt = rg.icpt;
+      if (isnan(slope) || fabs(slope) < kEps) status = 1;
+    }
+    sh.ibcast[0] = status;
+    sh.bcast[0] = slope;
+    sh.bcast[1] = icpt;
+  }
+  __syncthreads();
+  if (sh.ibcast[0] == 1) LB_RETURN(pk, pk + ns, noise, w_first);
+  const double slope = sh.bcast[0], icpt = sh.bcast[1];
+  double knee_t = fmin(fmax((noise - icpt) / slope, 0.0), t_last);
+  __syncthreads();
+
+  // ---- pass 2: three windows per 10 dB of decay ------------------------------------------------
+  const double den = fabs(slope) * 3;
+  wd = den < kEps ? t_last / 3.0 : 10.0 / den;
+  int64_t n2 = wd <= kEps ? 1 : (int64_t)((double)ns / (double)fs / wd);
+  if (n2 == 0) n2 = 1;
+  w = max((int64_t)((double)ns / (double)n2), (int64_t)1);
+  const int64_t n_t = n2;              // length of t_windows (kept even if the windows array is shortened)
+  if (n2 * w > ns) n2 = ns / w;
+  if (n2 > LB_MAXWIN) {
+    // Pathological (decay faster than ~60 dB in 10 ms): the reference would build > 4096 windows.
+    // Report the first-pass result rather than silently diverging; documented in DESIGN.md.
+    LB_RETURN(pk, pk + nearest_t(knee_t, step, ns), noise, w);
+  }
+  fill_windows(sq, (int)n2, w, sh);
+  const int nw = (int)n2;
+  const double t_win_last = (double)(n_t - 1) * wd + wd / 2;
+
+  // knee index in window units
+  if (lead) {
+    int k_idx = -1;
+    for (int64_t k = 0; k < n_t; ++k)
+      if ((double)k * wd + wd / 2 >= knee_t) { k_idx = (int)k; break; }
+    double kt = knee_t, kv;
+    if (k_idx < 0 || k_idx >= nw) {
+      kt = t_win_last;
+      k_idx = (int)(n_t - 1);
+      kv = sh.win[nw - 1];
+    } else {
+      kv = sh.win[k_idx];
+    }
+    sh.bcast[0] = kt;
+    sh.bcast[1] = kv;
+    sh.ibcast[0] = k_idx;
+  }
+  __syncthreads();
+  double knee_t_it = sh.bcast[0], knee_val_it = sh.bcast[1];
+  long long k_idx_it = sh.ibcast[0];
+  double noise_it = noise;
+  __syncthreads();
+
+  for (int iter = 0; iter < 5; ++iter) {
+    // -- noise segment bounds (thread 0) --
+    if (lead) {
+      long long go = 1;
+      int64_t a = 0, b = 0;
+      const int nf0 = first_le(sh.win, nw, knee_val_it - 5);
+      if (nf0 < 0) go = 0;
+      if (go) {
+        const double t0 = fmax((double)nf0 * wd + wd / 2, 0.1 * t_last);
+        if (t0 > t_win_last) go = 0;
+        if (go) {
+          const double t1 = fmin(t0 + knee_t_it, t_last);
+          a = nearest_t(t0, step, ns);
+          b = nearest_t(t1, step, ns);
+          if (a >= b) go = 0;
+        }
+      }
+      sh.ibcast[0] = go; sh.ibcast[1] = a; sh.ibcast[2] = b;
+    }
+    __syncthreads();
+    const long long go = sh.ibcast[0];
+    const int64_t a = sh.ibcast[1], b = sh.ibcast[2];
+    __syncthreads();
+    if (!go) break;
+    noise_it = 10.0 * log10(fmax(range_mean(sq, a, b, sh), kEps));
+    // -- late slope (thread 0) --
+    if (lead) {
+      long long state = 1;  // 1 continue iterating, 0 break, 2 converged (break after update)
+      int e = first_le(sh.win, nw, noise_it + 8);
+      int s = first_le(sh.win, nw, noise_it + 8 + 20);
+      double nkt = knee_t_it, nkv = knee_val_it;
+      long long nki = k_idx_it;
+      if (e < 0 || s < 0) state = 0;
+      if (state) {
+        e -= 1;
+        s = max(s - 1, 0);
+        if (e <= s + 1) state = 0;
+      }
+      if (state) {
+        const Regress rg = linregress_dev(sh.win, wd, s, e);
+        if (isnan(rg.slope) || fabs(rg.slope) < kEps) {
+          state = 0;
+        } else {
+          const double t_first = wd / 2;
+          const double new_t = fmin(fmax((noise_it - rg.icpt) / rg.slope, t_first), t_win_last);
+          long long new_idx = -1;
+          for (int64_t k = 0; k < n_t; ++k)
+            if ((double)k * wd + wd / 2 >= new_t) { new_idx = k; break; }
+          if (new_idx < 0) new_idx = n_t - 1;
+          if (new_idx == k_idx_it) {
+            nkt = (double)k_idx_it * wd + wd / 2;
+            state = 2;
+          } else {
+            nki = new_idx;
+            nkt = (double)new_idx * wd + wd / 2;
+            nkv = new_idx < nw ? sh.win[new_idx] : sh.win[nw - 1];
+          }
+        }
+      }
+      sh.ibcast[0] = state; sh.ibcast[1] = nki;
+      sh.bcast[0] = nkt; sh.bcast[1] = nkv;
+    }
+    __syncthreads();
+    const long long state = sh.ibcast[0];
+    k_idx_it = sh.ibcast[1];
+    knee_t_it = sh.bcast[0];
+    knee_val_it = sh.bcast[1];
+    __syncthreads();
+    if (state != 1) break;
+  }
+  LB_RETURN(pk, pk + nearest_t(knee_t_it, step, ns), noise_it, w);
+#undef LB_RETURN
+}
+
+// ------------------------------------------------------------------------------------------------
+// onset cross-correlation: one CTA per pair, direct evaluation in FP64
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_xcorr(const double* __restrict__ x, const int64_t* __restrict__ a_off,
+                                               const int64_t* __restrict__ a_len, const int64_t* __restrict__ b_off,
+                                               const int64_t* __restrict__ b_len, int64_t* __restrict__ lag_out) {
+  extern __shared__ double smx[];
+  const int r = blockIdx.x;
+  const int na = (int)a_len[r], nb = (int)b_len[r];
+  double* a = smx;
+  double* b = smx + na;
+  for (int i = threadIdx.x; i < na; i += blockDim.x) a[i] = x[a_off[r] + i];
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) b[i] = x[b_off[r] + i];
+  __syncthreads();
+  // z[k] = sum_l a[l] * b[l - k + nb - 1],  k in [0, na + nb - 1)
+  double best = -DBL_MAX;
+  int best_k = 0x7fffffff;
+  const int nk = na + nb - 1;
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) {
+    const int shift = k - (nb - 1);       // l - shift indexes b
+    const int lo = max(0, shift), hi = min(na, nb + shift);
+    double acc = 0.0;
+    for (int l = lo; l < hi; ++l) acc = fma(a[l], b[l - shift], acc);
+    if (acc > best) { best = acc; best_k = k; }
+  }
+  // block arg-max, first index on ties
+  __shared__ double sv[256];
+  __shared__ int sk[256];
+  sv[threadIdx.x] = best;
+  sk[threadIdx.x] = best_k;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double v2 = sv[threadIdx.x + o];
+      const int k2 = sk[threadIdx.x + o];
+      if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && k2 < sk[threadIdx.x])) {
+        sv[threadIdx.x] = v2;
+        sk[threadIdx.x] = k2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) lag_out[r] = (nk > 0 && na > 0) ? (int64_t)sk[0] - (int64_t)(na - 1) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused gather / shift / fade / gain
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_window(const double* __restrict__ src, const int64_t* __restrict__ src_start,
+                                                       const int64_t* __restrict__ shift, const int64_t* __restrict__ valid_lo,
+                                                       const int64_t* __restrict__ valid_hi, int64_t out_len,
+                                                       const double* __restrict__ fade_in, int64_t fade_in_len,
+                                                       const double* __restrict__ fade_out, int64_t fade_out_len, double gain,
+                                                       int apply_gain, double* __restrict__ dst, int64_t ld_dst) {
+  const int r = blockIdx.y;
+  const int64_t s0 = src_start[r], sh = shift ? shift[r] : 0;
+  const int64_t lo = valid_lo ? valid_lo[r] : 0, hi = valid_hi ? valid_hi[r] : out_len;
+  const int64_t fo0 = out_len - fade_out_len;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < out_len; j += (int64_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    if (j >= lo && j < hi) {
+      const int64_t m = j - sh;  // index into the head-cropped array
+      v = src[s0 + m];
+      if (m < fade_in_len) v = __dmul_rn(v, fade_in[m]);
+    }
+    if (j >= fo0 && fade_out_len > 0) v = __dmul_rn(v, fade_out[j - fo0]);
+    if (apply_gain) v = __dmul_rn(v, gain);
+    dst[(size_t)r * ld_dst + j] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t impb_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths, double height,
+                        int64_t* peak_out, int64_t batch, int64_t max_len, void* stream) {
+  if (!ctx || !x || !offsets || !lengths || !peak_out || batch < 0) {
+    set_error("impb_peak_index: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0) return IMPB_OK;
+  DeviceGuard g(ctx->device);
+  return run_peak_index(ctx, x, offsets, lengths, height, peak_out, batch, std::max<int64_t>(max_len, 1),
+                        (cudaStream_t)stream);
+}
+
+int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths, int32_t fs,
+                     int64_t* peak_out, int64_t* knee_out, double* noise_db_out, int64_t* win_out, int64_t batch,
+                     int64_t max_len, void* stream) {
+  if (!ctx || !x || !offsets || !lengths || !peak_out || !knee_out || !noise_db_out || !win_out || batch < 0 ||
+      fs <= 0) {
+    set_error("impb_lundeby: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0) return IMPB_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* peaks = nullptr;
+  IMPB_CUDA(cudaMallocAsync(&peaks, sizeof(int64_t) * batch, st));
+  int rc = run_peak_index(ctx, x, offsets, lengths, 0.12589, peaks, batch, std::max<int64_t>(max_len, 1), st);
+  if (!rc) {
+    for (int64_t b0 = 0; b0 < batch && !rc; b0 += 1 << 30) {
+      const int64_t nb = std::min<int64_t>((int64_t)1 << 30, batch - b0);
+      k_lundeby<<<(unsigned)nb, LB_THREADS, 0, st>>>(x, offsets + b0, lengths + b0, fs, peaks + b0, peak_out + b0,
+                                                    knee_out + b0, noise_db_out + b0, win_out + b0);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "k_lundeby");
+  }
+  cudaFreeAsync(peaks, st);
+  return rc;
+}
+
+int32_t impb_xcorr_lag(impb_ctx* ctx, const double* x, const int64_t* a_offsets, const int64_t* a_lengths,
+                       const int64_t* b_offsets, const int64_t* b_lengths, int64_t* lag_out, int64_t batch,
+                       int64_t max_seg_len, void* stream) {
+  if (!ctx || !x || !a_offsets || !a_lengths || !b_offsets || !b_lengths || !lag_out || batch < 0 || max_seg_len < 0) {
+    set_error("impb_xcorr_lag: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0) return IMPB_OK;
+  const size_t smem = 2 * (size_t)max_seg_len * sizeof(double);
+  if (smem > ctx->smem_optin) {
+    set_error("impb_xcorr_lag: segments of %lld samples do not fit shared memory", (long long)max_seg_len);
+    return IMPB_EUNSUPPORTED;
+  }
+  DeviceGuard g(ctx->device);
+  IMPB_CUDA(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_xcorr<<<(unsigned)batch, 256, smem, (cudaStream_t)stream>>>(x, a_offsets, a_lengths, b_offsets, b_lengths, lag_out);
+  IMPB_CUDA(cudaGetLastError());
+  return IMPB_OK;
+}
+
+int32_t impb_gather_window(impb_ctx* ctx, const double* src, const int64_t* src_start, const int64_t* shift,
+                           const int64_t* valid_lo, const int64_t* valid_hi, int64_t out_len, const double* fade_in,
+                           int64_t fade_in_len, const double* fade_out, int64_t fade_out_len, double gain, double* dst,
+                           int64_t ld_dst, int64_t batch, void* stream) {
+  if (!ctx || !src || !src_start || !dst || batch < 0 || out_len < 0 || ld_dst < out_len || fade_in_len < 0 ||
+      fade_out_len < 0 || fade_out_len > out_len || (fade_in_len > 0 && !fade_in) || (fade_out_len > 0 && !fade_out)) {
+    set_error("impb_gather_window: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0 || out_len == 0) return IMPB_OK;
+  DeviceGuard g(ctx->device);
+  const int thr = 256;
+  int64_t bx = std::max<int64_t>(1, std::min<int64_t>((out_len + thr * 4 - 1) / (thr * 4), 1024));
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = (int)std::min<int64_t>(65535, batch - b0);
+    k_gather_window<<<dim3((unsigned)bx, nb), thr, 0, (cudaStream_t)stream>>>(
+        src, src_start + b0, shift ? shift + b0 : nullptr, valid_lo ? valid_lo + b0 : nullptr,
+        valid_hi ? valid_hi + b0 : nullptr, out_len, fade_in, fade_in_len, fade_out, fade_out_len, gain,
+        gain != 1.0 ? 1 : 0, dst + (size_t)b0 * ld_dst, ld_dst);
+  }
+  IMPB_CUDA(cudaGetLastError());
+  return IMPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,559 @@
+// Per-IR frequency-response post-processing on the device.
+//   impb_magnitude_db   audio_io.magnitude_response                      core/audio_io.py:100-113
+//   impb_loglerp        InterpolatedUnivariateSpline(log10 f, y, k=1)    autoeq/frequency_response.py:874-894
+//   impb_savgol_blend   FrequencyResponse._smoothen_fractional_octave    autoeq/frequency_response.py:1060-1105
+//   impb_minphase_fir   firwin2 + minimum_phase(homomorphic, half=True)  autoeq/frequency_response.py:672-680,
+//                       scipy/signal/_fir_filter_design.py:577-775, 1383-1406
+// The transforms reuse the tile-FFT engine (fft2d.cuh) with exact-length plans; spectra stay in position
+// ("scrambled") order between a forward and an inverse transform, so no reordering pass exists.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "fft2d.cuh"
+
+using namespace impb;
+
+struct impb_fft {
+  impb_ctx* ctx = nullptr;
+  int64_t n = 0;
+  Fft2D<double> f;
+};
+
+namespace {
+
+constexpr int TILE = 8;
+
+// ---- real rows in (zero imaginary part), column pass ------------------------------------------------
+struct RealColIn {
+  const double* x;   // [batch, ld]
+  int64_t ld, n;     // valid samples per row (zero-padded to N)
+  double2* ws;
+  const double2* tw;
+  int64_t N;
+  int N2;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    const int64_t i = (int64_t)e * N2 + n2;
+    if (n2 >= N2 || i >= n) return make_double2(0.0, 0.0);
+    return make_double2(x[(size_t)b * ld + i], 0.0);
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return;
+    const size_t idx = (size_t)e * N2 + n2;
+    ws[(size_t)b * N + idx] = cmul(v, tw[idx]);
+  }
+};
+
+// ---- row pass whose store sees the natural frequency index k ------------------------------------------
+template <class OP> struct RowFwdOp {
+  const double2* ws;
+  int64_t N;
+  int N1, N2;
+  const int* perm1;
+  const int* perm2;
+  OP op;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int row = t * TILE + c;
+    if (row >= N1) return make_double2(0.0, 0.0);
+    return ws[(size_t)b * N + (size_t)row * N2 + e];
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int row = t * TILE + c;
+    if (row >= N1) return;
+    op(b, (size_t)row * N2 + e, (int64_t)perm1[row] + (int64_t)N1 * perm2[e], v);
+  }
+};
+
+struct MagDbOp {
+  double* out;
+  int64_t ld, half;
+  __device__ __forceinline__ void operator()(int b, size_t, int64_t k, double2 v) const {
+    if (k < half) out[(size_t)b * ld + k] = 20.0 * log10(hypot(v.x, v.y));
+  }
+};
+
+__global__ void k_loglerp(const double* __restrict__ lx, const double* __restrict__ y, int64_t n_in, int64_t ld_in,
+                          const double* __restrict__ lxo, int64_t n_out, double* __restrict__ out, int64_t ld_out) {
+  const int b = blockIdx.y;
+  const double* yy = y + (size_t)b * ld_in;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x) {
+    const double xo = lxo[j];
+    // searchsorted(lx, xo, 'right') - 1, clipped to [0, n_in-2]
+    int64_t lo = 0, hi = n_in;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (lx[mid] <= xo) lo = mid + 1; else hi = mid;
+    }
+    int64_t i = lo - 1;
+    i = max((int64_t)0, min(i, n_in - 2));
+    const double x0 = lx[i], x1 = lx[i + 1];
+    out[(size_t)b * ld_out + j] = (yy[i] * (x1 - xo) + yy[i + 1] * (xo - x0)) / (x1 - x0);
+  }
+}
+
+// ---- Savitzky-Golay (order 2, mode='interp') ------------------------------------------------------------
+__device__ void savgol_pass(const double* __restrict__ src, double* __restrict__ dst, int n, int w,
+                            const double* __restrict__ coef, const double* __restrict__ edge) {
+  const int half = w / 2;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double acc = 0.0;
+    if (i < half) {
+      const double* e = edge + (size_t)i * w;
+      for (int j = 0; j < w; ++j) acc += e[j] * src[j];
+    } else if (i >= n - half) {
+      const double* e = edge + (size_t)(n - 1 - i) * w;
+      for (int j = 0; j < w; ++j) acc += e[j] * src[n - 1 - j];
+    } else {
+      // np.convolve(y, c, 'same')[i] = sum_j c[j] * y[i + half - j]
+      for (int j = 0; j < w; ++j) acc += coef[j] * src[i + half - j];
+    }
+    dst[i] = acc;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_savgol_blend(const double* __restrict__ y, int n, int64_t ld, int wn, int itn,
+                                                      const double* __restrict__ cn, const double* __restrict__ en, int wt,
+                                                      int itt, const double* __restrict__ ct, const double* __restrict__ et,
+                                                      const double* __restrict__ kt, double* __restrict__ out, int64_t ld_out) {
+  extern __shared__ double sm[];
+  double* a = sm;          // ping
+  double* bb = sm + n;     // pong
+  double* yn = sm + 2 * n; // result of the normal filter
+  const int r = blockIdx.x;
+  const double* src = y + (size_t)r * ld;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = src[i];
+  __syncthreads();
+  double* cur = a;
+  double* nxt = bb;
+  for (int it = 0; it < itn; ++it) {
+    savgol_pass(cur, nxt, n, wn, cn, en);
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) yn[i] = cur[i];
+  __syncthreads();
+  if (itn > 0) {  // restart the treble chain from the input
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = src[i];
+    __syncthreads();
+  }
+  cur = a;
+  nxt = bb;
+  for (int it = 0; it < itt; ++it) {
+    savgol_pass(cur, nxt, n, wt, ct, et);
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double k_t = kt[i];
+    const double k_n = k_t * -1.0 + 1.0;
+    out[(size_t)r * ld_out + i] = __dadd_rn(__dmul_rn(yn[i], k_n), __dmul_rn(cur[i], k_t));
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// minimum-phase FIR
+// ================================================================================================
+struct impb_minphase {
+  impb_ctx* ctx = nullptr;
+  int64_t n = 0;         // gain points == output taps
+  int64_t numtaps = 0;   // 2n  (== n_fft of the homomorphic transform)
+  int64_t nf = 0;        // irfft length of firwin2: 2 * 2^ceil(log2(numtaps))
+  Fft2D<double> big;     // length nf
+  Fft2D<double> small;   // length numtaps
+  double* hamming = nullptr;  // [numtaps]
+  int64_t chunk = 256;
+};
+
+namespace {
+
+// firwin2 spectrum evaluated at natural index k in [0, nf):  Hermitian extension of fx * shift.
+//
+// The homomorphic transform downstream takes log|H| at the Nyquist bin, where a type-II filter is
+// analytically ZERO: what the reference feeds into the log there (~1e-12) is the imprint of the rounding
+// of its phase ramp  -(numtaps-1)/2 * 1j * pi * x / nyq.  To land on the same value the ramp is rebuilt
+// with the reference's exact sequence of IEEE operations (numpy divides a complex array by a real scalar
+// by multiplying with fl(1/nyq); verified bit-identical on the host for every supported rate).
+struct FirwinSpec {
+  const double* gain;  // [batch, ld]
+  int64_t ld, n, nf;
+  double step_x;   // nyq / (nfreqs - 1)          : np.linspace(0, nyq, nfreqs)
+  double nyq;
+  double rnyq;     // fl(1 / nyq)
+  double b;        // fl(-(numtaps - 1) / 2 * pi)
+  double step_f;   // (fs // 2) / (n - 1)         : np.linspace(0, fs // 2, n)
+  double f_stop;
+  __device__ __forceinline__ double fgrid(int64_t i) const { return i == n - 1 ? f_stop : __dmul_rn((double)i, step_f); }
+  __device__ __forceinline__ double2 at(int bidx, int64_t k) const {
+    const int64_t half = nf / 2;
+    const bool mirror = k > half;
+    const int64_t kk = mirror ? nf - k : k;
+    const double x = kk == half ? nyq : __dmul_rn((double)kk, step_x);
+    // np.interp(x, freq, gain)
+    const double* g = gain + (size_t)bidx * ld;
+    int64_t j = (int64_t)floor(x / step_f);
+    j = max((int64_t)0, min(j, n - 1));
+    while (j > 0 && fgrid(j) > x) --j;
+    while (j < n - 1 && fgrid(j + 1) <= x) ++j;
+    double fx;
+    if (j == n - 1) {
+      fx = g[j];
+    } else {
+      const double fj = fgrid(j);
+      if (fj == x) {
+        fx = g[j];
+      } else {
+        const double slope = __ddiv_rn(g[j + 1] - g[j], fgrid(j + 1) - fj);
+        fx = __dadd_rn(__dmul_rn(slope, x - fj), g[j]);
+      }
+    }
+    const double ang = __dmul_rn(__dmul_rn(b, x), rnyq);
+    double sn, cs;
+    sincos(ang, &sn, &cs);
+    double2 v = make_double2(fx * cs, fx * sn);
+    if (kk == 0 || kk == half) v.y = 0.0;  // c2r transforms ignore these imaginary parts
+    if (mirror) v.y = -v.y;
+    return v;
+  }
+};
+
+struct RowInvFirwin {  // row DIT whose input is synthesised from the gain curve
+  FirwinSpec spec;
+  double2* ws;
+  const double2* tw;
+  int64_t N;
+  int N1, N2;
+  const int* perm1;
+  const int* perm2;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int row = t * TILE + c;
+    if (row >= N1) return make_double2(0.0, 0.0);
+    return spec.at(b, (int64_t)perm1[row] + (int64_t)N1 * perm2[e]);
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int row = t * TILE + c;
+    if (row >= N1) return;
+    const size_t idx = (size_t)row * N2 + e;
+    ws[(size_t)b * N + idx] = cmul(v, cconj(tw[idx]));
+  }
+};
+
+// column DIT -> real output row, scaled and windowed:  out[b, m] = Re(v) * scale * win[m]  (m < keep)
+struct ColInvReal {
+  const double2* ws;
+  int64_t N;
+  int N2;
+  double* out;
+  int64_t ld, keep;
+  const double* win;  // may be nullptr
+  double scale;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return make_double2(0.0, 0.0);
+    return ws[(size_t)b * N + (size_t)e * N2 + n2];
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int n2 = t * TILE + c;
+    const int64_t m = (int64_t)e * N2 + n2;
+    if (n2 >= N2 || m >= keep) return;
+    double r = v.x * scale;
+    if (win) r *= win[m];
+    out[(size_t)b * ld + m] = r;
+  }
+};
+
+struct AbsOp {  // |X| in position order
+  double* mag;
+  int64_t N;
+  __device__ __forceinline__ void operator()(int b, size_t pos, int64_t, double2 v) const {
+    mag[(size_t)b * N + pos] = hypot(v.x, v.y);
+  }
+};
+
+struct ExpOp {  // exp(X) in position order, in place
+  double2* ws;
+  int64_t N;
+  __device__ __forceinline__ void operator()(int b, size_t pos, int64_t, double2 v) const {
+    double s, c;
+    sincos(v.y, &s, &c);
+    const double m = exp(v.x);
+    ws[(size_t)b * N + pos] = make_double2(m * c, m * s);
+  }
+};
+
+__global__ void __launch_bounds__(256) k_min_positive(const double* __restrict__ mag, int64_t N, double* __restrict__ out) {
+  const int b = blockIdx.x;
+  const double* m = mag + (size_t)b * N;
+  double v = INFINITY;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    const double t = m[i];
+    if (t > 0.0) v = fmin(v, t);
+  }
+  for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) v = fmin(v, sm[w]);
+    out[b] = v;
+  }
+}
+
+struct RowInvLogMag {  // load 0.5*log(|X| + 1e-7*minpos) as a real spectrum (position order)
+  const double* mag;
+  const double* minpos;
+  double2* ws;
+  const double2* tw;
+  int64_t N;
+  int N1, N2;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int row = t * TILE + c;
+    if (row >= N1) return make_double2(0.0, 0.0);
+    const double v = mag[(size_t)b * N + (size_t)row * N2 + e] + 1e-7 * minpos[b];
+    return make_double2(0.5 * log(v), 0.0);
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int row = t * TILE + c;
+    if (row >= N1) return;
+    const size_t idx = (size_t)row * N2 + e;
+    ws[(size_t)b * N + idx] = cmul(v, cconj(tw[idx]));
+  }
+};
+
+// homomorphic window  lmin[n] = 2u[n] - d[n]
+__global__ void k_homomorphic_window(double* __restrict__ w, int64_t n_fft) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_fft) return;
+  const int64_t stop = n_fft / 2;
+  double v = 0.0;
+  if (i == 0) v = 1.0;
+  else if (i < stop) v = 2.0;
+  else if (i == stop) v = 1.0 + (double)(n_fft % 2);
+  w[i] = v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t impb_fft_create(impb_ctx* ctx, int64_t n, int32_t precision, impb_fft** out) {
+  if (!ctx || !out || n < 4 || precision != 64) {
+    set_error("impb_fft_create: bad argument (n=%lld, precision=%d; only 64 is implemented)", (long long)n, precision);
+    return IMPB_EINVAL;
+  }
+  DeviceGuard g(ctx->device);
+  Plan2D p;
+  if (!plan_2d(ctx, n, true, 8, &p)) {
+    set_error("impb_fft_create: length %lld is not a product of two 5-smooth factors that fit shared memory", (long long)n);
+    return IMPB_EUNSUPPORTED;
+  }
+  impb_fft* f = new impb_fft();
+  f->ctx = ctx;
+  f->n = n;
+  int rc = f->f.init(p);
+  if (rc) { delete f; return rc; }
+  *out = f;
+  return IMPB_OK;
+}
+
+void impb_fft_destroy(impb_fft* f) {
+  if (!f) return;
+  DeviceGuard g(f->ctx->device);
+  f->f.release();
+  delete f;
+}
+
+int64_t impb_fft_workspace_bytes(const impb_fft* f, int64_t batch) {
+  if (!f || batch < 1) return 0;
+  return batch * f->n * (int64_t)sizeof(double2);
+}
+
+int32_t impb_magnitude_db(impb_fft* f, const double* x, int64_t ld_x, double* mag_out, int64_t ld_out, int64_t batch,
+                          void* workspace, void* stream) {
+  if (!f || !x || !mag_out || !workspace || batch < 0 || ld_x < f->n) {
+    set_error("impb_magnitude_db: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0) return IMPB_OK;
+  DeviceGuard g(f->ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const Plan2D& p = f->f.p;
+  const int64_t half = (f->n + 1) / 2;
+  if (ld_out < half) { set_error("impb_magnitude_db: ld_out < ceil(n/2)"); return IMPB_EINVAL; }
+  double2* ws = (double2*)workspace;
+  for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+    const int nb = (int)std::min<int64_t>(32768, batch - b0);
+    RealColIn ci{x + (size_t)b0 * ld_x, ld_x, f->n, ws + (size_t)b0 * p.N, f->f.tw, p.N, p.N2};
+    int rc = f->f.col_fwd<TILE>(ci, nb, st);
+    if (rc) return rc;
+    RowFwdOp<MagDbOp> ro{ws + (size_t)b0 * p.N, p.N, p.N1, p.N2, f->f.perm_col, f->f.perm_row,
+                         MagDbOp{mag_out + (size_t)b0 * ld_out, ld_out, half}};
+    if ((rc = f->f.row_fwd<TILE>(ro, nb, st))) return rc;
+  }
+  return IMPB_OK;
+}
+
+int32_t impb_loglerp(impb_ctx* ctx, const double* logf_in, const double* y_in, int64_t n_in, int64_t ld_in,
+                     const double* logf_out, int64_t n_out, double* y_out, int64_t ld_out, int64_t batch, void* stream) {
+  if (!ctx || !logf_in || !y_in || !logf_out || !y_out || n_in < 2 || n_out < 0 || batch < 0 || ld_in < n_in ||
+      ld_out < n_out) {
+    set_error("impb_loglerp: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0 || n_out == 0) return IMPB_OK;
+  DeviceGuard g(ctx->device);
+  const int thr = 256;
+  const unsigned bx = (unsigned)std::min<int64_t>((n_out + thr - 1) / thr, 64);
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = (int)std::min<int64_t>(65535, batch - b0);
+    k_loglerp<<<dim3(bx, nb), thr, 0, (cudaStream_t)stream>>>(logf_in, y_in + (size_t)b0 * ld_in, n_in, ld_in, logf_out,
+                                                            n_out, y_out + (size_t)b0 * ld_out, ld_out);
+  }
+  IMPB_CUDA(cudaGetLastError());
+  return IMPB_OK;
+}
+
+int32_t impb_savgol_blend(impb_ctx* ctx, const double* y, int64_t n, int64_t ld, int32_t w_normal, int32_t it_normal,
+                          const double* coef_normal, const double* edge_normal, int32_t w_treble, int32_t it_treble,
+                          const double* coef_treble, const double* edge_treble, const double* k_treble, double* out,
+                          int64_t ld_out, int64_t batch, void* stream) {
+  if (!ctx || !y || !out || !k_treble || !coef_normal || !edge_normal || !coef_treble || !edge_treble || n < 1 ||
+      ld < n || ld_out < n || batch < 0 || w_normal < 3 || w_treble < 3 || !(w_normal & 1) || !(w_treble & 1) ||
+      it_normal < 0 || it_treble < 0) {
+    set_error("impb_savgol_blend: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (w_normal > n || w_treble > n) {
+    set_error("If mode is 'interp', window_length must be less than or equal to the size of x.");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0) return IMPB_OK;
+  const size_t smem = 3 * (size_t)n * sizeof(double);
+  if (smem > ctx->smem_optin) {
+    set_error("impb_savgol_blend: curve of %lld points does not fit shared memory", (long long)n);
+    return IMPB_EUNSUPPORTED;
+  }
+  DeviceGuard g(ctx->device);
+  IMPB_CUDA(cudaFuncSetAttribute(k_savgol_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_savgol_blend<<<(unsigned)batch, 256, smem, (cudaStream_t)stream>>>(y, (int)n, ld, w_normal, it_normal, coef_normal,
+                                                                      edge_normal, w_treble, it_treble, coef_treble,
+                                                                      edge_treble, k_treble, out, ld_out);
+  IMPB_CUDA(cudaGetLastError());
+  return IMPB_OK;
+}
+
+// ---- minimum phase ------------------------------------------------------------------------------------
+int32_t impb_minphase_create(impb_ctx* ctx, int64_t n, const double* hamming_host, impb_minphase** out) {
+  if (!ctx || !out || n < 4 || !hamming_host) {
+    set_error("impb_minphase_create: bad argument");
+    return IMPB_EINVAL;
+  }
+  DeviceGuard g(ctx->device);
+  impb_minphase* mp = new impb_minphase();
+  mp->ctx = ctx;
+  mp->n = n;
+  mp->numtaps = 2 * n;
+  int64_t pw = 1;
+  while (pw < mp->numtaps) pw <<= 1;
+  mp->nf = 2 * pw;  // nfreqs = 1 + 2^ceil(log2(numtaps));  irfft length = 2 (nfreqs - 1)
+  Plan2D pb, ps;
+  if (!plan_2d(ctx, mp->nf, true, 8, &pb) || !plan_2d(ctx, mp->numtaps, true, 8, &ps)) {
+    set_error("impb_minphase_create: no FFT plan for n=%lld (2n must be 5-smooth)", (long long)n);
+    delete mp;
+    return IMPB_EUNSUPPORTED;
+  }
+  int rc = mp->big.init(pb);
+  if (!rc) rc = mp->small.init(ps);
+  if (!rc) {
+    cudaError_t e = cudaMalloc(&mp->hamming, mp->numtaps * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(mp->hamming, hamming_host, mp->numtaps * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "hamming upload");
+  }
+  if (rc) { impb_minphase_destroy(mp); return rc; }
+  *out = mp;
+  return IMPB_OK;
+}
+
+void impb_minphase_destroy(impb_minphase* mp) {
+  if (!mp) return;
+  DeviceGuard g(mp->ctx->device);
+  mp->big.release();
+  mp->small.release();
+  cudaFree(mp->hamming);
+  delete mp;
+}
+
+static int64_t minphase_per_filter_bytes(const impb_minphase* mp) {
+  // complex nf | complex numtaps | real numtaps (h / cepstrum) | real numtaps (|H|) | window | minpos
+  return mp->nf * 16 + mp->numtaps * 16 + mp->numtaps * 8 + mp->numtaps * 8 + 8;
+}
+
+int64_t impb_minphase_workspace_bytes(const impb_minphase* mp, int64_t batch) {
+  if (!mp || batch < 1) return 0;
+  return std::min<int64_t>(batch, mp->chunk) * minphase_per_filter_bytes(mp) + mp->numtaps * 8 + 256;
+}
+
+int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_t ld_gain, int32_t fs, double* fir_out,
+                          int64_t ld_out, int64_t batch, void* workspace, void* stream) {
+  if (!mp || !gain || !fir_out || !workspace || batch < 0 || ld_gain < mp->n || ld_out < mp->n || fs < 2) {
+    set_error("impb_minphase_fir: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0) return IMPB_OK;
+  DeviceGuard g(mp->ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t cb = std::min<int64_t>(batch, mp->chunk);
+  char* w = (char*)workspace;
+  double2* ws_big = (double2*)w;            w += cb * mp->nf * 16;
+  double2* ws_small = (double2*)w;          w += cb * mp->numtaps * 16;
+  double* real_buf = (double*)w;            w += cb * mp->numtaps * 8;
+  double* mag = (double*)w;                 w += cb * mp->numtaps * 8;
+  double* minpos = (double*)w;              w += cb * 8;
+  w = (char*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
+  double* hwin = (double*)w;
+  const Plan2D& pb = mp->big.p;
+  const Plan2D& ps = mp->small.p;
+  const int64_t nt = mp->numtaps;
+  k_homomorphic_window<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(hwin, nt);
+  for (int64_t b0 = 0; b0 < batch; b0 += cb) {
+    const int nb = (int)std::min<int64_t>(cb, batch - b0);
+    int rc;
+    // 1. firwin2: h = irfft(fx * shift)[:numtaps] * hamming
+    const double nyq = 0.5 * (double)fs;
+    const int64_t nfreqs = mp->nf / 2 + 1;
+    FirwinSpec spec{gain + (size_t)b0 * ld_gain, ld_gain, mp->n, mp->nf, nyq / (double)(nfreqs - 1), nyq, 1.0 / nyq,
+                    (-(double)(nt - 1) / 2.0) * 3.141592653589793, (double)(fs / 2) / (double)(mp->n - 1),
+                    (double)(fs / 2)};
+    RowInvFirwin ri{spec, ws_big, mp->big.tw, pb.N, pb.N1, pb.N2, mp->big.perm_col, mp->big.perm_row};
+    if ((rc = mp->big.row_inv<TILE>(ri, nb, st))) return rc;
+    ColInvReal c1{ws_big, pb.N, pb.N2, real_buf, nt, nt, mp->hamming, 1.0 / (double)mp->nf};
+    if ((rc = mp->big.col_inv<TILE>(c1, nb, st))) return rc;
+    // 2. |fft(h, n_fft)|
+    RealColIn ci{real_buf, nt, nt, ws_small, mp->small.tw, ps.N, ps.N2};
+    if ((rc = mp->small.col_fwd<TILE>(ci, nb, st))) return rc;
+    RowFwdOp<AbsOp> ra{ws_small, ps.N, ps.N1, ps.N2, mp->small.perm_col, mp->small.perm_row, AbsOp{mag, ps.N}};
+    if ((rc = mp->small.row_fwd<TILE>(ra, nb, st))) return rc;
+    k_min_positive<<<nb, 256, 0, st>>>(mag, ps.N, minpos);
+    // 3. cepstrum = ifft(0.5 log(|H| + 1e-7 min+)).real * homomorphic window
+    RowInvLogMag rl{mag, minpos, ws_small, mp->small.tw, ps.N, ps.N1, ps.N2};
+    if ((rc = mp->small.row_inv<TILE>(rl, nb, st))) return rc;
+    ColInvReal c2{ws_small, ps.N, ps.N2, real_buf, nt, nt, hwin, 1.0 / (double)nt};
+    if ((rc = mp->small.col_inv<TILE>(c2, nb, st))) return rc;
+    // 4. h_min = ifft(exp(fft(cepstrum))).real[:n]
+    RealColIn ci2{real_buf, nt, nt, ws_small, mp->small.tw, ps.N, ps.N2};
+    if ((rc = mp->small.col_fwd<TILE>(ci2, nb, st))) return rc;
+    RowFwdOp<ExpOp> re{ws_small, ps.N, ps.N1, ps.N2, mp->small.perm_col, mp->small.perm_row, ExpOp{ws_small, ps.N}};
+    if ((rc = mp->small.row_fwd<TILE>(re, nb, st))) return rc;
+    RowPlain<double, TILE> rp{ws_small, ws_small, mp->small.tw, ps.N, ps.N1, ps.N2, 1, 0};
+    if ((rc = mp->small.row_inv<TILE>(rp, nb, st))) return rc;
+    ColInvReal c3{ws_small, ps.N, ps.N2, fir_out + (size_t)b0 * ld_out, ld_out, mp->n, nullptr, 1.0 / (double)nt};
+    if ((rc = mp->small.col_inv<TILE>(c3, nb, st))) return rc;
+  }
+  IMPB_CUDA(cudaGetLastError());
+  return IMPB_OK;
+}
+
+}  // extern "C"

@@ -178,8 +178,8 @@ static bool is_5smooth(int64_t n) {
 bool plan_2d(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, Plan2D* out) {
   const int tile = 64 / elem_bytes;
   const size_t cx = 2 * (size_t)elem_bytes;
-  const size_t smem_max = ctx->smem_optin ? ctx->smem_optin : (size_t)227 * 1024;
-  const size_t smem_two = (ctx->smem_per_sm ? ctx->smem_per_sm : (size_t)228 * 1024) / 2 - 1024;
+  const size_t smem_max = (ctx && ctx->smem_optin) ? ctx->smem_optin : (size_t)227 * 1024;
+  const size_t smem_two = ((ctx && ctx->smem_per_sm) ? ctx->smem_per_sm : (size_t)228 * 1024) / 2 - 1024;
   if (n_min < 4) return false;
 
   int force1 = 0, force2 = 0;
@@ -278,5 +278,22 @@ int32_t impb_ctx_create(int32_t device, impb_ctx** out) {
 }
 
 void impb_ctx_destroy(impb_ctx* ctx) { delete ctx; }
+
+int32_t impb_plan_probe(int64_t n_min, int32_t exact, int32_t elem_bytes, int64_t* n1, int64_t* n2,
+                        int32_t* radices_col, int32_t* radices_row) {
+  if ((elem_bytes != 8 && elem_bytes != 4) || n_min < 4) return IMPB_EINVAL;
+  impb::Plan2D p;
+  if (!impb::plan_2d(nullptr, n_min, exact != 0, elem_bytes, &p)) {
+    impb::set_error("no plan for n=%lld", (long long)n_min);
+    return IMPB_EUNSUPPORTED;
+  }
+  if (n1) *n1 = p.N1;
+  if (n2) *n2 = p.N2;
+  for (int s = 0; s < impb::MAX_STAGES; ++s) {
+    if (radices_col) radices_col[s] = s < p.col.nst ? p.col.radix[s] : 0;
+    if (radices_row) radices_row[s] = s < p.row.nst ? p.row.radix[s] : 0;
+  }
+  return IMPB_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,341 @@
+"""Thin torch-tensor wrappers over the C ABI (``include/impb.h``): one function per device entry point.
+
+Everything here takes and returns CUDA tensors and launches on the current torch stream of the tensor's
+device; nothing synchronises and nothing runs on the CPU.  Host-side numpy is only used to build the small
+constant tables the reference also builds on the host (window shapes, Savitzky-Golay coefficients).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import math
+import threading
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _i64(t):
+    torch = _torch()
+    assert t.dtype == torch.int64 and t.is_cuda and t.is_contiguous()
+    return t.data_ptr()
+
+
+def _dev(t):
+    return t.device.index if t.device.index is not None else 0
+
+
+def _stream(t):
+    return _lib.current_stream_ptr(t.device)
+
+
+def as_index_tensor(values, device):
+    torch = _torch()
+    if isinstance(values, torch.Tensor):
+        return values.to(device=device, dtype=torch.int64).contiguous()
+    return torch.as_tensor(np.asarray(values, dtype=np.int64), device=device)
+
+
+# ---- K2 -------------------------------------------------------------------------------------------
+def peak_index(x, offsets, lengths, height=0.12589, max_len=None):
+    """First-peak index of every segment ``x[offsets[r] : offsets[r]+lengths[r]]`` (relative to the segment)."""
+    torch = _torch()
+    x = x.contiguous()
+    assert x.dtype == torch.float64 and x.is_cuda
+    offsets = as_index_tensor(offsets, x.device)
+    lengths = as_index_tensor(lengths, x.device)
+    batch = offsets.numel()
+    out = torch.empty(batch, dtype=torch.int64, device=x.device)
+    if max_len is None:
+        max_len = int(lengths.max().item()) if batch else 0
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().impb_peak_index(_lib.context(_dev(x)).handle, x.data_ptr(), _i64(offsets), _i64(lengths),
+                                              float(height), out.data_ptr(), batch, int(max_len), _stream(x)),
+                   "impb_peak_index")
+    return out
+
+
+# ---- K4 -------------------------------------------------------------------------------------------
+def lundeby(x, offsets, lengths, fs, max_len=None):
+    """decay_params of every segment -> (peak, knee, noise_db, window) tensors (indices relative to the segment)."""
+    torch = _torch()
+    x = x.contiguous()
+    assert x.dtype == torch.float64 and x.is_cuda
+    offsets = as_index_tensor(offsets, x.device)
+    lengths = as_index_tensor(lengths, x.device)
+    batch = offsets.numel()
+    peak = torch.empty(batch, dtype=torch.int64, device=x.device)
+    knee = torch.empty_like(peak)
+    win = torch.empty_like(peak)
+    noise = torch.empty(batch, dtype=torch.float64, device=x.device)
+    if max_len is None:
+        max_len = int(lengths.max().item()) if batch else 0
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().impb_lundeby(_lib.context(_dev(x)).handle, x.data_ptr(), _i64(offsets), _i64(lengths),
+                                           int(fs), peak.data_ptr(), knee.data_ptr(), noise.data_ptr(), win.data_ptr(),
+                                           batch, int(max_len), _stream(x)), "impb_lundeby")
+    return peak, knee, noise, win
+
+
+# ---- K6 -------------------------------------------------------------------------------------------
+def xcorr_lag(x, a_offsets, a_lengths, b_offsets, b_lengths, max_seg_len=None):
+    torch = _torch()
+    x = x.contiguous()
+    a_offsets, a_lengths = as_index_tensor(a_offsets, x.device), as_index_tensor(a_lengths, x.device)
+    b_offsets, b_lengths = as_index_tensor(b_offsets, x.device), as_index_tensor(b_lengths, x.device)
+    batch = a_offsets.numel()
+    out = torch.empty(batch, dtype=torch.int64, device=x.device)
+    if max_seg_len is None:
+        max_seg_len = int(max(a_lengths.max().item(), b_lengths.max().item())) if batch else 0
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().impb_xcorr_lag(_lib.context(_dev(x)).handle, x.data_ptr(), _i64(a_offsets),
+                                             _i64(a_lengths), _i64(b_offsets), _i64(b_lengths), out.data_ptr(), batch,
+                                             int(max_seg_len), _stream(x)), "impb_xcorr_lag")
+    return out
+
+
+# ---- K3 + K5 + K7 + K16 ---------------------------------------------------------------------------
+def gather_window(src, src_start, out_len, shift=None, valid_lo=None, valid_hi=None, fade_in=None, fade_out=None,
+                  gain=1.0, out=None):
+    """dst[r, j] = gain * fade_out(j) * fade_in(j - shift) * src[src_start[r] + j - shift[r]] (0 outside valid)."""
+    torch = _torch()
+    src = src.contiguous()
+    assert src.dtype == torch.float64 and src.is_cuda
+    dev = src.device
+    src_start = as_index_tensor(src_start, dev)
+    batch = src_start.numel()
+    shift_t = None if shift is None else as_index_tensor(shift, dev)
+    lo_t = None if valid_lo is None else as_index_tensor(valid_lo, dev)
+    hi_t = None if valid_hi is None else as_index_tensor(valid_hi, dev)
+    fi = None if fade_in is None or len(fade_in) == 0 else torch.as_tensor(np.asarray(fade_in, np.float64), device=dev)
+    fo = None if fade_out is None or len(fade_out) == 0 else torch.as_tensor(np.asarray(fade_out, np.float64), device=dev)
+    if out is None:
+        out = torch.empty((batch, int(out_len)), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_gather_window(
+            _lib.context(_dev(src)).handle, src.data_ptr(), _i64(src_start),
+            None if shift_t is None else _i64(shift_t), None if lo_t is None else _i64(lo_t),
+            None if hi_t is None else _i64(hi_t), int(out_len),
+            None if fi is None else fi.data_ptr(), 0 if fi is None else fi.numel(),
+            None if fo is None else fo.data_ptr(), 0 if fo is None else fo.numel(),
+            float(gain), out.data_ptr(), out.stride(0) if batch > 1 else max(int(out_len), 1), batch, _stream(src)),
+            "impb_gather_window")
+    return out
+
+
+# ---- K8 -------------------------------------------------------------------------------------------
+class FftPlan:
+    """Exact-length transform plan used by ``magnitude_db``."""
+
+    def __init__(self, n: int, device: int = 0):
+        torch = _torch()
+        self.n, self.device = int(n), int(device)
+        self.ctx = _lib.context(self.device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().impb_fft_create(self.ctx.handle, self.n, 64, C.byref(h)), "impb_fft_create")
+        self.handle = h
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().impb_fft_destroy(self.handle)
+        except Exception:
+            pass
+
+    def workspace(self, batch):
+        torch = _torch()
+        need = _lib.lib().impb_fft_workspace_bytes(self.handle, int(batch))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+
+_plan_lock = threading.Lock()
+_fft_plans = {}
+_minphase_plans = {}
+
+
+def fft_plan(n, device=0) -> FftPlan:
+    with _plan_lock:
+        p = _fft_plans.get((n, device))
+        if p is None:
+            p = _fft_plans[(n, device)] = FftPlan(n, device)
+        return p
+
+
+def magnitude_db(x):
+    """20*log10(|rfft(x)|)[: ceil(n/2)] for every row of ``x`` ([batch, n] float64 CUDA)."""
+    torch = _torch()
+    if x.dim() == 1:
+        x = x[None, :]
+    x = x.contiguous()
+    batch, n = x.shape
+    plan = fft_plan(n, _dev(x))
+    half = (n + 1) // 2
+    out = torch.empty((batch, half), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = plan.workspace(batch)
+        _lib.check(_lib.lib().impb_magnitude_db(plan.handle, x.data_ptr(), n, out.data_ptr(), half, batch, ws.data_ptr(),
+                                                _stream(x)), "impb_magnitude_db")
+    return out
+
+
+# ---- K10 ------------------------------------------------------------------------------------------
+def loglerp(logf_in, y, logf_out):
+    """Piecewise-linear interpolation of rows of ``y`` from grid ``logf_in`` to ``logf_out`` (log10 Hz)."""
+    torch = _torch()
+    if y.dim() == 1:
+        y = y[None, :]
+    y = y.contiguous()
+    dev = y.device
+    lx = torch.as_tensor(np.asarray(logf_in, np.float64), device=dev) if not isinstance(logf_in, torch.Tensor) else logf_in
+    lo = torch.as_tensor(np.asarray(logf_out, np.float64), device=dev) if not isinstance(logf_out, torch.Tensor) else logf_out
+    batch, n_in = y.shape
+    out = torch.empty((batch, lo.numel()), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_loglerp(_lib.context(_dev(y)).handle, lx.data_ptr(), y.data_ptr(), n_in, n_in,
+                                           lo.data_ptr(), lo.numel(), out.data_ptr(), lo.numel(), batch, _stream(y)),
+                   "impb_loglerp")
+    return out
+
+
+# ---- K11 ------------------------------------------------------------------------------------------
+@functools.lru_cache(maxsize=64)
+def savgol_tables(window: int, order: int = 2):
+    """(conv coefficients [w], edge-fit matrix [w//2, w]) exactly as scipy builds them
+    (``savgol_coeffs`` least squares; ``np.polyfit`` on the first ``window`` samples)."""
+    half = window // 2
+    x = np.arange(-half, window - half, dtype=np.float64)[::-1]
+    A = x ** np.arange(order + 1, dtype=np.float64).reshape(-1, 1)
+    y = np.zeros(order + 1)
+    y[0] = 1.0
+    coef = np.linalg.lstsq(A, y, rcond=None)[0]
+    t = np.arange(window, dtype=np.float64)
+    V = np.vander(t, order + 1)
+    edge = np.vander(np.arange(half, dtype=np.float64), order + 1) @ np.linalg.pinv(V)
+    return np.ascontiguousarray(coef), np.ascontiguousarray(edge)
+
+
+_dev_tables = {}
+
+
+def _savgol_dev(window, device):
+    torch = _torch()
+    key = (window, str(device))
+    with _plan_lock:
+        t = _dev_tables.get(key)
+        if t is None:
+            c, e = savgol_tables(window)
+            t = _dev_tables[key] = (torch.as_tensor(c, device=device), torch.as_tensor(e, device=device))
+        return t
+
+
+def savgol_blend(y, w_normal, it_normal, w_treble, it_treble, k_treble):
+    """rows of y -> savgol^it_normal(y) * (1 - k) + savgol^it_treble(y) * k   (order 2, mode='interp')."""
+    torch = _torch()
+    if y.dim() == 1:
+        y = y[None, :]
+    y = y.contiguous()
+    dev = y.device
+    batch, n = y.shape
+    if w_normal > n or w_treble > n:
+        raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")
+    cn, en = _savgol_dev(int(w_normal), dev)
+    ct, et = _savgol_dev(int(w_treble), dev)
+    kt = k_treble if isinstance(k_treble, torch.Tensor) else torch.as_tensor(np.asarray(k_treble, np.float64), device=dev)
+    out = torch.empty_like(y)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_savgol_blend(_lib.context(_dev(y)).handle, y.data_ptr(), n, n, int(w_normal),
+                                                int(it_normal), cn.data_ptr(), en.data_ptr(), int(w_treble),
+                                                int(it_treble), ct.data_ptr(), et.data_ptr(), kt.data_ptr(),
+                                                out.data_ptr(), n, batch, _stream(y)), "impb_savgol_blend")
+    return out
+
+
+# ---- K12 + K13 ------------------------------------------------------------------------------------
+class MinPhasePlan:
+    def __init__(self, n: int, device: int = 0):
+        torch = _torch()
+        from scipy.signal import get_window
+        self.n, self.device = int(n), int(device)
+        self.ctx = _lib.context(self.device)
+        ham = np.ascontiguousarray(get_window('hamming', 2 * self.n, fftbins=False), dtype=np.float64)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().impb_minphase_create(self.ctx.handle, self.n, ham.ctypes.data, C.byref(h)),
+                       "impb_minphase_create")
+        self.handle = h
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().impb_minphase_destroy(self.handle)
+        except Exception:
+            pass
+
+    def workspace(self, batch):
+        torch = _torch()
+        need = _lib.lib().impb_minphase_workspace_bytes(self.handle, int(batch))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+
+def minphase_plan(n, device=0) -> MinPhasePlan:
+    with _plan_lock:
+        p = _minphase_plans.get((n, device))
+        if p is None:
+            p = _minphase_plans[(n, device)] = MinPhasePlan(n, device)
+        return p
+
+
+def minphase_fir(gain, fs):
+    """rows of linear gain on linspace(0, fs//2, n) (last = 0) -> n-tap minimum-phase FIRs."""
+    torch = _torch()
+    if gain.dim() == 1:
+        gain = gain[None, :]
+    gain = gain.contiguous()
+    batch, n = gain.shape
+    plan = minphase_plan(n, _dev(gain))
+    out = torch.empty_like(gain)
+    with torch.cuda.device(gain.device):
+        ws = plan.workspace(batch)
+        _lib.check(_lib.lib().impb_minphase_fir(plan.handle, gain.data_ptr(), n, int(fs), out.data_ptr(), n, batch, ws.data_ptr(),
+                                                _stream(gain)), "impb_minphase_fir")
+    return out
+
+
+# ---- K15 + K9 -------------------------------------------------------------------------------------
+def window_resample(x, taps, up, down, decay=None):
+    """resample_poly(x * decay_window, up, down, window=taps/up) for every row; taps already scaled by up."""
+    torch = _torch()
+    if x.dim() == 1:
+        x = x[None, :]
+    x = x.contiguous()
+    dev = x.device
+    batch, n = x.shape
+    g = math.gcd(int(up), int(down))
+    n_out = _lib.lib().impb_resample_out_len(n, int(up), int(down))
+    tp = None
+    if taps is not None:
+        tp = taps if isinstance(taps, torch.Tensor) else torch.as_tensor(np.asarray(taps, np.float64), device=dev)
+    dc = None
+    if decay is not None:
+        dc = decay if isinstance(decay, torch.Tensor) else torch.as_tensor(np.asarray(decay, np.float64), device=dev)
+        dc = dc.reshape(batch, 4).contiguous()
+    out = torch.empty((batch, n_out), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_window_resample(
+            _lib.context(_dev(x)).handle, x.data_ptr(), n, n, None if dc is None else dc.data_ptr(),
+            None if tp is None else tp.data_ptr(), 0 if tp is None else tp.numel(), int(up) // g, int(down) // g,
+            out.data_ptr(), n_out, batch, _stream(x)), "impb_window_resample")
+    return out

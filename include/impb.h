@@ -74,24 +74,25 @@ IMPB_API int32_t impb_deconv_launches_per_execute(const impb_plan* plan, int64_t
  * Replaces ImpulseResponse.peak_index(), core/impulse_response.py:32-70 and its twin
  * core/decay.py:12-41: m = max|x|; if m < 1e-20 -> start; first strict local maximum (plateau midpoint,
  * scipy _local_maxima_1d) of x/m or -x/m that is >= height; else argmax|x|.  Segment r is
- * x[offsets[r] : offsets[r] + lengths[r]]; peak_out[r] is relative to the segment start.  Bit-exact. */
+ * x[offsets[r] : offsets[r] + lengths[r]]; peak_out[r] is relative to the segment start; max_len = the
+ * longest segment (grid sizing only); height must be > 0.  Bit-exact. */
 IMPB_API int32_t impb_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,
-                        double height, int64_t* peak_out, int64_t batch, void* stream);
+                        double height, int64_t* peak_out, int64_t batch, int64_t max_len, void* stream);
 
 /* ---- K4: Lundeby decay parameters ----------------------------------------------------------------
  * Replaces decay.decay_params(), core/decay.py:44-260 (called by HRIR.crop_tails, core/hrir.py:627-636).
  * peak_out / knee_out are relative to the segment start. */
 IMPB_API int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths, int32_t fs,
                      int64_t* peak_out, int64_t* knee_out, double* noise_db_out, int64_t* win_out,
-                     int64_t batch, void* stream);
+                     int64_t batch, int64_t max_len, void* stream);
 
 /* ---- K6: onset cross-correlation lag ---------------------------------------------------------------
  * Replaces the scipy.signal.correlate(..., 'full') + argmax of HRIR.align_ipsilateral_all,
- * core/hrir.py:932-948.  a, b: [batch] segments given by offsets/lengths (zero-extended to seg_len);
- * lag_out[r] = argmax_k sum_n a[n+k] b[n] - (len-1) semantics of `lags[np.argmax(corr)]`. */
+ * core/hrir.py:932-948.  a, b: [batch] segments of x given by offsets/lengths (<= max_seg_len samples);
+ * lag_out[r] = np.arange(-len(a)+1, len(a))[np.argmax(correlate(a, b, 'full'))], first maximum on ties. */
 IMPB_API int32_t impb_xcorr_lag(impb_ctx* ctx, const double* x, const int64_t* a_offsets, const int64_t* a_lengths,
                        const int64_t* b_offsets, const int64_t* b_lengths, int64_t* lag_out, int64_t batch,
-                       void* stream);
+                       int64_t max_seg_len, void* stream);
 
 /* ---- K3+K5+K7+K16: fused gather / window --------------------------------------------------------------
  * Replaces the slicing, ImpulseResponse.shift (core/impulse_response.py:92-108), Hann fade-in of
@@ -100,12 +101,16 @@ IMPB_API int32_t impb_xcorr_lag(impb_ctx* ctx, const double* x, const int64_t* a
  *   dst[r, j] = gain * fade_out(j) * S(j),  j in [0, out_len)
  *   S(j)      = fade_in(j - shift[r]) * src[src_start[r] + j - shift[r]]   if valid_lo[r] <= j < valid_hi[r]
  *             = 0                                                            otherwise
- * fade_in(m) = hann(2*fade_in_len)[m] for m < fade_in_len (1 otherwise); fade_out is the second half of
- * hann(fade_out_len) laid over the last fade_out_len/2... samples exactly as np.concatenate([ones, win]). */
+ * fade_in: [fade_in_len] rising half window (hann(2*head)[:head], built by the host exactly as the
+ * reference does) applied to head-relative index m = j - shift; fade_out: [fade_out_len] falling half
+ * window laid over the last fade_out_len output samples.  shift / valid_lo / valid_hi may be NULL
+ * (no shift, everything valid).  Each factor is applied as a separately rounded multiply, in the
+ * reference's order, so results are bit-identical to numpy for identical src. */
 IMPB_API int32_t impb_gather_window(impb_ctx* ctx, const double* src, const int64_t* src_start, const int64_t* shift,
                            const int64_t* valid_lo, const int64_t* valid_hi, int64_t out_len,
-                           int64_t fade_in_len, int64_t fade_out_len, double gain, double* dst, int64_t ld_dst,
-                           int64_t batch, void* stream);
+                           const double* fade_in, int64_t fade_in_len, const double* fade_out,
+                           int64_t fade_out_len, double gain, double* dst, int64_t ld_dst, int64_t batch,
+                           void* stream);
 
 /* ---- generic batched complex FFT plan (used by K8 / K12 / K13 and the host-side shim) -------------- */
 IMPB_API int32_t impb_fft_create(impb_ctx* ctx, int64_t n, int32_t precision, impb_fft** out);
@@ -139,13 +144,16 @@ IMPB_API int32_t impb_savgol_blend(impb_ctx* ctx, const double* y, int64_t n, in
 /* ---- K12+K13: minimum-phase FIR ---------------------------------------------------------------------------
  * Replaces scipy firwin2 + minimum_phase(method='homomorphic', half=True) as called by
  * FrequencyResponse.minimum_phase_impulse_response, autoeq/frequency_response.py:672-680.
- * gain: [batch, n] linear amplitude on linspace(0, fs/2, n) (last sample 0); fir_out: [batch, n]. */
+ * gain: [batch, n] linear amplitude on linspace(0, fs//2, n) (last sample 0); fir_out: [batch, n].
+ * fs (even) only enters through the rounding of firwin2's phase ramp, which is reproduced bit for bit
+ * because the homomorphic log amplifies it ("min-phase tolerance"). */
 typedef struct impb_minphase impb_minphase;
-IMPB_API int32_t impb_minphase_create(impb_ctx* ctx, int64_t n, impb_minphase** out);
+/* hamming_host: scipy.signal.get_window('hamming', 2n, fftbins=False), [2n] doubles on the HOST */
+IMPB_API int32_t impb_minphase_create(impb_ctx* ctx, int64_t n, const double* hamming_host, impb_minphase** out);
 IMPB_API void impb_minphase_destroy(impb_minphase* mp);
 IMPB_API int64_t impb_minphase_workspace_bytes(const impb_minphase* mp, int64_t batch);
-IMPB_API int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_t ld_gain, double* fir_out, int64_t ld_out,
-                          int64_t batch, void* workspace, void* stream);
+IMPB_API int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_t ld_gain, int32_t fs, double* fir_out,
+                          int64_t ld_out, int64_t batch, void* workspace, void* stream);
 
 /* ---- K15+K9: decay window + polyphase resampling ------------------------------------------------------------
  * Replaces decay.apply_decay_window (core/decay.py:383-403) followed by ImpulseResponse.resample,
@@ -155,6 +163,16 @@ IMPB_API int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_
 IMPB_API int32_t impb_window_resample(impb_ctx* ctx, const double* src, int64_t ld_src, int64_t n, const double* decay,
                              const double* taps, int64_t ntaps, int32_t up, int32_t down, double* dst,
                              int64_t ld_dst, int64_t batch, void* stream);
+
+/* ceil(n * up / down) after reducing up/down by their gcd: the row length impb_window_resample writes */
+IMPB_API int64_t impb_resample_out_len(int64_t n, int32_t up, int32_t down);
+
+/* ---- planner introspection (host only, needs no device) -------------------------------------------------
+ * The N = n1 x n2 factorisation and radix sequences the library would use for a transform of at least
+ * (exact = 0) or exactly (exact = 1) n_min points with elem_bytes-wide reals (8 / 4).
+ * radices_col / radices_row: int32[6], zero-terminated. */
+IMPB_API int32_t impb_plan_probe(int64_t n_min, int32_t exact, int32_t elem_bytes, int64_t* n1, int64_t* n2,
+                        int32_t* radices_col, int32_t* radices_row);
 
 #ifdef __cplusplus
 }

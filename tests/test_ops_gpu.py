@@ -1,0 +1,257 @@
+"""K2..K13 parity: every device entry point against the CPU oracle (and through it the reference goldens)."""
+import numpy as np
+import pytest
+
+import impulcifer_oracle as O
+from _util import load, rel_peak_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _pack(arrs, T):
+    """list of 1-D arrays -> (flat CUDA tensor, offsets, lengths)"""
+    lens = np.array([len(a) for a in arrs], dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    flat = np.concatenate([np.asarray(a, np.float64) for a in arrs]) if len(arrs) else np.zeros(0)
+    return T.from_numpy(flat).cuda(), offs, lens
+
+
+def test_peak_index_edge_cases_bit_exact(T):
+    from impulcifer_pip313_b200 import ops
+    g = load('small_cases.npz')
+    keys = [k[3:-2] for k in g.files if k.startswith('pk_') and k.endswith('_x')]
+    arrs = [g[f'pk_{k}_x'] for k in keys]
+    flat, offs, lens = _pack(arrs, T)
+    got = ops.peak_index(flat, offs, lens).cpu().numpy()
+    want = [int(g[f'pk_{k}_idx']) for k in keys]
+    assert list(got) == want, dict(zip(keys, zip(got, want)))
+
+
+def test_peak_index_fuzz_bit_exact(T):
+    from impulcifer_pip313_b200 import ops
+    rng = np.random.default_rng(42)
+    arrs = []
+    for i in range(200):
+        n = int(rng.integers(3, 5000))
+        kind = i % 5
+        if kind == 0:
+            x = rng.standard_normal(n)
+        elif kind == 1:  # quantised -> many plateaus and ties
+            x = np.round(rng.standard_normal(n) * 3) / 3
+        elif kind == 2:  # decaying IR after a delay
+            d = int(rng.integers(0, n - 1))
+            x = np.zeros(n)
+            x[d:] = rng.standard_normal(n - d) * np.exp(-np.arange(n - d) / 50.0)
+        elif kind == 3:  # negative dominant
+            x = -np.abs(rng.standard_normal(n)) * np.hanning(n)
+        else:  # everything below threshold except a ramp
+            x = np.linspace(0, 1, n) * rng.choice([-1.0, 1.0])
+        arrs.append(x)
+    flat, offs, lens = _pack(arrs, T)
+    got = ops.peak_index(flat, offs, lens).cpu().numpy()
+    want = [O.peak_index(a) for a in arrs]
+    assert list(got) == want
+    # a different height
+    got2 = ops.peak_index(flat, offs, lens, height=0.5).cpu().numpy()
+    assert list(got2) == [O.peak_index(a, peak_height=0.5) for a in arrs]
+
+
+def test_lundeby_degenerate_and_golden(T):
+    from impulcifer_pip313_b200 import ops
+    g = load('small_cases.npz')
+    keys = [k[3:-2] for k in g.files if k.startswith('dc_') and k.endswith('_x')]
+    arrs = [g[f'dc_{k}_x'] for k in keys]
+    flat, offs, lens = _pack(arrs, T)
+    pk, knee, noise, win = [t.cpu().numpy() for t in ops.lundeby(flat, offs, lens, 48000)]
+    for i, k in enumerate(keys):
+        ref = g[f'dc_{k}_out']
+        assert (pk[i], knee[i], win[i]) == (int(ref[0]), int(ref[1]), int(ref[3])), k
+        assert abs(noise[i] - ref[2]) < 1e-9, k
+
+
+def test_lundeby_fuzz(T):
+    from impulcifer_pip313_b200 import ops
+    rng = np.random.default_rng(9)
+    fs = 48000
+    arrs = []
+    for i in range(48):
+        n = int(rng.integers(5000, 150000))
+        d = int(rng.integers(10, 4000))
+        rt = rng.uniform(0.05, 0.9)
+        x = np.zeros(n)
+        m = n - d
+        x[d:] = rng.standard_normal(m) * 10 ** (-3 * np.arange(m) / (fs * rt))
+        x[d] = 2.0
+        x += 10 ** rng.uniform(-6, -3) * rng.standard_normal(n)
+        arrs.append(x)
+    flat, offs, lens = _pack(arrs, T)
+    pk, knee, noise, win = [t.cpu().numpy() for t in ops.lundeby(flat, offs, lens, fs)]
+    for i, a in enumerate(arrs):
+        rp, rk, rn, rw = O.decay_params(a, fs)
+        assert (pk[i], knee[i], win[i]) == (rp, rk, rw), i
+        assert abs(noise[i] - rn) < 1e-9
+
+
+def test_xcorr_lag(T):
+    from impulcifer_pip313_b200 import ops
+    rng = np.random.default_rng(2)
+    pairs = []
+    for i in range(40):
+        n = 1440 if i % 3 else int(rng.integers(20, 1440))
+        base = rng.standard_normal(n + 200) * np.exp(-np.arange(n + 200) / 150.0)
+        s = int(rng.integers(-60, 60))
+        a = base[100:100 + n] + 0.01 * rng.standard_normal(n)
+        b = base[100 + s:100 + s + n] + 0.01 * rng.standard_normal(n)
+        pairs.append((a, b))
+    flat, offs, lens = _pack([p[0] for p in pairs] + [p[1] for p in pairs], T)
+    k = len(pairs)
+    got = ops.xcorr_lag(flat, offs[:k], lens[:k], offs[k:], lens[k:]).cpu().numpy()
+    want = [O.xcorr_lag(a, b) for a, b in pairs]
+    assert list(got) == want
+
+
+def test_gather_window_matches_reference_sequence(T):
+    """crop_heads slice + fade-in, two shifts, crop_tails slice + fade-out, gain — bit-exact vs numpy."""
+    from impulcifer_pip313_b200 import ops
+    rng = np.random.default_rng(3)
+    fs = 48000
+    head = 48
+    fade_in = O.hann(2 * head)[:head]
+    fo_len = 1892
+    fade_out = O.hann(fo_len)[fo_len // 2:]
+    L = 60000
+    src = rng.standard_normal((6, L))
+    crops = np.array([100, 0, 2500, 31, 17, 999])
+    shifts1 = [0, 5, -7, 12, -3, 0]
+    shifts2 = [0, -9, 4, 3, -20, 11]
+    tail = 21600
+    want = []
+    los, his, tot = [], [], []
+    for r in range(6):
+        d = src[r, crops[r]:].copy()
+        d[:head] *= fade_in
+        n = len(d)
+        d = O.shift(d, shifts1[r])
+        d = O.shift(d, shifts2[r])
+        d = d[:tail].copy()
+        d *= np.concatenate([np.ones(len(d) - len(fade_out)), fade_out])
+        d *= 0.731
+        want.append(d)
+        # composite shift and the surviving index range (host-side bookkeeping, as in the shim)
+        lo, hi, s = 0, n, 0
+        for sft in (shifts1[r], shifts2[r]):
+            lo, hi = max(lo + sft, 0), min(hi + sft, n)
+            s += sft
+        los.append(lo), his.append(min(hi, tail)), tot.append(s)
+    flat = T.from_numpy(src.reshape(-1)).cuda()
+    starts = np.arange(6) * L + crops
+    got = ops.gather_window(flat, starts, tail, shift=tot, valid_lo=los, valid_hi=his, fade_in=fade_in,
+                            fade_out=fade_out, gain=0.731).cpu().numpy()
+    assert np.array_equal(got, np.stack(want))
+
+
+@pytest.mark.parametrize("n", [21600, 22500, 57600, 96000, 4096, 1000])
+def test_magnitude_db(T, n):
+    from impulcifer_pip313_b200 import ops
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((3, n)) * np.exp(-np.arange(n) / (n / 8.0))
+    got = ops.magnitude_db(T.from_numpy(x).cuda()).cpu().numpy()
+    for r in range(3):
+        f, m = O.magnitude_response(x[r], 48000)
+        assert got[r].shape == m.shape
+        assert np.max(np.abs(got[r] - m)) < 1e-8
+
+
+def test_frequency_response_chain_golden(T):
+    """magnitude -> decimate -> log-f lerp onto the 783-point grid == reference frequency_response()."""
+    from impulcifer_pip313_b200 import ops
+    g = load('synth71_golden.npz')
+    gold = load('demo_room_golden.npz')
+    ir = gold['fc_left']
+    fs = 48000
+    mag = ops.magnitude_db(T.from_numpy(ir).cuda())
+    n = len(ir)
+    half = (n + 1) // 2
+    f = np.arange(half) * (fs / n)
+    step = int(round(len(f) / ((fs / 2) / 4.0))) or 1
+    grid = O.generate_frequencies(10, fs / 2, 1.01)
+    fd = f[1::step]
+    md = mag[:, 1::step].contiguous()
+    got = ops.loglerp(np.log10(fd), md, np.log10(grid)).cpu().numpy()[0]
+    assert np.array_equal(grid, gold['fc_fr_frequency'])
+    assert np.max(np.abs(got - gold['fc_fr_raw'])) < 1e-8
+    del g
+
+
+def test_savgol_blend_golden(T):
+    from impulcifer_pip313_b200 import ops
+    g = load('synth71_golden.npz')
+    f = g['fr_frequency']
+    raw = T.from_numpy(g['fr_raw']).cuda()
+    k = O.sigmoid(f, 100.0, 10000.0)
+    w = O.window_size(f, 1 / 3)
+    got = ops.savgol_blend(raw, w, 1, w, 1, k).cpu().numpy()
+    assert np.max(np.abs(got - g['fr_smoothed'])) < 1e-9
+    # custom: 2-octave x2 normal, 1/12-octave x3 treble, 2k..12k transition
+    k2 = O.sigmoid(f, 2000.0, 12000.0)
+    got2 = ops.savgol_blend(raw, O.window_size(f, 2), 2, O.window_size(f, 1 / 12), 3, k2).cpu().numpy()
+    assert np.max(np.abs(got2 - g['fr_custom'])) < 1e-9
+    # window larger than the curve is rejected like scipy does
+    with pytest.raises(ValueError):
+        ops.savgol_blend(raw[:, :50].contiguous(), 99, 1, 7, 1, k[:50])
+
+
+def test_minphase_fir_golden(T):
+    from impulcifer_pip313_b200 import ops
+    g = load('synth71_golden.npz')
+    f = g['fr_frequency']
+    fs = 48000
+    gains5, gains10 = [], []
+    for i in range(len(g['fr_names'])):
+        eq = -(g['fr_smoothed'][i] - np.mean(g['fr_smoothed'][i]))
+        gains5.append(O.minphase_grid(f, eq, fs, 5, False)[1])
+        gains10.append(O.minphase_grid(f, eq, fs, 10, True)[1])
+    got5 = ops.minphase_fir(T.from_numpy(np.stack(gains5)).cuda(), fs).cpu().numpy()
+    got10 = ops.minphase_fir(T.from_numpy(np.stack(gains10)).cuda(), fs).cpu().numpy()
+    assert got5.shape == (4, 9600) and got10.shape == (4, 4800)
+    for i in range(4):
+        # tolerance: see DESIGN.md "min-phase tolerance" (log of rounding noise at the type-II Nyquist null)
+        assert rel_peak_err(got5[i], g['minphase_f5'][i]) < 5e-6
+        assert rel_peak_err(got10[i], g['minphase_f10'][i]) < 5e-6
+        # magnitude response of the FIR (what the EQ stage actually relies on) is tight
+        H_ref = np.abs(np.fft.rfft(g['minphase_f5'][i]))
+        H_got = np.abs(np.fft.rfft(got5[i]))
+        # ... everywhere except the Nyquist end, where the reference itself takes the log of rounding noise
+        assert np.max(np.abs(H_got - H_ref)[:-8]) / np.max(H_ref) < 1e-7
+        assert np.max(np.abs(H_got - H_ref)) / np.max(H_ref) < 5e-5
+
+
+def test_resample_matches_port(T):
+    from impulcifer_pip313_b200 import ops
+    g = load('synth71_golden.npz')
+    ir = g['final_FL_left']
+    up, down, taps = O.resample_filter(44100, 48000)
+    got = ops.window_resample(T.from_numpy(ir).cuda(), taps * up, up, down).cpu().numpy()[0]
+    ref = g['resampled_FL_left_44100']
+    assert got.shape == ref.shape
+    assert rel_peak_err(got, ref) < 1e-12
+    # 4:1 decimation (192 kHz -> 48 kHz config) on a short signal
+    x = np.random.default_rng(0).standard_normal(20000)
+    up, down, taps = O.resample_filter(48000, 192000)
+    got = ops.window_resample(T.from_numpy(x).cuda(), taps * up, up, down).cpu().numpy()[0]
+    ref = O.resample(x, 48000, 192000)
+    assert got.shape == ref.shape and rel_peak_err(got, ref) < 1e-12
+    # decay window fused in front
+    params = (100.0, 3000.0, 3100.0, -12.0)
+    ref = O.resample(O.apply_decay_window(x.copy(), (100, 3000, 3100, -12.0)), 44100, 48000)
+    up, down, taps = O.resample_filter(44100, 48000)
+    got = ops.window_resample(T.from_numpy(x).cuda(), taps * up, up, down, decay=np.array(params)).cpu().numpy()[0]
+    assert rel_peak_err(got, ref) < 1e-12
