@@ -39,6 +39,7 @@ template <typename T> struct DeconvArgs {
   int N1, N2;
   // input
   const void* rec;
+  const int64_t* in_offsets;  // optional: start of row r inside rec (else r * ld_in)
   int64_t ld_in, len, nrows, row0;
   int in_fmt;
   // output
@@ -63,8 +64,13 @@ template <typename T, int TILE> struct DeconvColIn {
     const int64_t n = (int64_t)e * a.N2 + n2;
     if (n2 >= a.N2 || n >= a.len) return mkc<T>(0, 0);
     const int64_t ra = a.row0 + 2 * (int64_t)b, rb = ra + 1;
-    const T re = (T)load_sample(a.rec, a.in_fmt, ra * a.ld_in + n);
-    const T im = rb < a.nrows ? (T)load_sample(a.rec, a.in_fmt, rb * a.ld_in + n) : (T)0;
+    const int64_t oa = a.in_offsets ? __ldg(a.in_offsets + ra) : ra * a.ld_in;
+    const T re = (T)load_sample(a.rec, a.in_fmt, oa + n);
+    T im = (T)0;
+    if (rb < a.nrows) {
+      const int64_t ob = a.in_offsets ? __ldg(a.in_offsets + rb) : rb * a.ld_in;
+      im = (T)load_sample(a.rec, a.in_fmt, ob + n);
+    }
     return mkc<T>(re, im);
   }
   __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v) const {
@@ -370,10 +376,11 @@ int32_t impb_deconv_launches_per_execute(const impb_plan* pl, int64_t batch) {
   return (int32_t)(3 * ((pairs + pl->chunk_pairs - 1) / pl->chunk_pairs));
 }
 
-int32_t impb_deconv_execute(impb_plan* pl, const void* rec, int64_t ld_in, int32_t in_fmt, int64_t len, void* out,
-                            int64_t ld_out, int32_t out_f64, int64_t out_offset, int64_t out_len, int64_t batch,
-                            void* workspace, void* stream) {
-  if (!pl || !rec || !out || !workspace || batch < 0 || len < 0 || len > pl->L || ld_in < len || out_offset < 0 ||
+int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_offsets, int64_t ld_in, int32_t in_fmt,
+                            int64_t len, void* out, int64_t ld_out, int32_t out_f64, int64_t out_offset, int64_t out_len,
+                            int64_t batch, void* workspace, void* stream) {
+  if (!pl || !rec || !out || !workspace || batch < 0 || len < 0 || len > pl->L || (!in_offsets && ld_in < len) ||
+      out_offset < 0 ||
       out_len < 0 || out_offset + out_len > len || ld_out < out_len || in_fmt < 0 || in_fmt > 2) {
     set_error("impb_deconv_execute: bad argument (len=%lld L=%lld out_offset=%lld out_len=%lld)", (long long)len,
               pl ? (long long)pl->L : 0LL, (long long)out_offset, (long long)out_len);
@@ -391,7 +398,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, int64_t ld_in, int32
       const Plan2D& p = pl->e64.fft.p;
       a.ws = (double2*)workspace; a.tw = pl->e64.fft.tw; a.hs = pl->e64.hs;
       a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
-      a.rec = rec; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
+      a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = 1;
       rc = pl->e64.launch(a, np, st);
     } else {
@@ -399,7 +406,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, int64_t ld_in, int32
       const Plan2D& p = pl->e32.fft.p;
       a.ws = (float2*)workspace; a.tw = pl->e32.fft.tw; a.hs = pl->e32.hs;
       a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
-      a.rec = rec; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
+      a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = out_f64 ? 1 : 0;
       rc = pl->e32.launch(a, np, st);
     }

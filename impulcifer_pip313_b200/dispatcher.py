@@ -1,0 +1,327 @@
+"""GPU batch dispatcher — the replacement for the reference's process / thread pools
+(``core/parallel_utils.py:97-152``, ``core/parallel_processing.py:84-190``, ``core/parallel_workers.py:24-131``).
+
+The reference maps a Python worker over (speaker, side) items.  Here every item of MANY recording sets is a
+row of one launch:
+
+  ``BatchDispatcher.process``       deconvolution -> crop_heads -> align_ipsilateral_all ->
+                                    align_onset_groups_peak_leftref -> crop_tails  for S recording sets at once
+  ``BatchDispatcher.postprocess``   frequency_response -> smoothen_fractional_octave -> minimum-phase FIR
+                                    (the arithmetic of ``process_equalization_worker``) for every row
+  ``DeviceShard``                   which recording sets a rank owns (sets never split across GPUs) and the
+                                    final result gather; no collective on the compute path.
+
+Integer decisions (crop indices, lags, shifts) are taken with torch integer ops on the device, so a batch
+needs ONE host synchronisation: reading the knee indices that fix each set's output length.
+"""
+from __future__ import annotations
+
+import threading
+import warnings
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import ops
+from .constants import IPSILATERAL_PAIRS, ONSET_GROUPS, SPEAKER_DELAYS, speaker_side
+from .frequency_response import minimum_phase_batch, next_fast_len, smoothen_batch
+from .hrir import ingest_layout
+from .impulse_response import frequency_response_batch
+
+_conv_lock = threading.Lock()
+_conv_plans = {}
+
+
+def fft_convolve_full(x, fir):
+    """``scipy.signal.convolve(x_row, fir, 'full')`` for every row of ``x`` (CUDA [B, n]) -> CUDA [B, n+m-1]
+    (``ImpulseResponse.equalize``, reference core/impulse_response.py:110-119; next-row component)."""
+    import torch
+    from .estimator import DeconvPlan
+    fir = np.ascontiguousarray(fir, dtype=np.float64)
+    n, m = x.shape[1], len(fir)
+    total = n + m - 1
+    s = (m - 1) // 2
+    key = (fir.tobytes(), total, x.device.index)
+    with _conv_lock:
+        plan = _conv_plans.get(key)
+        if plan is None:
+            if len(_conv_plans) > 64:
+                _conv_plans.clear()
+            plan = _conv_plans[key] = DeconvPlan(fir, total, 64, x.device.index or 0)
+    padded = torch.zeros((x.shape[0], total), dtype=torch.float64, device=x.device)
+    padded[:, s:s + n] = x
+    return plan.execute(padded)
+
+
+@dataclass
+class SetResult:
+    """Cropped responses of one recording set, in the reference's estimation order."""
+    names: list            # ["FL-left", "FL-right", ...]
+    data: object           # CUDA tensor [n_irs, tail_ind]
+    tail_ind: int
+    peaks: np.ndarray      # raw-estimate peak index per IR
+    crop: np.ndarray       # head crop index per IR
+    knees: np.ndarray      # Lundeby knee index per IR (after alignment)
+    warnings: list = field(default_factory=list)
+
+    def as_dict(self):
+        out = {}
+        host = self.data.cpu().numpy()
+        for name, row in zip(self.names, host):
+            spk, side = name.split('-')
+            out.setdefault(spk, {})[side] = row
+        return out
+
+
+class BatchDispatcher:
+    def __init__(self, estimator, speakers, side=None, silence_length=2.0, head_ms=1, segment_ms=30):
+        self.estimator = estimator
+        self.speakers = list(speakers)
+        self.side = side
+        self.silence_length = silence_length
+        self.head_ms = head_ms
+        self.segment_ms = segment_ms
+        self.fs = estimator.fs
+        self._layout = None
+        self.launches = 0
+
+    # ---- static layout of one set ---------------------------------------------------------------------
+    def _prepare(self, n_tracks, n_samples, device):
+        import torch
+        key = (n_tracks, n_samples, str(device))
+        if self._layout is not None and self._layout['key'] == key:
+            return self._layout
+        fs = self.fs
+        columns, plan = ingest_layout(n_tracks, n_samples, self.speakers, len(self.estimator), fs, self.side,
+                                      self.silence_length)
+        lengths = {columns[c][1] - columns[c][0] for _, _, _, c in plan}
+        if len(lengths) != 1:
+            raise ValueError("BatchDispatcher needs full-length columns; use HRIR.open_recording for clipped files")
+        L = lengths.pop()
+        names = [f"{spk}-{sd}" for spk, sd, _, _ in plan]
+        row_of = {nm: i for i, nm in enumerate(names)}
+        offs = np.array([trk * n_samples + columns[c][0] for _, _, trk, c in plan], dtype=np.int64)
+        spk_list = []
+        for spk, _, _, _ in plan:
+            if spk not in spk_list:
+                spk_list.append(spk)
+        paired = self.side is None
+        lay = dict(key=key, L=L, names=names, row_of=row_of, n=len(plan), speakers=spk_list, paired=paired,
+                   offs=torch.as_tensor(offs, device=device))
+        if paired:
+            left = np.array([row_of[f"{s}-left"] for s in spk_list])
+            right = np.array([row_of[f"{s}-right"] for s in spk_list])
+            lay['left'] = torch.as_tensor(left, device=device)
+            lay['right'] = torch.as_tensor(right, device=device)
+            head = int(self.head_ms * fs / 1000)
+            lay['delay'] = torch.as_tensor([int(np.round(SPEAKER_DELAYS[s] * fs)) + head for s in spk_list],
+                                           device=device)
+            lay['side_code'] = [speaker_side(s) for s in spk_list]
+            # ipsilateral pairs present in this layout, in the reference's order
+            pairs = [(a, b) for a, b in IPSILATERAL_PAIRS if a in spk_list and b in spk_list]
+            lay['pairs'] = pairs
+            lay['pa'] = torch.as_tensor([row_of[f"{a}-left"] for a, _ in pairs], device=device)
+            lay['pb'] = torch.as_tensor([row_of[f"{b}-right"] for _, b in pairs], device=device)
+            groups = [g for g in ONSET_GROUPS if g[0] in spk_list]
+            lay['groups'] = groups
+            lay['gl'] = torch.as_tensor([row_of[f"{g[0]}-left"] for g in groups], device=device)
+        self._layout = lay
+        return lay
+
+    # ---- the batched crop / align pipeline ------------------------------------------------------------------
+    def process(self, recordings, precision=None):
+        """recordings: CUDA tensor [S, n_tracks, n_samples] (float64, float32 or int32 PCM).
+        Returns a list of ``SetResult`` (one per recording set)."""
+        import torch
+        from scipy.signal.windows import hann
+        if recordings.dim() == 2:
+            recordings = recordings[None]
+        S, n_tracks, n_samples = recordings.shape
+        dev = recordings.device
+        lay = self._prepare(n_tracks, n_samples, dev)
+        if not lay['paired']:
+            raise ValueError("BatchDispatcher.process handles binaural (two tracks per speaker) sets")
+        est, fs, L, n = self.estimator, self.fs, lay['L'], lay['n']
+        B = S * n
+        head = int(self.head_ms * fs / 1000)
+        launches = 0
+        with torch.cuda.device(dev):
+            set_base = torch.arange(S, device=dev, dtype=torch.int64)[:, None]
+            # 1. deconvolution of every column of every set (K1)
+            row_offs = (set_base * (n_tracks * n_samples) + lay['offs'][None, :]).reshape(-1)
+            plan = est.plan(L, precision)
+            E = plan.execute(recordings.reshape(-1), length=L, row_offsets=row_offs)
+            if E.dtype != torch.float64:
+                E = E.to(torch.float64)
+            launches += plan.launches(B)
+            flatE = E.reshape(-1)
+            rows = torch.arange(B, device=dev, dtype=torch.int64)
+            full = torch.full((B,), L, device=dev, dtype=torch.int64)
+            # 2. first peaks (K2) and the pairwise head crop (ref core/hrir.py:573-606), integer ops on device
+            peaks = ops.peak_index(flatE, rows * L, full, max_len=L)
+            launches += 4
+            pk = peaks.view(S, n)
+            pl, pr = pk[:, lay['left']], pk[:, lay['right']]
+            first = torch.where(pl < pr, pl, pr)
+            crop_sp = torch.clamp(first - lay['delay'][None, :], min=0)
+            crop = torch.zeros((S, n), device=dev, dtype=torch.int64)
+            crop[:, lay['left']] = crop_sp
+            crop[:, lay['right']] = crop_sp
+            crop = crop.reshape(-1)
+            n1 = L - crop
+            window_in = hann(head * 2)[:head]
+            X1 = ops.gather_window(flatE, rows * L + crop, L, valid_hi=n1, fade_in=window_in)
+            launches += 1
+            del E, flatE
+            flat1 = X1.reshape(-1)
+            # 3. ipsilateral onset alignment (ref :921-955): lag of the first 30 ms, K6
+            seg = int(fs * self.segment_ms / 1000)
+            shift = torch.zeros((S, n), device=dev, dtype=torch.int64)
+            if len(lay['pairs']):
+                n1v = n1.view(S, n)
+                ra = (set_base * n + lay['pa'][None, :]).reshape(-1)
+                rb = (set_base * n + lay['pb'][None, :]).reshape(-1)
+                la = torch.clamp(n1v[:, lay['pa']], max=seg).reshape(-1)
+                lb = torch.clamp(n1v[:, lay['pb']], max=seg).reshape(-1)
+                lags = ops.xcorr_lag(flat1, ra * L, la, rb * L, lb, max_seg_len=seg).view(S, -1)
+                launches += 1
+                for k, (a, b) in enumerate(lay['pairs']):
+                    lag = lags[:, k]
+                    pos, neg = torch.clamp(lag, min=0), torch.clamp(-lag, min=0)
+                    if a == b:
+                        shift[:, lay['row_of'][f"{a}-right"]] += pos
+                        shift[:, lay['row_of'][f"{a}-left"]] += neg
+                    else:
+                        for sd in ('left', 'right'):
+                            shift[:, lay['row_of'][f"{b}-{sd}"]] += pos
+                            shift[:, lay['row_of'][f"{a}-{sd}"]] += neg
+            X2 = self._shift(flat1, rows, L, n1, shift.reshape(-1))
+            launches += 1
+            del X1, flat1
+            flat2 = X2.reshape(-1)
+            # 4. group onset alignment against FL-left (ref :957-1001), K2 on the group leaders
+            shift2 = torch.zeros((S, n), device=dev, dtype=torch.int64)
+            if 'FL' in lay['speakers'] and len(lay['groups']) > 1:
+                rg = (set_base * n + lay['gl'][None, :]).reshape(-1)
+                gp = ops.peak_index(flat2, rg * L, n1[rg], max_len=L).view(S, -1)
+                launches += 4
+                ref_col = [i for i, g in enumerate(lay['groups']) if g[0] == 'FL'][0]
+                for gi, g in enumerate(lay['groups']):
+                    if g == ("FL", "FR"):
+                        continue
+                    d = gp[:, gi] - gp[:, ref_col]
+                    for spk in g:
+                        if spk in lay['speakers']:
+                            for sd in ('left', 'right'):
+                                shift2[:, lay['row_of'][f"{spk}-{sd}"]] -= d
+            elif 'FL' not in lay['speakers']:
+                raise RuntimeError("Cannot find FL left channel reference for onset alignment.")
+            X3 = self._shift(flat2, rows, L, n1, shift2.reshape(-1))
+            launches += 1
+            del X2, flat2
+            flat3 = X3.reshape(-1)
+            # 5. Lundeby knee per response (K4) -> per-set tail index (ref :614-653): the one host sync
+            _, knee, _, _ = ops.lundeby(flat3, rows * L, n1, fs, max_len=L)
+            launches += 5
+            host = torch.stack([knee, n1, peaks, crop]).cpu().numpy()
+            knees_h, n1_h, peaks_h, crop_h = (host[i].reshape(S, n) for i in range(4))
+            if head > 0 and n1_h.min() < head:
+                raise ValueError("an impulse response is shorter than the fade-in; use the HRIR class for such files")
+            seconds_per_octave = len(est) / est.fs / est.n_octaves
+            fade_out = 2 * int(fs * seconds_per_octave * (1 / 24))
+            window_out = hann(fade_out)[fade_out // 2:]
+            tails = [int(min(n1_h[s].min(), next_fast_len(int(knees_h[s].max())))) for s in range(S)]
+            results = [None] * S
+            for tail in sorted(set(tails)):
+                if tail < len(window_out):
+                    raise ValueError("negative dimensions are not allowed")
+                sets = [s for s in range(S) if tails[s] == tail]
+                sel = (torch.as_tensor(sets, device=dev, dtype=torch.int64)[:, None] * n +
+                       torch.arange(n, device=dev, dtype=torch.int64)[None, :]).reshape(-1)
+                out = ops.gather_window(flat3, sel * L, tail, fade_out=window_out).view(len(sets), n, tail)
+                launches += 1
+                for k, s in enumerate(sets):
+                    results[s] = SetResult(lay['names'], out[k], tail, peaks_h[s], crop_h[s], knees_h[s],
+                                           self._side_warnings(lay, peaks_h[s]))
+        self.launches = launches
+        return results
+
+    @staticmethod
+    def _shift(flat, rows, L, n1, shift):
+        """Length-preserving shift of every row (its own length n1), zero padded to L."""
+        import torch
+        lo = torch.clamp(shift, min=0)
+        hi = torch.maximum(torch.minimum(n1 + shift, n1), lo)
+        return ops.gather_window(flat, rows * L, L, shift=shift, valid_lo=lo, valid_hi=hi)
+
+    def _side_warnings(self, lay, peaks):
+        msgs = []
+        for k, spk in enumerate(lay['speakers']):
+            pl, pr = int(peaks[lay['row_of'][f"{spk}-left"]]), int(peaks[lay['row_of'][f"{spk}-right"]])
+            if pl < pr and lay['side_code'][k] == 'right':
+                msgs.append(f"Warning: {spk} measurement has lower delay to left ear than to right ear.")
+            elif pl >= pr and lay['side_code'][k] == 'left':
+                msgs.append(f"Warning: {spk} measurement has lower delay to right ear than to left ear.")
+        for m in msgs:
+            warnings.warn(m)
+        return msgs
+
+    # ---- per-IR frequency-response post-processing -----------------------------------------------------------
+    def postprocess(self, results, window_size=1 / 3, f_res=5, normalize=False):
+        """frequency_response -> smoothen_fractional_octave(window_size) -> minimum-phase FIR of the inverse
+        smoothed response, for every row of every set (sets of equal tail share launches).
+        Returns per set ``(frequency[F], raw[n,F], smoothed[n,F], fir[n,taps])`` as CUDA tensors."""
+        import torch
+        from .frequency_response import FrequencyResponse
+        grid = FrequencyResponse.generate_frequencies(f_step=1.01, f_min=10, f_max=self.fs / 2)
+        out = [None] * len(results)
+        by_tail = {}
+        for i, r in enumerate(results):
+            by_tail.setdefault(r.tail_ind, []).append(i)
+        for tail, idxs in by_tail.items():
+            data = torch.cat([results[i].data for i in idxs]) if len(idxs) > 1 else results[idxs[0]].data
+            raw = frequency_response_batch(data, self.fs)
+            sm = smoothen_batch(grid, raw, window_size, 1, window_size, 1, 100.0, 10000.0)
+            eq = -(sm - sm.mean(dim=1, keepdim=True))
+            fir = minimum_phase_batch(grid, eq, fs=self.fs, f_res=f_res, normalize=normalize)
+            n = results[idxs[0]].data.shape[0]
+            for k, i in enumerate(idxs):
+                sl = slice(k * n, (k + 1) * n)
+                out[i] = (grid, raw[sl], sm[sl], fir[sl])
+        return out
+
+
+class DeviceShard:
+    """Partition of recording sets over ranks (one process per GPU).  Sets are independent and never split
+    (crop_heads / align / crop_tails / normalize couple all responses of a set), so the
+    compute path has no collective; ``gather`` is the final result gather."""
+
+    def __init__(self, world_size: int = 1, rank: int = 0):
+        if not (0 <= rank < world_size):
+            raise ValueError("rank out of range")
+        self.world_size, self.rank = int(world_size), int(rank)
+
+    def owned(self, n_sets: int):
+        """Indices of the sets this rank processes (round-robin: set s -> rank s mod world_size)."""
+        return list(range(self.rank, n_sets, self.world_size))
+
+    def owner(self, set_index: int) -> int:
+        return set_index % self.world_size
+
+    def count(self, n_sets: int) -> int:
+        return len(range(self.rank, n_sets, self.world_size))
+
+    def gather(self, local_results, n_sets: int, dst: int = 0):
+        """Collect ``{set_index: picklable result}`` from every rank on ``dst`` in set order
+        (``torch.distributed.gather_object``; identity when world_size == 1)."""
+        if self.world_size == 1:
+            return [local_results[i] for i in range(n_sets)]
+        import torch.distributed as dist
+        bucket = [None] * self.world_size if self.rank == dst else None
+        dist.gather_object(local_results, bucket, dst=dst)
+        if self.rank != dst:
+            return None
+        merged = {}
+        for part in bucket:
+            merged.update(part)
+        return [merged[i] for i in range(n_sets)]

@@ -67,15 +67,23 @@ class DeconvPlan:
     def launches(self, batch: int) -> int:
         return int(_lib.lib().impb_deconv_launches_per_execute(self.handle, int(batch)))
 
-    def execute(self, rec, out=None, length=None, out_offset=0, out_len=None):
-        """rec: CUDA tensor [batch, ld] (float64 / float32 / int32 PCM).  Returns CUDA tensor [batch, out_len]."""
+    def execute(self, rec, out=None, length=None, out_offset=0, out_len=None, row_offsets=None):
+        """rec: CUDA tensor [batch, ld] (float64 / float32 / int32 PCM), or any CUDA tensor plus
+        ``row_offsets`` (int64 CUDA tensor: element offset of every row inside ``rec``) and ``length``.
+        Returns CUDA tensor [batch, out_len]."""
         import torch
-        if rec.dim() == 1:
+        if row_offsets is None and rec.dim() == 1:
             rec = rec[None, :]
-        if not rec.is_cuda or rec.stride(1) != 1:
+        if not rec.is_cuda or rec.stride(-1) != 1:
             raise ValueError("rec must be a CUDA tensor with contiguous rows")
         fmt = {torch.float64: _lib.FMT_F64, torch.float32: _lib.FMT_F32, torch.int32: _lib.FMT_I32PCM}[rec.dtype]
-        batch = rec.shape[0]
+        if row_offsets is not None:
+            if length is None:
+                raise ValueError("length is required with row_offsets")
+            row_offsets = row_offsets.to(device=rec.device, dtype=torch.int64).contiguous()
+            batch = row_offsets.numel()
+        else:
+            batch = rec.shape[0]
         length = rec.shape[1] if length is None else int(length)
         out_len = length - out_offset if out_len is None else int(out_len)
         out_dtype = torch.float64 if self.precision == 64 else torch.float32
@@ -85,7 +93,8 @@ class DeconvPlan:
         with self._lock:
             ws = self.workspace(batch)
             _lib.check(_lib.lib().impb_deconv_execute(
-                self.handle, rec.data_ptr(), rec.stride(0) if batch > 1 else rec.shape[1], fmt, length,
+                self.handle, rec.data_ptr(), None if row_offsets is None else row_offsets.data_ptr(),
+                (rec.stride(0) if batch > 1 else rec.shape[-1]) if row_offsets is None else 0, fmt, length,
                 out.data_ptr(), out.stride(0) if batch > 1 else out.shape[1], out_f64, int(out_offset), out_len,
                 batch, ws.data_ptr(), _lib.current_stream_ptr(rec.device)), "impb_deconv_execute")
         return out

@@ -55,7 +55,9 @@ IMPB_API const char* impb_last_error(void); /* thread-local */
  *
  * A plan caches the spectrum of the inverse filter for recordings of up to L samples.  precision is
  * 64 (FP64 arithmetic) or 32 (FP32 fast path, FP64-computed spectrum rounded to FP32).
- * execute(): rec is [batch, ld_in] in in_fmt, every row holds `len` valid samples (len <= L).  Row r of
+ * execute(): rec is [batch, ld_in] in in_fmt, every row holds `len` valid samples (len <= L); with
+ * in_offsets != NULL (device int64[batch]) row r instead starts at rec + in_offsets[r] elements, which is
+ * how the track/column split of core/hrir.py:194-216 is consumed without a gather copy.  Row r of
  * out ([batch, ld_out] f64 for precision 64, f32 for precision 32 unless out_f64 != 0) receives
  *   convolve(rec[r, :len], inverse_filter, 'same')[out_offset : out_offset + out_len].
  */
@@ -64,9 +66,9 @@ IMPB_API int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter
 IMPB_API void impb_deconv_plan_destroy(impb_plan* plan);
 IMPB_API int64_t impb_deconv_workspace_bytes(const impb_plan* plan, int64_t batch);
 IMPB_API int32_t impb_deconv_plan_info(const impb_plan* plan, int64_t* nfft, int64_t* n1, int64_t* n2);
-IMPB_API int32_t impb_deconv_execute(impb_plan* plan, const void* rec, int64_t ld_in, int32_t in_fmt, int64_t len,
-                            void* out, int64_t ld_out, int32_t out_f64, int64_t out_offset, int64_t out_len,
-                            int64_t batch, void* workspace, void* stream);
+IMPB_API int32_t impb_deconv_execute(impb_plan* plan, const void* rec, const int64_t* in_offsets, int64_t ld_in,
+                            int32_t in_fmt, int64_t len, void* out, int64_t ld_out, int32_t out_f64,
+                            int64_t out_offset, int64_t out_len, int64_t batch, void* workspace, void* stream);
 /* name and launch count of the kernels one execute() issues (bench.py gpu_launches accounting) */
 IMPB_API int32_t impb_deconv_launches_per_execute(const impb_plan* plan, int64_t batch);
 

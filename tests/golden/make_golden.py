@@ -147,7 +147,7 @@ def synth71():
     gold['final_BR_left'] = h.irs['BR']['left'].data.copy()
     # FR post-processing on four IRs
     fr_names = [('FL', 'left'), ('FL', 'right'), ('FC', 'left'), ('BR', 'right')]
-    raws, sm13, hl_s, hl_e, mp5, mp10, sm_custom = [], [], [], [], [], [], []
+    raws, sm13, hl_s, hl_e, mp5, mp10, sm_custom, eqw_eq, eqw_fir = [], [], [], [], [], [], [], [], []
     for s, e in fr_names:
         fr = h.irs[s][e].frequency_response()
         gold['fr_frequency'] = fr.frequency.copy()
@@ -159,6 +159,10 @@ def synth71():
         fr2.smoothen_heavy_light()
         hl_s.append(fr2.smoothed.copy())
         hl_e.append(fr2.error_smoothed.copy())
+        # the arithmetic of process_equalization_worker (core/parallel_workers.py:98-131)
+        fr2.equalize(max_gain=40, treble_f_lower=10000, treble_f_upper=est.fs / 2)
+        eqw_eq.append(fr2.equalization.copy())
+        eqw_fir.append(fr2.minimum_phase_impulse_response(fs=est.fs, normalize=False, f_res=5))
         fr3 = fr.copy()
         fr3.smoothen_fractional_octave(window_size=2, iterations=2, treble_window_size=1 / 12, treble_iterations=3,
                                        treble_f_lower=2000, treble_f_upper=12000)
@@ -168,7 +172,17 @@ def synth71():
         mp10.append(fr.minimum_phase_impulse_response(fs=est.fs, f_res=10, normalize=True))
     gold.update(fr_names=np.array([f'{s}-{e}' for s, e in fr_names]), fr_raw=np.array(raws),
                 fr_smoothed=np.array(sm13), fr_hl_smoothed=np.array(hl_s), fr_hl_error=np.array(hl_e),
-                fr_custom=np.array(sm_custom), minphase_f5=np.array(mp5), minphase_f10=np.array(mp10))
+                fr_custom=np.array(sm_custom), minphase_f5=np.array(mp5), minphase_f10=np.array(mp10),
+                eqw_equalization=np.array(eqw_eq), eqw_fir=np.array(eqw_fir))
+    # EQ-FIR application (ImpulseResponse.equalize, next-row component) on one response
+    ir = ImpulseResponse(h.irs['FL']['left'].data.copy(), est.fs)
+    ir.equalize(eqw_fir[0])
+    gold['equalized_FL_left_ck'] = checksums(ir.data)
+    gold['equalized_FL_left_head'] = ir.data[:4096].copy()
+    # normalisation gain of the whole set (HRIR.normalize, next-row component)
+    hn = h.copy()
+    gold['normalize_gain'] = np.array(hn.normalize(peak_target=-0.1, avg_target=None))
+    gold['normalized_FC_right_ck'] = checksums(hn.irs['FC']['right'].data)
     # resample 48k -> 44.1k through the reference method (nnresample = restated port: UNPINNED)
     ir = ImpulseResponse(h.irs['FL']['left'].data.copy(), est.fs)
     ir.resample(44100)
