@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Headline benchmark: IR deconvolutions/s for the 6.15 s @ 48 kHz sweep (BASELINE.json), 7.1 layout.
+
+    python bench.py --gpus N --steps K --warmup W              # this framework (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch of synthetic recording sets per GPU:
+  deconvolution of all 14 (speaker, ear) columns of every set (K1) -> first-peak search (K2) -> pairwise
+  head crop + fade-in (K3) -> ipsilateral / onset alignment (K6, K7) -> Lundeby knee (K4) -> tail crop (K5)
+i.e. ``HRIR.open_recording -> crop_heads -> align_ipsilateral_all -> align_onset_groups_peak_leftref ->
+crop_tails`` of the reference, through ``BatchDispatcher.process``.  ``value`` counts deconvolved impulse
+responses per second over all ranks with the recordings already resident in HBM; ``e2e`` is the same
+call fed from pinned HOST buffers with the H2D copy of the recordings and the D2H read of the cropped
+responses inside the timed region.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+FS = 48000
+LAYOUT = ['FL', 'FR', 'FC', 'SL', 'SR', 'BL', 'BR']
+N_IRS = 2 * len(LAYOUT)
+N_BASE_SETS = 2          # distinct host-synthesised recording sets; device batches are seeded variants
+
+
+def _host_sets(test_signal, n):
+    from impulcifer_pip313_b200 import synth
+    return [synth.recording_set(test_signal, FS, LAYOUT, seed=1234 + i) for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, one recording set per task, all host cores
+# ---------------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(inv, est_len, n_oct):
+    _CPU.update(inv=inv, est_len=est_len, n_oct=n_oct)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
+
+
+def _cpu_one_set(rec):
+    import impulcifer_oracle as O
+    irs = O.open_recording(rec, FS, LAYOUT, _CPU['inv'], FS)
+    O.crop_heads(irs, FS)
+    O.align_ipsilateral_all(irs, FS)
+    O.align_onset_groups_peak_leftref(irs)
+    tail = O.crop_tails(irs, FS, _CPU['est_len'], _CPU['n_oct'], FS)
+    return tail
+
+
+def cpu_throughput(test_signal, inv, n_oct, base_sets, sets_per_round, rounds, warm=1):
+    """IRs/s of the CPU path: process pool over all host cores (the reference's own parallel_map is a
+    ProcessPoolExecutor with max_workers=os.cpu_count(), core/parallel_utils.py:97-152)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = min(cores, sets_per_round)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers, initializer=_cpu_init, initargs=(inv, len(test_signal), n_oct)) as pool:
+        work = [base_sets[i % len(base_sets)] for i in range(sets_per_round)]
+        for _ in range(warm):
+            pool.map(_cpu_one_set, work[:workers])
+        times = []
+        for _ in range(rounds):
+            t0 = time.perf_counter()
+            pool.map(_cpu_one_set, work)
+            times.append(time.perf_counter() - t0)
+    return sets_per_round * N_IRS / min(times), workers, times
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import impulcifer_oracle as O
+    ts = O.generate_test_signal(5.0, FS)
+    P, _, _ = O.sweep_parameters(FS)
+    inv = O.generate_inverse_filter(ts, P)
+    base = _host_sets(ts, N_BASE_SETS)
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 4)
+    _, workers, t_all = cpu_throughput(ts, inv, P, base, per_step, rounds=args.steps, warm=min(args.warmup, 1))
+    value = per_step * N_IRS / (sum(t_all) / len(t_all))
+    line = {
+        "impl": "reference", "metric": "IR deconvolutions/s (6.15s@48kHz sweep)", "value": value, "unit": "IR/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(t_all) / len(t_all), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic 7.1 layout (FL,FR,FC,SL,SR,BL,BR x 2 ears) 6.15 s@48 kHz sweep "
+                               "deconvolution + crop", "sets_per_step": per_step, "irs_per_set": N_IRS,
+                   "samples_per_ir": 2 * FS + len(ts)},
+        "cpu_baseline": {"value": value, "unit": "IR/s", "cores": workers, "kind": "port",
+                         "sample": f"{per_step} recording sets ({per_step * N_IRS} IRs) per step through the oracle "
+                                   f"port of the reference path, fork pool of {workers} processes"},
+        "e2e": {"value": value, "unit": "IR/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sets", type=int, default=int(os.environ.get("BENCH_SETS", "32")),
+                    help="recording sets per GPU per step")
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    from impulcifer_pip313_b200.estimator import ImpulseResponseEstimator
+    est = ImpulseResponseEstimator(min_duration=5.0, fs=FS, device=local_rank, precision=args.precision)
+    L = 2 * FS + len(est)
+    base = _host_sets(est.test_signal, N_BASE_SETS)
+
+    # ---- CPU baseline first: the fork pool must exist before this process touches CUDA --------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sets = max(cores, 4)
+        v, workers, times = cpu_throughput(est.test_signal, est.inverse_filter, est.n_octaves, base, n_sets, rounds=2)
+        cpu = {"value": v, "unit": "IR/s", "cores": workers, "kind": "port",
+               "sample": f"{n_sets} recording sets ({n_sets * N_IRS} IRs), best of 2 rounds, oracle port of "
+                         f"open_recording+crop_heads+align+crop_tails, fork pool of {workers} processes"}
+
+    import torch
+    import torch.distributed as dist
+    from impulcifer_pip313_b200.dispatcher import BatchDispatcher
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic batch, resident in HBM: seeded variants of the host-synthesised base sets ------------------
+    S = args.sets
+    n_samples = base[0].shape[1]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321 + rank)
+    base_d = torch.from_numpy(np.stack(base)).to(dev)
+    batch = torch.empty((S, 2, n_samples), dtype=torch.float64, device=dev)
+    for s in range(S):
+        g = 0.5 + 0.5 * torch.rand(1, generator=gen, device=dev, dtype=torch.float64)
+        batch[s] = base_d[s % N_BASE_SETS] * g
+        batch[s] += 2e-6 * torch.randn((2, n_samples), generator=gen, device=dev, dtype=torch.float64)
+    del base_d
+    disp = BatchDispatcher(est, LAYOUT)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        return disp.process(batch)
+
+    for _ in range(args.warmup):
+        res = step()
+    tails = sorted({r.tail_ind for r in res})
+    out_bytes = sum(r.data.numel() * 8 for r in res)
+    launches_per_step = disp.launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * S * N_IRS * args.steps / (elapsed_ms / 1e3)
+
+    # ---- dominant kernel: the K1 launch triple, timed alone with events on its own stream ---------------------
+    plan = est.plan(L)
+    B = S * N_IRS
+    set_base = torch.arange(S, device=dev, dtype=torch.int64)[:, None]
+    lay = disp._layout
+    row_offs = (set_base * (2 * n_samples) + lay['offs'][None, :]).reshape(-1)
+    k1_out = torch.empty((B, L), dtype=torch.float64 if args.precision == 64 else torch.float32, device=dev)
+    for _ in range(2):
+        plan.execute(batch.reshape(-1), out=k1_out, length=L, row_offsets=row_offs)
+    torch.cuda.synchronize()
+    k1 = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        plan.execute(batch.reshape(-1), out=k1_out, length=L, row_offsets=row_offs)
+        b.record()
+        torch.cuda.synchronize()
+        k1.append(a.elapsed_time(b))
+    k1_ms = float(np.mean(k1))
+    del k1_out
+    bytes_per_ir = (8 + (8 if args.precision == 64 else 4)) * L
+    peak, peak_src = measured_peak()
+    achieved = B * bytes_per_ir / (k1_ms / 1e3) / 1e9
+
+    # ---- end to end: pinned host recordings in, cropped responses out, copies inside the timed region -------------
+    host_in = torch.empty((S, 2, n_samples), dtype=torch.float64).pin_memory()
+    host_in.copy_(batch.cpu())
+    host_out = torch.empty(2 * max(out_bytes // 8, 1), dtype=torch.float64).pin_memory()
+    stage = torch.empty_like(batch)
+
+    def e2e_step():
+        stage.copy_(host_in, non_blocking=True)
+        r = disp.process(stage)
+        off = 0
+        for x in r:
+            n = x.data.numel()
+            host_out[off:off + n].copy_(x.data.reshape(-1), non_blocking=True)
+            off += n
+        torch.cuda.synchronize()
+        return off
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        n_out = e2e_step()
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * S * N_IRS * e2e_steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        line = {
+            "metric": "IR deconvolutions/s (6.15s@48kHz sweep)", "value": value, "unit": "IR/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
+            "config": {"workload": "synthetic 7.1 layout (FL,FR,FC,SL,SR,BL,BR x 2 ears) 6.15 s@48 kHz sweep "
+                                   "deconvolution + crop (BASELINE.json configs[1])",
+                       "sets_per_gpu_per_step": S, "irs_per_set": N_IRS, "samples_per_ir": L,
+                       "sweep_samples": len(est), "fft_plan": f"{plan.n1}x{plan.n2}",
+                       "tail_samples": tails, "l2_policy": "inputs larger than L2 "
+                       f"({batch.numel() * 8 / 2**20:.0f} MiB of recordings per step)", "parallelism": f"sets x{world}"},
+            "e2e": {"value": e2e_value, "unit": "IR/s", "h2d_bytes_per_step": int(host_in.numel() * 8),
+                    "d2h_bytes_per_step": int(n_out * 8), "steps": e2e_steps,
+                    "api": "BatchDispatcher.process on pinned host float64 recordings"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "K1 deconvolution (k_fx_fwd + k_fx_conv + k_fx_inv launch triple)",
+                         "algorithmic_bytes_per_ir": bytes_per_ir, "irs_per_launch": B, "ms_per_launch": k1_ms,
+                         "peak_source": peak_src,
+                         "note": "FP64 FFT convolution is FP64-ALU/LSU bound, not HBM bound (DESIGN.md)"},
+            "clocks": clocks,
+        }
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+            line["roofline"]["traffic"] = tr.get("dram_bytes_per_ir", 0) * B
+        except Exception:
+            pass
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""Drop the B200 hot path under an unmodified checkout of the reference (115dkk/Impulcifer-pip313).
+
+    import impulcifer_pip313_b200 as b200
+    b200.install()                # before the pipeline modules are imported (or after: importers are re-bound)
+    import impulcifer; impulcifer.main(dir_path=..., test_signal='default')
+
+``install()`` builds three classes that put this package's device-backed methods IN FRONT of the reference's
+own classes in the MRO, so everything outside the hot path (plotting mix-ins, channel balance, README
+metrics, CSV I/O ...) keeps running the reference's code on top of them:
+
+    ImpulseResponseEstimator  <- estimator.ImpulseResponseEstimator , core.impulse_response_estimator.*
+    ImpulseResponse           <- impulse_response.ImpulseResponse   , core.impulse_response.ImpulseResponse
+    HRIR                      <- hrir.HRIR                          , core.hrir.HRIR
+    FrequencyResponse         <- frequency_response.FrequencyResponse, autoeq.frequency_response.FrequencyResponse
+
+and rebinds every already-imported module attribute that still points at the reference classes.
+Nothing in the reference tree is edited.  See INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import sys
+
+_installed = {}
+
+
+def install(verbose: bool = False):
+    if _installed:
+        return _installed
+    from core import hrir as ref_hrir
+    from core import impulse_response as ref_ir
+    from core import impulse_response_estimator as ref_est
+    from autoeq import frequency_response as ref_fr
+
+    from . import estimator, frequency_response, hrir, impulse_response
+
+    RefEst, RefIR, RefHRIR, RefFR = (ref_est.ImpulseResponseEstimator, ref_ir.ImpulseResponse, ref_hrir.HRIR,
+                                     ref_fr.FrequencyResponse)
+
+    class FrequencyResponse(frequency_response.FrequencyResponse, RefFR):
+        __doc__ = RefFR.__doc__
+
+    class ImpulseResponse(impulse_response.ImpulseResponse, RefIR):
+        __doc__ = RefIR.__doc__
+
+        def frequency_response(self):
+            fr = impulse_response.ImpulseResponse.frequency_response(self)
+            return FrequencyResponse(name=fr.name, frequency=fr.frequency, raw=fr.raw)
+
+    class HRIR(hrir.HRIR, RefHRIR):
+        __doc__ = RefHRIR.__doc__
+
+    class ImpulseResponseEstimator(estimator.ImpulseResponseEstimator, RefEst):
+        __doc__ = RefEst.__doc__
+
+    # the shim modules construct these classes themselves: point them at the merged ones
+    hrir.ImpulseResponse = ImpulseResponse
+    impulse_response.FrequencyResponse = FrequencyResponse
+
+    mapping = {RefEst: ImpulseResponseEstimator, RefIR: ImpulseResponse, RefHRIR: HRIR, RefFR: FrequencyResponse}
+    rebound = 0
+    for mod in list(sys.modules.values()):
+        d = getattr(mod, '__dict__', None)
+        if not d or getattr(mod, '__name__', '').startswith('impulcifer_pip313_b200'):
+            continue
+        for k, v in list(d.items()):
+            if isinstance(v, type) and v in mapping:
+                d[k] = mapping[v]
+                rebound += 1
+    _installed.update(ImpulseResponseEstimator=ImpulseResponseEstimator, ImpulseResponse=ImpulseResponse, HRIR=HRIR,
+                      FrequencyResponse=FrequencyResponse, rebound=rebound)
+    if verbose:
+        print(f"impulcifer_pip313_b200: installed over the reference ({rebound} bindings replaced)")
+    return _installed

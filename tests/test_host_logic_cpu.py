@@ -1,0 +1,143 @@
+"""Host-side logic of the shim (no GPU): integer ingest layout, window arithmetic, sharding — against the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import impulcifer_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_estimator_constants_match_oracle():
+    from impulcifer_pip313_b200 import ImpulseResponseEstimator
+    for dur, fs in ((0.05, 2000), (1.0, 48000)):
+        est = ImpulseResponseEstimator(min_duration=dur, fs=fs)
+        ts = O.generate_test_signal(dur, fs)
+        P, low, high = O.sweep_parameters(fs)
+        assert est.n_octaves == P and est.low == low and est.high == high
+        assert np.array_equal(est.test_signal, ts)
+        inv = O.generate_inverse_filter(ts, P)
+        assert np.max(np.abs(est.inverse_filter - inv)) <= 1e-12 * np.max(np.abs(inv))
+        assert len(est) == len(ts) and est.duration == len(ts) / fs
+    with pytest.raises(ValueError):
+        ImpulseResponseEstimator(min_duration=1.0, fs=44100.5)
+
+
+@pytest.mark.parametrize("n_tracks,n_samples,speakers,side", [
+    (2, 96000 + 7 * 391270, ['FL', 'FR', 'FC', 'SL', 'SR', 'BL', 'BR'], None),
+    (1, 878540, ['FL', 'FR'], 'left'),
+    (1, 487270, ['FC'], 'right'),
+    (2, 487270, ['FC'], None),
+    (1, 878540 - 100000, ['FL', 'FR'], 'left'),       # clipped last column
+    (2, 96000 + 300000, ['FL'], None),                # short recording: fallbacks
+    (2, 96000 + 250000, ['FL'], None),
+    (4, 96000 + 2 * 391270, ['FL', 'FR', 'SL', 'SR'], None),
+    (2, 96000 + 2 * 391270, ['FL', 'X'], None),       # non-standard speaker name is skipped
+])
+def test_ingest_layout_matches_oracle(n_tracks, n_samples, speakers, side):
+    from impulcifer_pip313_b200.hrir import ingest_layout
+    _, cols_o, plan_o = O.ingest_layout(n_tracks, n_samples, speakers, 295270, 48000, side)
+    cols, plan = ingest_layout(n_tracks, n_samples, speakers, 295270, 48000, side)
+    assert cols == cols_o and plan == plan_o
+
+
+def test_ingest_layout_errors():
+    from impulcifer_pip313_b200.hrir import ingest_layout
+    with pytest.raises(ValueError, match="No valid columns"):
+        ingest_layout(2, 96000 + 1000, ['FL'], 295270, 48000)
+    with pytest.raises(ValueError, match="Silence length"):
+        ingest_layout(2, 10 ** 6, ['FL'], 295270, 44100, silence_length=2.00001)
+
+
+def test_window_arithmetic_and_tables():
+    from impulcifer_pip313_b200 import frequency_response as FR
+    from impulcifer_pip313_b200 import ops
+    f = FR.FrequencyResponse.generate_frequencies(f_min=10, f_max=24000, f_step=1.01)
+    assert np.array_equal(f, O.generate_frequencies(10, 24000, 1.01)) and len(f) == 783
+    for octv in (1 / 3, 1 / 6, 1 / 5, 1 / 12, 1.3, 1.4, 2):
+        assert FR.window_size(f, octv) == O.window_size(f, octv)
+    assert np.allclose(FR.sigmoid(f, 100.0, 10000.0), O.sigmoid(f, 100.0, 10000.0), rtol=0, atol=1e-15)
+    for t in (1, 7, 97, 21555, 93949, 686539):
+        assert FR.next_fast_len(t) == O.next_fast_len_5smooth(t)
+    for w in (7, 23, 139):
+        c, e = ops.savgol_tables(w)
+        assert np.allclose(c, O.savgol_coeffs(w), atol=1e-15) and np.allclose(e, O.savgol_edge_matrix(w), atol=1e-13)
+
+
+def test_resample_taps_match_port():
+    from impulcifer_pip313_b200.impulse_response import resample_taps
+    for new, old in ((44100, 48000), (48000, 192000), (96000, 48000)):
+        up, down, taps = resample_taps(new, old)
+        u, d, t = O.resample_filter(new, old)
+        assert (up, down) == (u, d) and np.array_equal(taps, t * u)
+
+
+def test_frequency_response_host_contract():
+    from impulcifer_pip313_b200 import FrequencyResponse
+    f = FrequencyResponse.generate_frequencies(f_min=10, f_max=24000, f_step=1.01)
+    fr = FrequencyResponse(name='t', frequency=f, raw=np.zeros(len(f)), error=0)
+    assert len(fr.error) == len(f) and fr.smoothed.size == 0
+    with pytest.raises(TypeError):
+        FrequencyResponse(name='')
+    with pytest.raises(ValueError, match="Upper transition boundary"):
+        fr.smoothen_fractional_octave(treble_f_lower=1000, treble_f_upper=1000)
+    fr.raw[3] = np.nan
+    with pytest.raises(ValueError, match="NaN values present"):
+        fr.smoothen_fractional_octave()
+    fr2 = FrequencyResponse(name='t', frequency=f, raw=np.zeros(len(f)))
+    with pytest.raises(ValueError, match="Error data is missing"):
+        fr2.equalize()
+    # equalize() is host arithmetic: clamp / invert behaviour of tests/test_frequency_response_core.py:73-96
+    fr3 = FrequencyResponse(name='t', frequency=f, raw=np.zeros(len(f)), error=np.full(len(f), -10.0))
+    fr3.equalize(max_gain=6.0, smoothen=False)
+    assert np.allclose(fr3.equalization, 6.0, atol=1e-9)
+    fr4 = FrequencyResponse(name='t', frequency=f, raw=np.zeros(len(f)), error=np.full(len(f), 3.0))
+    fr4.equalize(max_gain=6.0)
+    assert np.allclose(fr4.equalization, -3.0, atol=1e-9) and np.allclose(fr4.equalized_raw, -3.0, atol=1e-9)
+
+
+def test_device_shard_partition():
+    from impulcifer_pip313_b200 import DeviceShard
+    n = 37
+    seen = []
+    for r in range(8):
+        sh = DeviceShard(8, r)
+        own = sh.owned(n)
+        assert all(sh.owner(i) == r for i in own) and sh.count(n) == len(own)
+        seen += own
+    assert sorted(seen) == list(range(n))
+    assert DeviceShard(1, 0).gather({0: 'a', 1: 'b'}, 2) == ['a', 'b']
+    with pytest.raises(ValueError):
+        DeviceShard(2, 2)
+
+
+def test_device_shard_gather_two_ranks_gloo(tmp_path):
+    """N > 1 path on CPU: two gloo ranks shard 5 recording sets and rank 0 gathers them in set order."""
+    script = tmp_path / "shard_worker.py"
+    script.write_text(f'''
+import os, sys, json
+sys.path.insert(0, {ROOT!r})
+import torch.distributed as dist
+from impulcifer_pip313_b200 import DeviceShard
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sh = DeviceShard(world, rank)
+local = {{i: {{"set": i, "rank": rank, "tail": 1000 + i}} for i in sh.owned(5)}}
+out = sh.gather(local, 5)
+if rank == 0:
+    assert [o["set"] for o in out] == [0, 1, 2, 3, 4]
+    assert [o["rank"] for o in out] == [0, 1, 0, 1, 0]
+    print("GATHER_OK")
+else:
+    assert out is None
+dist.destroy_process_group()
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "GATHER_OK" in r.stdout
