@@ -45,8 +45,8 @@ struct DeviceGuard {
 bool make_subplan(int S, int tile, int threads, SubPlan* sp);
 // radices of the compile-time specialised kernel for length S, if one exists
 bool fixed_radices(int S, int* r);
-// per-stage twiddle table of the specialised kernels: tw[np*(R-1)+p-1] = exp(-2 pi i np p / len_s)
-std::vector<double> stage_table(const SubPlan& sp, int s);
+// per-stage twiddle table of the specialised kernels (column-pass or transposed row-pass layout)
+std::vector<double> stage_table(const SubPlan& sp, int s, bool transposed);
 // digit-reversal: perm[pos] = frequency index held at tile position pos after the DIF stages
 std::vector<int> subplan_perm(const SubPlan& sp);
 

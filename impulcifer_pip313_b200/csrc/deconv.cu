@@ -56,8 +56,8 @@ __device__ __forceinline__ double load_sample(const void* p, int fmt, int64_t i)
   }
 }
 
-// A: real pair -> column DIF
-template <typename T, int TILE> struct DeconvColIn {
+// A: real pair -> column DIF   (PRE: the kernel applies post() itself, store() must not)
+template <typename T, int TILE, bool PRE = false> struct DeconvColIn {
   DeconvArgs<T> a;
   __device__ __forceinline__ cx_t<T> load(int b, int t, int e, int c) const {
     const int n2 = t * TILE + c;
@@ -77,12 +77,26 @@ template <typename T, int TILE> struct DeconvColIn {
     const int n2 = t * TILE + c;
     if (n2 >= a.N2) return;
     const size_t idx = (size_t)e * a.N2 + n2;
-    a.ws[(size_t)b * a.N + idx] = cmul(v, __ldg(a.tw + idx));
+    a.ws[(size_t)b * a.N + idx] = PRE ? v : cmul(v, __ldg(a.tw + idx));
+  }
+  // four-step twiddle of output (e, c), fetched ahead of the butterfly by the specialised kernels
+  __device__ __forceinline__ cx_t<T> post(int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    return n2 < a.N2 ? __ldg(a.tw + (size_t)e * a.N2 + n2) : mkc<T>(0, 0);
+  }
+  // address of the f64 sample feeding re (which=0) / im (which=1) of element (e, c); nullptr = zero padding
+  __device__ __forceinline__ const T* src(int b, int t, int e, int c, int which) const {
+    const int n2 = t * TILE + c;
+    const int64_t n = (int64_t)e * a.N2 + n2;
+    const int64_t r = a.row0 + 2 * (int64_t)b + which;
+    if (n2 >= a.N2 || n >= a.len || r >= a.nrows) return nullptr;
+    const int64_t o = a.in_offsets ? __ldg(a.in_offsets + r) : r * a.ld_in;
+    return reinterpret_cast<const T*>(a.rec) + o + n;
   }
 };
 
 // BC: row DIF x H x row DIT, in place
-template <typename T, int TILE> struct DeconvRow {
+template <typename T, int TILE, bool PRE = false> struct DeconvRow {
   DeconvArgs<T> a;
   __device__ __forceinline__ cx_t<T> load(int b, int t, int e, int c) const {
     const int row = t * TILE + c;
@@ -96,7 +110,11 @@ template <typename T, int TILE> struct DeconvRow {
     const int row = t * TILE + c;
     if (row >= a.N1) return;
     const size_t idx = (size_t)row * a.N2 + e;
-    a.ws[(size_t)b * a.N + idx] = cmul(v, cconj(__ldg(a.tw + idx)));
+    a.ws[(size_t)b * a.N + idx] = PRE ? v : cmul(v, cconj(__ldg(a.tw + idx)));
+  }
+  __device__ __forceinline__ cx_t<T> post(int t, int e, int c) const {
+    const int row = t * TILE + c;
+    return row < a.N1 ? cconj(__ldg(a.tw + (size_t)row * a.N2 + e)) : mkc<T>(0, 0);
   }
 };
 
@@ -137,7 +155,8 @@ __global__ void k_spec_to_natural(const double2* __restrict__ ws, double2* __res
 // natural order -> the register/lane order of the fused row kernel:  hs[(tile*R + q)*items + w]
 template <typename T>
 __global__ void k_spec_layout(const double2* __restrict__ nat, cx_t<T>* __restrict__ hs, const int* __restrict__ perm1,
-                              const int* __restrict__ perm2, int N1, int N2, int TILE, int R, double scale) {
+                              const int* __restrict__ perm2, int N1, int N2, int TILE, int R, double scale,
+                              int j_fastest) {
   const int items = (N2 / R) * TILE;
   const int64_t total = (int64_t)((N1 + TILE - 1) / TILE) * R * items;
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -145,7 +164,8 @@ __global__ void k_spec_layout(const double2* __restrict__ nat, cx_t<T>* __restri
   const int w = (int)(i % items);
   const int q = (int)((i / items) % R);
   const int t = (int)(i / ((int64_t)items * R));
-  const int c = w % TILE, j = w / TILE;
+  // work-item order of the consuming kernel: specialised row pass = j fastest, generic = c fastest
+  const int c = j_fastest ? w / (N2 / R) : w % TILE, j = j_fastest ? w % (N2 / R) : w / TILE;
   const int row = t * TILE + c, p2 = j * R + q;
   double2 v = make_double2(0.0, 0.0);
   if (row < N1) v = nat[(size_t)perm1[row] + (size_t)N1 * perm2[p2]];
@@ -168,7 +188,7 @@ template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
 #define IMPB_FX_CASE(KERNEL, S_, R0_, R1_, R2_)                                                 \
   case S_: {                                                                                    \
     auto k = KERNEL<T, TILE, 256, Radix3<R0_, R1_, R2_>, F>;                                     \
-    const size_t smem = (size_t)S_ * (TILE + 1) * sizeof(cx_t<T>);                               \
+    const size_t smem = (size_t)S_ * TILE * sizeof(cx_t<T>);                                     \
     int rc = fx_prepare(k, smem, device);                                                        \
     if (rc) return rc;                                                                           \
     k<<<grid, 256, smem, st>>>(tw0, tw1, f);                                                     \
@@ -181,11 +201,12 @@ template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
   static int NAME(int S, dim3 grid, cudaStream_t st, int device, const cx_t<T>* tw0, const cx_t<T>* tw1,     \
                   const F& f) {                                                                              \
     switch (S) {                                                                                             \
-      IMPB_FX_CASE(KERNEL, 768, 12, 8, 8)                                                                    \
+      IMPB_FX_CASE(KERNEL, 768, 8, 12, 8)                                                                    \
       default: set_error("no specialised kernel for S=%d", S); return IMPB_EUNSUPPORTED;                    \
     }                                                                                                        \
   }
 IMPB_FX_DISPATCH(fx_fwd, k_fx_fwd)
+IMPB_FX_DISPATCH(fx_fwd_async, k_fx_fwd_async)
 IMPB_FX_DISPATCH(fx_inv, k_fx_inv)
 IMPB_FX_DISPATCH(fx_conv, k_fx_conv)
 
@@ -199,11 +220,22 @@ template <typename T, int TILE> struct DeconvEngine {
     static const bool no_fixed = getenv("IMPB_NO_FIXED") != nullptr;
     if (fft.col_fixed && fft.row_fixed && !no_fixed) {
       const Plan2D& p = fft.p;
-      if ((rc = fx_fwd<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
-                                DeconvColIn<T, TILE>{a})))
-        return rc;
+      static const bool no_async = getenv("IMPB_NO_ASYNC") != nullptr;
+      if constexpr (sizeof(T) == 8) {
+        if (a.in_fmt == IMPB_FMT_F64 && !no_async) {
+          rc = fx_fwd_async<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
+                                     DeconvColIn<T, TILE, true>{a});
+        } else {
+          rc = fx_fwd<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
+                               DeconvColIn<T, TILE, true>{a});
+        }
+      } else {
+        rc = fx_fwd<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
+                             DeconvColIn<T, TILE, true>{a});
+      }
+      if (rc) return rc;
       if ((rc = fx_conv<T, TILE>(p.N2, dim3(fft.row_tiles(), pairs), st, device, fft.fx_row[0], fft.fx_row[1],
-                                 DeconvRow<T, TILE>{a})))
+                                 DeconvRow<T, TILE, true>{a})))
         return rc;
       return fx_inv<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
                              DeconvColOut<T, TILE>{a});
@@ -273,13 +305,15 @@ static int build_spectrum(impb_plan* pl, const double* inv_host) {
       const size_t total = (size_t)((N1 + 7) / 8) * 8 * N2;
       IMPB_CUDA(cudaMalloc(&pl->e64.hs, total * sizeof(double2)));
       k_spec_layout<double><<<(unsigned)((total + thr - 1) / thr), thr>>>(nat, pl->e64.hs, pl->e64.fft.perm_col,
-                                                                       pl->e64.fft.perm_row, N1, N2, 8, R, scale);
+                                                                       pl->e64.fft.perm_row, N1, N2, 8, R, scale,
+                                                                       (pl->e64.fft.col_fixed && pl->e64.fft.row_fixed && !getenv("IMPB_NO_FIXED")) ? 1 : 0);
     } else {
       const int R = target.row.radix[target.row.nst - 1];
       const size_t total = (size_t)((N1 + 15) / 16) * 16 * N2;
       IMPB_CUDA(cudaMalloc(&pl->e32.hs, total * sizeof(float2)));
       k_spec_layout<float><<<(unsigned)((total + thr - 1) / thr), thr>>>(nat, pl->e32.hs, pl->e32.fft.perm_col,
-                                                                      pl->e32.fft.perm_row, N1, N2, 16, R, scale);
+                                                                      pl->e32.fft.perm_row, N1, N2, 16, R, scale,
+                                                                      (pl->e32.fft.col_fixed && pl->e32.fft.row_fixed && !getenv("IMPB_NO_FIXED")) ? 1 : 0);
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) rc = cuda_fail(e, "inverse-filter spectrum build");

@@ -51,7 +51,7 @@ template <typename T> struct Fft2D {
       (which ? row_fixed : col_fixed) = fixed;
       if (!fixed) continue;
       for (int s = 0; s < 2; ++s) {
-        std::vector<double> t = stage_table(sp, s);
+        std::vector<double> t = stage_table(sp, s, /*transposed=*/which == 1);
         std::vector<cx_t<T>> tt(t.size() / 2);
         for (size_t i = 0; i < tt.size(); ++i) tt[i] = mkc<T>((T)t[2 * i], (T)t[2 * i + 1]);
         cx_t<T>** dst = which ? &fx_row[s] : &fx_col[s];

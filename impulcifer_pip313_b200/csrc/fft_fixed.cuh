@@ -4,9 +4,17 @@
 // read-only path; the 8 columns of a tile share each entry, so a warp touches one or two sectors).
 // Used for the sub-FFT lengths the headline workloads need; every other length takes the generic path.
 #pragma once
+#include <type_traits>
+
 #include "fft_tile.cuh"
 
+#ifndef IMPB_TRIP_UNROLL
+#define IMPB_TRIP_UNROLL 1
+#endif
+
 namespace impb {
+
+constexpr int kTripUnroll = IMPB_TRIP_UNROLL;
 
 template <int R0_, int R1_, int R2_> struct Radix3 {
   static constexpr int R0 = R0_, R1 = R1_, R2 = R2_;
@@ -17,57 +25,110 @@ template <int R0_, int R1_, int R2_> struct Radix3 {
   static constexpr int TW1 = S1 * (R1_ - 1);
 };
 
-// one radix-R stage over the whole tile; LD/ST address elements as (e, c)
-template <typename T, int TILE, int NT, int S, int LEN, int R, bool INV, class LD, class ST>
-__device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, ST st) {
+// Work-item -> (column c, butterfly j) decode and shared-memory addressing.
+//  * column pass (ROW = false): c fastest.  A quarter-warp (8 lanes x 16 B) is one row x 8 columns: one 128-byte
+//    HBM segment, and 8 distinct bank groups through the XOR swizzle  slot = c ^ (e & 7).
+//  * row pass (ROW = true): j fastest.  A quarter-warp is 8 consecutive elements of ONE row: again one 128-byte
+//    HBM segment (with c fastest it would be 8 different lines = 8x the LSU wavefronts, measured 18 wavefronts
+//    per request in round 1).  Tile is [c][S] with  e' = e ^ ((e >> 3) & 7), conflict-free for strides 64, 8, 1.
+// No padding: the tile is exactly S * TILE elements.
+template <bool ROW, int TILE, int PER_COL> __device__ __forceinline__ void fx_decode(int w, int& c, int& j) {
+  if (ROW) { j = w % PER_COL; c = w / PER_COL; } else { c = w % TILE; j = w / TILE; }
+}
+template <bool ROW, int TILE, int S> __device__ __forceinline__ int fx_smem(int e, int c) {
+  return ROW ? c * S + (e ^ ((e >> 3) & 7)) : e * TILE + (c ^ (e & (TILE - 1)));
+}
+
+// Stage twiddles w_p = exp(-2 pi i np p / LEN), p = 1..R-1, from the power-of-two entries of the table only
+// (w_1, w_2, w_4, w_8: 3-4 loads instead of R-1; the rest are single products of table values, <= 2 roundings).
+// Table layout: entry k of butterfly np holds w_(2^k):  column pass tw[np][k], row pass tw[k][np] (coalesced).
+template <typename T, int R, bool ROW, int STRIDE>
+__device__ __forceinline__ void fx_twiddles(const cx_t<T>* __restrict__ tw, int np, cx_t<T>* w) {
+  constexpr int NB = (R > 8) ? 4 : (R > 4) ? 3 : (R > 2) ? 2 : 1;
+  const cx_t<T>* twp = ROW ? tw + np : tw + np * NB;
+  constexpr int TWS = ROW ? STRIDE : 1;
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+    if ((1 << k) < R) w[1 << k] = __ldg(twp + k * TWS);
+#pragma unroll
+  for (int p = 3; p < R; ++p) {
+    const int hi = (p >= 8) ? 8 : (p >= 4) ? 4 : 2;
+    if (p != hi) w[p] = cmul(w[hi], w[p - hi]);
+  }
+}
+
+// one radix-R stage over the whole tile; LD/ST address elements as (e, c).  POST (optional) supplies one
+// multiplier per OUTPUT element (four-step twiddle); it is fetched at the top of the trip so that its latency
+// hides behind the butterfly instead of sitting in front of the store.
+struct NoPost {};
+template <typename T, int TILE, int NT, int S, int LEN, int R, bool INV, bool ROW, class LD, class ST, class POST>
+__device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, ST st, POST post) {
   constexpr int STRIDE = LEN / R;
-  constexpr int ITEMS = (S / R) * TILE;
+  constexpr int PER_COL = S / R;
+  constexpr int ITEMS = PER_COL * TILE;
   constexpr int TRIPS = (ITEMS + NT - 1) / NT;
-#pragma unroll 1
+  constexpr bool HAS_POST = !std::is_same<POST, NoPost>::value;
+#pragma unroll kTripUnroll
   for (int it = 0; it < TRIPS; ++it) {
     const int w = threadIdx.x + it * NT;
     if ((ITEMS % NT) != 0 && w >= ITEMS) break;
-    const int c = w % TILE, j = w / TILE;
+    int c, j;
+    fx_decode<ROW, TILE, PER_COL>(w, c, j);
     const int b = j / STRIDE, np = j % STRIDE;
     const int base = b * LEN + np;
+    cx_t<T> m[HAS_POST ? R : 1];
+    if constexpr (HAS_POST) {
+#pragma unroll
+      for (int p = 0; p < R; ++p) m[p] = post(base + p * STRIDE, c);
+    }
     cx_t<T> x[R];
 #pragma unroll
     for (int q = 0; q < R; ++q) x[q] = ld(base + q * STRIDE, c);
     if (STRIDE > 1) {
-      const cx_t<T>* twp = tw + np * (R - 1);
+      cx_t<T> wv[R];
+      fx_twiddles<T, R, ROW, STRIDE>(tw, np, wv);
       if (INV) {
 #pragma unroll
-        for (int p = 1; p < R; ++p) x[p] = cmul(x[p], cconj(__ldg(twp + p - 1)));
+        for (int p = 1; p < R; ++p) x[p] = cmul(x[p], cconj(wv[p]));
         Dft<T, R, true>::run(x);
       } else {
         Dft<T, R, false>::run(x);
 #pragma unroll
-        for (int p = 1; p < R; ++p) x[p] = cmul(x[p], __ldg(twp + p - 1));
+        for (int p = 1; p < R; ++p) x[p] = cmul(x[p], wv[p]);
       }
     } else {
       Dft<T, R, INV>::run(x);
+    }
+    if constexpr (HAS_POST) {
+#pragma unroll
+      for (int p = 0; p < R; ++p) x[p] = cmul(x[p], m[p]);
     }
 #pragma unroll
     for (int p = 0; p < R; ++p) st(base + p * STRIDE, c, x[p]);
   }
 }
 
-// last forward stage x pointwise x first inverse stage, in registers
+// last forward stage x pointwise x first inverse stage, in registers (row pass only)
 template <typename T, int TILE, int NT, int S, int R, class LD, class ST, class PW>
 __device__ __forceinline__ void fx_mid(LD ld, ST st, PW pw) {
-  constexpr int ITEMS = (S / R) * TILE;
+  constexpr int PER_COL = S / R;
+  constexpr int ITEMS = PER_COL * TILE;
   constexpr int TRIPS = (ITEMS + NT - 1) / NT;
-#pragma unroll 1
+#pragma unroll kTripUnroll
   for (int it = 0; it < TRIPS; ++it) {
     const int w = threadIdx.x + it * NT;
     if ((ITEMS % NT) != 0 && w >= ITEMS) break;
-    const int c = w % TILE, j = w / TILE;
+    int c, j;
+    fx_decode<true, TILE, PER_COL>(w, c, j);
+    cx_t<T> h[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) h[q] = pw(q, w);
     cx_t<T> x[R];
 #pragma unroll
     for (int q = 0; q < R; ++q) x[q] = ld(j * R + q, c);
     Dft<T, R, false>::run(x);
 #pragma unroll
-    for (int q = 0; q < R; ++q) x[q] = cmul(x[q], pw(q, w));
+    for (int q = 0; q < R; ++q) x[q] = cmul(x[q], h[q]);
     Dft<T, R, true>::run(x);
 #pragma unroll
     for (int q = 0; q < R; ++q) st(j * R + q, c, x[q]);
@@ -79,17 +140,55 @@ __global__ void __launch_bounds__(NT, 2)
 k_fx_fwd(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
-  constexpr int PITCH = TILE + 1;
   const int t = blockIdx.x, b = blockIdx.y;
   auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
   auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
-  auto sl = [&](int e, int c) -> cx_t<T> { return tile[e * PITCH + c]; };
-  auto ss = [&](int e, int c, cx_t<T> v) { tile[e * PITCH + c] = v; };
-  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false>(tw0, gl, ss);
+  auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
+  auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
+  auto post = [&](int e, int c) -> cx_t<T> { return f.post(t, e, c); };
+  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, false>(tw0, gl, ss, NoPost{});
   __syncthreads();
-  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false>(tw1, sl, ss);
+  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false, false>(tw1, sl, ss, NoPost{});
   __syncthreads();
-  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, false>(nullptr, sl, gs);
+  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, false, false>(nullptr, sl, gs, post);
+}
+
+// Column forward pass whose input tile is staged HBM -> shared memory with cp.async (LDGSTS): every load of
+// the tile is in flight at once and none of them occupies a register, so the pass is bound by HBM bandwidth
+// instead of (trips x HBM latency).  F::src(b, t, e, c, which) returns the address of the real sample that
+// becomes the re (which = 0) / im (which = 1) part of element (e, c), or nullptr for a zero.
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+template <typename T, int TILE, int NT, class RX, class F>
+__global__ void __launch_bounds__(NT, 2)
+k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
+  static_assert(sizeof(T) == 8, "cp.async staging is written for FP64 tiles");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
+  const int t = blockIdx.x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < RX::S * TILE; i += NT) {
+    const int e = i / TILE, c = i % TILE;
+    T* dst = reinterpret_cast<T*>(&tile[fx_smem<false, TILE, RX::S>(e, c)]);
+    const T* re = f.src(b, t, e, c, 0);
+    const T* im = f.src(b, t, e, c, 1);
+    if (re) cp_async_8(dst, re); else dst[0] = (T)0;
+    if (im) cp_async_8(dst + 1, im); else dst[1] = (T)0;
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
+  auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
+  auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
+  auto post = [&](int e, int c) -> cx_t<T> { return f.post(t, e, c); };
+  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, false>(tw0, sl, ss, NoPost{});
+  __syncthreads();
+  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false, false>(tw1, sl, ss, NoPost{});
+  __syncthreads();
+  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, false, false>(nullptr, sl, gs, post);
 }
 
 template <typename T, int TILE, int NT, class RX, class F>
@@ -97,41 +196,41 @@ __global__ void __launch_bounds__(NT, 2)
 k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
-  constexpr int PITCH = TILE + 1;
   const int t = blockIdx.x, b = blockIdx.y;
   auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
   auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
-  auto sl = [&](int e, int c) -> cx_t<T> { return tile[e * PITCH + c]; };
-  auto ss = [&](int e, int c, cx_t<T> v) { tile[e * PITCH + c] = v; };
-  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true>(nullptr, gl, ss);
+  auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
+  auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
+  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false>(nullptr, gl, ss, NoPost{});
   __syncthreads();
-  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true>(tw1, sl, ss);
+  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true, false>(tw1, sl, ss, NoPost{});
   __syncthreads();
-  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, true>(tw0, sl, gs);
+  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, true, false>(tw0, sl, gs, NoPost{});
 }
 
+// row pass: forward, x spectrum, inverse.  tw0r / tw1r are the [p-1][np] (transposed) stage tables.
 template <typename T, int TILE, int NT, class RX, class F>
 __global__ void __launch_bounds__(NT, 2)
-k_fx_conv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
+k_fx_conv(const cx_t<T>* __restrict__ tw0r, const cx_t<T>* __restrict__ tw1r, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
-  constexpr int PITCH = TILE + 1;
   const int t = blockIdx.x, b = blockIdx.y;
   constexpr int ITEMS_MID = (RX::S / RX::R2) * TILE;
   auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
   auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
-  auto sl = [&](int e, int c) -> cx_t<T> { return tile[e * PITCH + c]; };
-  auto ss = [&](int e, int c, cx_t<T> v) { tile[e * PITCH + c] = v; };
+  auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<true, TILE, RX::S>(e, c)]; };
+  auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<true, TILE, RX::S>(e, c)] = v; };
   auto pw = [&](int q, int w) -> cx_t<T> { return f.pw(t, RX::R2, ITEMS_MID, q, w); };
-  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false>(tw0, gl, ss);
+  auto post = [&](int e, int c) -> cx_t<T> { return f.post(t, e, c); };
+  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, true>(tw0r, gl, ss, NoPost{});
   __syncthreads();
-  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false>(tw1, sl, ss);
+  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false, true>(tw1r, sl, ss, NoPost{});
   __syncthreads();
   fx_mid<T, TILE, NT, RX::S, RX::R2>(sl, ss, pw);
   __syncthreads();
-  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true>(tw1, sl, ss);
+  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true, true>(tw1r, sl, ss, NoPost{});
   __syncthreads();
-  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, true>(tw0, sl, gs);
+  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, true, true>(tw0r, sl, gs, post);
 }
 
 }  // namespace impb

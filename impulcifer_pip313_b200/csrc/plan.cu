@@ -67,7 +67,7 @@ bool fixed_radices(int S, int* r) {
   // sub-FFT lengths with a compile-time specialised kernel (fft_fixed.cuh); keep in sync with the
   // dispatch switches in deconv.cu
   switch (S) {
-    case 768: r[0] = 12; r[1] = 8; r[2] = 8; return true;
+    case 768: r[0] = 8; r[1] = 12; r[2] = 8; return true;
     default: return false;
   }
 }
@@ -139,16 +139,19 @@ void unit_root(int64_t k, int64_t N, double* re, double* im) {
   *im = (double)(-sr);  // exp(-i theta)
 }
 
-std::vector<double> stage_table(const SubPlan& sp, int s) {
-  // tw[np*(R-1) + p-1] = exp(-2 pi i np p / len_s)
+std::vector<double> stage_table(const SubPlan& sp, int s, bool transposed) {
+  // power-of-two twiddles exp(-2 pi i np 2^k / len_s), k < NB, at [np*NB + k] (column pass) or
+  // [k*stride + np] (row pass); fft_fixed.cuh:fx_twiddles builds the other powers from them
   const int R = sp.radix[s], st = sp.stride[s], len = sp.len[s];
-  std::vector<double> t(2 * (size_t)st * (R - 1));
+  const int NB = R > 8 ? 4 : R > 4 ? 3 : R > 2 ? 2 : 1;
+  std::vector<double> t(2 * (size_t)st * NB);
   for (int np = 0; np < st; ++np)
-    for (int p = 1; p < R; ++p) {
+    for (int k = 0; k < NB; ++k) {
       double re, im;
-      unit_root((int64_t)np * p, len, &re, &im);
-      t[2 * ((size_t)np * (R - 1) + p - 1)] = re;
-      t[2 * ((size_t)np * (R - 1) + p - 1) + 1] = im;
+      unit_root((int64_t)np * (1 << k), len, &re, &im);
+      const size_t i = transposed ? (size_t)k * st + np : (size_t)np * NB + k;
+      t[2 * i] = re;
+      t[2 * i + 1] = im;
     }
   return t;
 }

@@ -52,7 +52,7 @@ def test_planner_headline_and_exact_sizes():
     # 6.15 s @ 48 kHz: L = 391270, M = 295270 -> circular length >= L + ceil((M-1)/2) = 538905
     rc, n1, n2, rcol, rrow = _probe(391270 + (295270 - 1) - (295270 - 1) // 2, 0)
     assert rc == 0 and n1 * n2 >= 538905 and (n1, n2) == (768, 768)
-    assert rcol == [12, 8, 8] and rrow == [12, 8, 8]
+    assert rcol == [8, 12, 8] and rrow == [8, 12, 8]
     for n in (19200, 65536, 9600, 32768, 21600, 22500, 57600, 96000, 84375):
         rc, n1, n2, rcol, rrow = _probe(n, 1)
         assert rc == 0 and n1 * n2 == n, n
