@@ -34,9 +34,9 @@ SIGNATURES = {
     "impb_deconv_execute": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64,
                                     c_vp, c_vp]),
     "impb_deconv_launches_per_execute": (c_i32, [c_vp, c_i64]),
-    "impb_peak_index": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_i64, c_i64, c_vp]),
-    "impb_lundeby": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
-    "impb_xcorr_lag": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "impb_peak_index": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_i64, c_i64, c_vp]),
+    "impb_lundeby": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "impb_xcorr_lag": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "impb_gather_window": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp,
                                    c_i64, c_i64, c_vp]),
     "impb_fft_create": (c_i32, [c_vp, c_i64, c_i32, C.POINTER(c_vp)]),
@@ -56,6 +56,11 @@ SIGNATURES = {
     "impb_window_resample": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_i64,
                                      c_i64, c_vp]),
 }
+
+
+class View(C.Structure):
+    """``impb_view`` of include/impb.h (all members optional)."""
+    _fields_ = [("shift", c_vp), ("valid_lo", c_vp), ("valid_hi", c_vp), ("fade_in", c_vp), ("fade_in_len", c_i64)]
 
 
 class ImpbError(RuntimeError):

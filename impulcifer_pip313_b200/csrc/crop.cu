@@ -20,6 +20,41 @@ namespace {
 constexpr double kEps = 1e-20;
 constexpr unsigned long long kNoIndex = 0xFFFFFFFFFFFFFFFFull;
 
+// A "view" of one response: the array the reference would hold after head crop, fade-in and a chain of
+// length-preserving shifts, expressed as index arithmetic over the untouched source (no materialised copy):
+//   v[j] = fade(j - shift) * src[start + j - shift]   for lo <= j < hi,   0 elsewhere      (0 <= j < n)
+struct ViewArgs {
+  const int64_t* offsets;  // start of row r in x (after the head crop)
+  const int64_t* lengths;  // logical length n of row r
+  const int64_t* shift;    // nullable
+  const int64_t* lo;       // nullable
+  const int64_t* hi;       // nullable
+  const double* fade;      // nullable: rising half window applied to source index m < fade_len
+  int64_t fade_len;
+};
+
+struct RowView {
+  const double* p;
+  int64_t n, sh, lo, hi, fade_len;
+  const double* fade;
+  __device__ __forceinline__ RowView(const double* x, const ViewArgs& a, int64_t r) {
+    p = x + a.offsets[r];
+    n = a.lengths[r];
+    sh = a.shift ? a.shift[r] : 0;
+    lo = a.lo ? a.lo[r] : 0;
+    hi = a.hi ? a.hi[r] : n;
+    fade = a.fade;
+    fade_len = a.fade ? a.fade_len : 0;
+  }
+  __device__ __forceinline__ double operator[](int64_t j) const {
+    if (j < lo || j >= hi) return 0.0;
+    const int64_t m = j - sh;
+    double v = p[m];
+    if (m < fade_len) v = __dmul_rn(v, fade[m]);
+    return v;
+  }
+};
+
 struct PeakScratch {
   unsigned long long max_bits;  // bits of max |x| (non-negative doubles order like integers)
   unsigned long long first_peak;
@@ -35,11 +70,11 @@ __global__ void k_peak_init(PeakScratch* s, int64_t batch) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_absmax(const double* __restrict__ x, const int64_t* __restrict__ offsets,
-                                                const int64_t* __restrict__ lengths, PeakScratch* __restrict__ s) {
+__global__ void __launch_bounds__(256) k_absmax(const double* __restrict__ x, const ViewArgs va, int64_t r0,
+                                                PeakScratch* __restrict__ s) {
   const int r = blockIdx.y;
-  const int64_t n = lengths[r];
-  const double* p = x + offsets[r];
+  const RowView p(x, va, r0 + r);
+  const int64_t n = p.n;
   double m = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     m = fmax(m, fabs(p[i]));
@@ -54,7 +89,7 @@ __global__ void __launch_bounds__(256) k_absmax(const double* __restrict__ x, co
 }
 
 // candidate test for sample i of the normalised signal q = sign * x / m (scipy _local_maxima_1d semantics)
-__device__ __forceinline__ bool peak_at(const double* p, int64_t n, int64_t i, double m, double sign, double height,
+__device__ __forceinline__ bool peak_at(const RowView& p, int64_t n, int64_t i, double m, double sign, double height,
                                         int64_t* mid) {
   const double qi = sign * __ddiv_rn(p[i], m);
   if (!(qi >= height)) return false;
@@ -72,12 +107,11 @@ __device__ __forceinline__ bool peak_at(const double* p, int64_t n, int64_t i, d
   return true;
 }
 
-__global__ void __launch_bounds__(256) k_first_peak(const double* __restrict__ x, const int64_t* __restrict__ offsets,
-                                                    const int64_t* __restrict__ lengths, double height,
-                                                    PeakScratch* __restrict__ s) {
+__global__ void __launch_bounds__(256) k_first_peak(const double* __restrict__ x, const ViewArgs va, int64_t r0,
+                                                    double height, PeakScratch* __restrict__ s) {
   const int r = blockIdx.y;
-  const int64_t n = lengths[r];
-  const double* p = x + offsets[r];
+  const RowView p(x, va, r0 + r);
+  const int64_t n = p.n;
   const double m = __longlong_as_double((long long)s[r].max_bits);
   if (!(m >= kEps)) return;
   const double guard = 0.999 * height * m;
@@ -106,8 +140,8 @@ __global__ void k_peak_final(const PeakScratch* __restrict__ s, int64_t* __restr
   out[i] = r;
 }
 
-int run_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths, double height,
-                   int64_t* peak_out, int64_t batch, int64_t max_len_hint, cudaStream_t st) {
+int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double height, int64_t* peak_out, int64_t batch,
+                   int64_t max_len_hint, cudaStream_t st) {
   PeakScratch* scratch = nullptr;
   IMPB_CUDA(cudaMallocAsync(&scratch, sizeof(PeakScratch) * batch, st));
   const int thr = 256;
@@ -118,8 +152,8 @@ int run_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = (int)std::min<int64_t>(65535, batch - b0);
     dim3 grid((unsigned)per_seg, nb);
-    k_absmax<<<grid, thr, 0, st>>>(x, offsets + b0, lengths + b0, scratch + b0);
-    k_first_peak<<<grid, thr, 0, st>>>(x, offsets + b0, lengths + b0, height, scratch + b0);
+    k_absmax<<<grid, thr, 0, st>>>(x, va, b0, scratch + b0);
+    k_first_peak<<<grid, thr, 0, st>>>(x, va, b0, height, scratch + b0);
   }
   k_peak_final<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, peak_out, batch);
   IMPB_CUDA(cudaGetLastError());
@@ -162,12 +196,14 @@ __device__ __forceinline__ double block_max(double v, LundebyShared& sh) {
   return t;
 }
 
-struct SqView {  // squared, peak-normalised analysis segment  sq[i] = (x[pk+i] / mx)^2
-  const double* p;
+struct SqView {  // squared, peak-normalised analysis segment  sq[i] = (v[pk+i] / mx)^2
+  const RowView* p;
+  int64_t pk;
   double mx;
   bool norm;
   __device__ __forceinline__ double operator()(int64_t i) const {
-    const double v = norm ? __ddiv_rn(p[i], mx) : p[i];
+    const double s = (*p)[pk + i];
+    const double v = norm ? __ddiv_rn(s, mx) : s;
     return __dmul_rn(v, v);
   }
 };
@@ -232,15 +268,14 @@ __device__ int64_t nearest_t(double t, double step, int64_t ns) {
   return best;
 }
 
-__global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict__ x, const int64_t* __restrict__ offsets,
-                                                        const int64_t* __restrict__ lengths, int fs,
+__global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict__ x, const ViewArgs va, int64_t r0, int fs,
                                                         const int64_t* __restrict__ peaks, int64_t* __restrict__ peak_out,
                                                         int64_t* __restrict__ knee_out, double* __restrict__ noise_out,
                                                         int64_t* __restrict__ win_out) {
   __shared__ LundebyShared sh;
   const int r = blockIdx.x;
-  const int64_t n_ir = lengths[r];
-  const double* ir = x + offsets[r];
+  const RowView ir(x, va, r0 + r);
+  const int64_t n_ir = ir.n;
   const bool lead = threadIdx.x == 0;
 #define LB_RETURN(pk_, knee_, noise_, w_)                                                    \
   do {                                                                                       \
@@ -252,11 +287,10 @@ __global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict
   const int64_t pk = peaks[r];
   const int64_t stop = min(pk + (int64_t)(2 * fs), n_ir);
   const int64_t ns = stop - pk;  // >= 1 because pk <= n_ir - 1
-  const double* seg = ir + pk;
   double mx = 0.0;
-  for (int64_t i = threadIdx.x; i < ns; i += LB_THREADS) mx = fmax(mx, fabs(seg[i]));
+  for (int64_t i = threadIdx.x; i < ns; i += LB_THREADS) mx = fmax(mx, fabs(ir[pk + i]));
   mx = block_max(mx, sh);
-  SqView sq{seg, mx, mx >= kEps};
+  SqView sq{&ir, pk, mx, mx >= kEps};
   const double step = ns > 1 ? ((double)ns / (double)fs) / (double)(ns - 1) : 0.0;  // linspace(0, ns/fs, ns)
   const double t_last = (double)(ns - 1) * step;
 
@@ -420,14 +454,22 @@ __global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_xcorr(const double* __restrict__ x, const int64_t* __restrict__ a_off,
                                                const int64_t* __restrict__ a_len, const int64_t* __restrict__ b_off,
-                                               const int64_t* __restrict__ b_len, int64_t* __restrict__ lag_out) {
+                                               const int64_t* __restrict__ b_len, const double* __restrict__ fade,
+                                               int64_t fade_len, int64_t* __restrict__ lag_out) {
   extern __shared__ double smx[];
   const int r = blockIdx.x;
   const int na = (int)a_len[r], nb = (int)b_len[r];
   double* a = smx;
   double* b = smx + na;
-  for (int i = threadIdx.x; i < na; i += blockDim.x) a[i] = x[a_off[r] + i];
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) b[i] = x[b_off[r] + i];
+  // segments start at the head of a cropped response: the fade-in of crop_heads applies to their first samples
+  for (int i = threadIdx.x; i < na; i += blockDim.x) {
+    double v = x[a_off[r] + i];
+    a[i] = (fade && i < fade_len) ? __dmul_rn(v, fade[i]) : v;
+  }
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    double v = x[b_off[r] + i];
+    b[i] = (fade && i < fade_len) ? __dmul_rn(v, fade[i]) : v;
+  }
   __syncthreads();
   // z[k] = sum_l a[l] * b[l - k + nb - 1],  k in [0, na + nb - 1)
   double best = -DBL_MAX;
@@ -490,21 +532,34 @@ __global__ void __launch_bounds__(256) k_gather_window(const double* __restrict_
 
 extern "C" {
 
-int32_t impb_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths, double height,
-                        int64_t* peak_out, int64_t batch, int64_t max_len, void* stream) {
-  if (!ctx || !x || !offsets || !lengths || !peak_out || batch < 0) {
+static ViewArgs make_view(const int64_t* offsets, const int64_t* lengths, const impb_view* v) {
+  ViewArgs a{offsets, lengths, nullptr, nullptr, nullptr, nullptr, 0};
+  if (v) {
+    a.shift = v->shift;
+    a.lo = v->valid_lo;
+    a.hi = v->valid_hi;
+    a.fade = v->fade_in_len > 0 ? v->fade_in : nullptr;
+    a.fade_len = v->fade_in_len;
+  }
+  return a;
+}
+
+int32_t impb_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,
+                        const impb_view* view, double height, int64_t* peak_out, int64_t batch, int64_t max_len,
+                        void* stream) {
+  if (!ctx || !x || !offsets || !lengths || !peak_out || batch < 0 || !(height > 0.0)) {
     set_error("impb_peak_index: bad argument");
     return IMPB_EINVAL;
   }
   if (batch == 0) return IMPB_OK;
   DeviceGuard g(ctx->device);
-  return run_peak_index(ctx, x, offsets, lengths, height, peak_out, batch, std::max<int64_t>(max_len, 1),
-                        (cudaStream_t)stream);
+  return run_peak_index(ctx, x, make_view(offsets, lengths, view), height, peak_out, batch,
+                        std::max<int64_t>(max_len, 1), (cudaStream_t)stream);
 }
 
-int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths, int32_t fs,
-                     int64_t* peak_out, int64_t* knee_out, double* noise_db_out, int64_t* win_out, int64_t batch,
-                     int64_t max_len, void* stream) {
+int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,
+                     const impb_view* view, int32_t fs, int64_t* peak_out, int64_t* knee_out, double* noise_db_out,
+                     int64_t* win_out, int64_t batch, int64_t max_len, void* stream) {
   if (!ctx || !x || !offsets || !lengths || !peak_out || !knee_out || !noise_db_out || !win_out || batch < 0 ||
       fs <= 0) {
     set_error("impb_lundeby: bad argument");
@@ -515,12 +570,13 @@ int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, con
   cudaStream_t st = (cudaStream_t)stream;
   int64_t* peaks = nullptr;
   IMPB_CUDA(cudaMallocAsync(&peaks, sizeof(int64_t) * batch, st));
-  int rc = run_peak_index(ctx, x, offsets, lengths, 0.12589, peaks, batch, std::max<int64_t>(max_len, 1), st);
+  const ViewArgs va = make_view(offsets, lengths, view);
+  int rc = run_peak_index(ctx, x, va, 0.12589, peaks, batch, std::max<int64_t>(max_len, 1), st);
   if (!rc) {
     for (int64_t b0 = 0; b0 < batch && !rc; b0 += 1 << 30) {
       const int64_t nb = std::min<int64_t>((int64_t)1 << 30, batch - b0);
-      k_lundeby<<<(unsigned)nb, LB_THREADS, 0, st>>>(x, offsets + b0, lengths + b0, fs, peaks + b0, peak_out + b0,
-                                                    knee_out + b0, noise_db_out + b0, win_out + b0);
+      k_lundeby<<<(unsigned)nb, LB_THREADS, 0, st>>>(x, va, b0, fs, peaks + b0, peak_out + b0, knee_out + b0,
+                                                    noise_db_out + b0, win_out + b0);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = cuda_fail(e, "k_lundeby");
@@ -530,8 +586,8 @@ int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, con
 }
 
 int32_t impb_xcorr_lag(impb_ctx* ctx, const double* x, const int64_t* a_offsets, const int64_t* a_lengths,
-                       const int64_t* b_offsets, const int64_t* b_lengths, int64_t* lag_out, int64_t batch,
-                       int64_t max_seg_len, void* stream) {
+                       const int64_t* b_offsets, const int64_t* b_lengths, const double* fade_in, int64_t fade_in_len,
+                       int64_t* lag_out, int64_t batch, int64_t max_seg_len, void* stream) {
   if (!ctx || !x || !a_offsets || !a_lengths || !b_offsets || !b_lengths || !lag_out || batch < 0 || max_seg_len < 0) {
     set_error("impb_xcorr_lag: bad argument");
     return IMPB_EINVAL;
@@ -544,7 +600,8 @@ int32_t impb_xcorr_lag(impb_ctx* ctx, const double* x, const int64_t* a_offsets,
   }
   DeviceGuard g(ctx->device);
   IMPB_CUDA(cudaFuncSetAttribute(k_xcorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_xcorr<<<(unsigned)batch, 256, smem, (cudaStream_t)stream>>>(x, a_offsets, a_lengths, b_offsets, b_lengths, lag_out);
+  k_xcorr<<<(unsigned)batch, 256, smem, (cudaStream_t)stream>>>(x, a_offsets, a_lengths, b_offsets, b_lengths,
+                                                                fade_in_len > 0 ? fade_in : nullptr, fade_in_len, lag_out);
   IMPB_CUDA(cudaGetLastError());
   return IMPB_OK;
 }

@@ -271,6 +271,13 @@ int32_t impb_ctx_create(int32_t device, impb_ctx** out) {
                     prop.minor);
     return IMPB_EUNSUPPORTED;
   }
+  // stream-ordered scratch (cudaMallocAsync) must stay cached across synchronisation points: with the default
+  // release threshold of 0 every host sync returns the pool to the OS and the next launch pays a real allocation
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   impb_ctx* c = new impb_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;

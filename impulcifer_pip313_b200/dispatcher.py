@@ -169,11 +169,10 @@ class BatchDispatcher:
             crop[:, lay['right']] = crop_sp
             crop = crop.reshape(-1)
             n1 = L - crop
-            window_in = hann(head * 2)[:head]
-            X1 = ops.gather_window(flatE, rows * L + crop, L, valid_hi=n1, fade_in=window_in)
-            launches += 1
-            del E, flatE
-            flat1 = X1.reshape(-1)
+            off1 = rows * L + crop
+            # From here on nothing is materialised: the cropped, faded and shifted responses are VIEWS over E
+            # (impb_view: start offset, composite shift, surviving index range, fade-in table).
+            window_in = hann(head * 2)[:head] if head > 0 else None
             # 3. ipsilateral onset alignment (ref :921-955): lag of the first 30 ms, K6
             seg = int(fs * self.segment_ms / 1000)
             shift = torch.zeros((S, n), device=dev, dtype=torch.int64)
@@ -183,7 +182,7 @@ class BatchDispatcher:
                 rb = (set_base * n + lay['pb'][None, :]).reshape(-1)
                 la = torch.clamp(n1v[:, lay['pa']], max=seg).reshape(-1)
                 lb = torch.clamp(n1v[:, lay['pb']], max=seg).reshape(-1)
-                lags = ops.xcorr_lag(flat1, ra * L, la, rb * L, lb, max_seg_len=seg).view(S, -1)
+                lags = ops.xcorr_lag(flatE, off1[ra], la, off1[rb], lb, max_seg_len=seg, fade_in=window_in).view(S, -1)
                 launches += 1
                 for k, (a, b) in enumerate(lay['pairs']):
                     lag = lags[:, k]
@@ -195,15 +194,16 @@ class BatchDispatcher:
                         for sd in ('left', 'right'):
                             shift[:, lay['row_of'][f"{b}-{sd}"]] += pos
                             shift[:, lay['row_of'][f"{a}-{sd}"]] += neg
-            X2 = self._shift(flat1, rows, L, n1, shift.reshape(-1))
-            launches += 1
-            del X1, flat1
-            flat2 = X2.reshape(-1)
-            # 4. group onset alignment against FL-left (ref :957-1001), K2 on the group leaders
+            shift = shift.reshape(-1)
+            lo = torch.clamp(shift, min=0)
+            hi = torch.maximum(torch.minimum(n1 + shift, n1), lo)
+            # 4. group onset alignment against FL-left (ref :957-1001): K2 on the shifted views of the leaders
             shift2 = torch.zeros((S, n), device=dev, dtype=torch.int64)
             if 'FL' in lay['speakers'] and len(lay['groups']) > 1:
                 rg = (set_base * n + lay['gl'][None, :]).reshape(-1)
-                gp = ops.peak_index(flat2, rg * L, n1[rg], max_len=L).view(S, -1)
+                gp = ops.peak_index(flatE, off1[rg], n1[rg], max_len=L,
+                                    view=dict(shift=shift[rg], valid_lo=lo[rg], valid_hi=hi[rg],
+                                              fade_in=window_in)).view(S, -1)
                 launches += 4
                 ref_col = [i for i, g in enumerate(lay['groups']) if g[0] == 'FL'][0]
                 for gi, g in enumerate(lay['groups']):
@@ -216,12 +216,14 @@ class BatchDispatcher:
                                 shift2[:, lay['row_of'][f"{spk}-{sd}"]] -= d
             elif 'FL' not in lay['speakers']:
                 raise RuntimeError("Cannot find FL left channel reference for onset alignment.")
-            X3 = self._shift(flat2, rows, L, n1, shift2.reshape(-1))
-            launches += 1
-            del X2, flat2
-            flat3 = X3.reshape(-1)
+            shift2 = shift2.reshape(-1)
+            # two length-preserving shifts compose into one shift plus a surviving range
+            total = shift + shift2
+            lo = torch.clamp(lo + shift2, min=0)
+            hi = torch.maximum(torch.minimum(hi + shift2, n1), lo)
+            view = dict(shift=total, valid_lo=lo, valid_hi=hi, fade_in=window_in)
             # 5. Lundeby knee per response (K4) -> per-set tail index (ref :614-653): the one host sync
-            _, knee, _, _ = ops.lundeby(flat3, rows * L, n1, fs, max_len=L)
+            _, knee, _, _ = ops.lundeby(flatE, off1, n1, fs, max_len=L, view=view)
             launches += 5
             host = torch.stack([knee, n1, peaks, crop]).cpu().numpy()
             knees_h, n1_h, peaks_h, crop_h = (host[i].reshape(S, n) for i in range(4))
@@ -238,7 +240,8 @@ class BatchDispatcher:
                 sets = [s for s in range(S) if tails[s] == tail]
                 sel = (torch.as_tensor(sets, device=dev, dtype=torch.int64)[:, None] * n +
                        torch.arange(n, device=dev, dtype=torch.int64)[None, :]).reshape(-1)
-                out = ops.gather_window(flat3, sel * L, tail, fade_out=window_out).view(len(sets), n, tail)
+                out = ops.gather_window(flatE, off1[sel], tail, shift=total[sel], valid_lo=lo[sel], valid_hi=hi[sel],
+                                        fade_in=window_in, fade_out=window_out).view(len(sets), n, tail)
                 launches += 1
                 for k, s in enumerate(sets):
                     results[s] = SetResult(lay['names'], out[k], tail, peaks_h[s], crop_h[s], knees_h[s],
@@ -246,13 +249,59 @@ class BatchDispatcher:
         self.launches = launches
         return results
 
-    @staticmethod
-    def _shift(flat, rows, L, n1, shift):
-        """Length-preserving shift of every row (its own length n1), zero padded to L."""
+    # ---- host buffers in, host buffers out ------------------------------------------------------------------
+    def process_host(self, recordings, out=None, chunk_sets=8, precision=None):
+        """``process`` for recordings that live in (pinned) HOST memory: ``[S, n_tracks, n_samples]`` float64,
+        float32 or int32 PCM (the samples of a PCM WAV exactly as stored; scaled by 2^-31 inside K1).
+
+        The sets are cut into chunks; the H2D copy of chunk k+1 (copy stream), the kernels of chunk k (compute
+        stream) and the D2H copy of the cropped responses of chunk k-1 (third stream) overlap.  Returns the list of
+        ``SetResult`` with ``data`` in host memory (views of ``out`` if a pinned float64 buffer is passed)."""
         import torch
-        lo = torch.clamp(shift, min=0)
-        hi = torch.maximum(torch.minimum(n1 + shift, n1), lo)
-        return ops.gather_window(flat, rows * L, L, shift=shift, valid_lo=lo, valid_hi=hi)
+        S = recordings.shape[0]
+        dev = torch.device("cuda", self.estimator.device)
+        key = (tuple(recordings.shape), recordings.dtype, chunk_sets)
+        st = getattr(self, "_host_state", None)
+        if st is None or st['key'] != key:
+            st = dict(key=key, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
+                      stage=torch.empty(recordings.shape, dtype=recordings.dtype, device=dev))
+            self._host_state = st
+        stage, h2d, d2h = st['stage'], st['h2d'], st['d2h']
+        compute = torch.cuda.current_stream(dev)
+        bounds = [(a, min(a + chunk_sets, S)) for a in range(0, S, chunk_sets)]
+        h2d.wait_stream(compute)  # the staging buffer may still be read by the previous call
+        ready = []
+        with torch.cuda.stream(h2d):
+            for a, b in bounds:
+                stage[a:b].copy_(recordings[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(h2d)
+                ready.append(ev)
+        results, off, launches = [], 0, 0
+        done = []
+        for (a, b), ev in zip(bounds, ready):
+            compute.wait_event(ev)
+            part = self.process(stage[a:b], precision)
+            launches += self.launches
+            fin = torch.cuda.Event()
+            fin.record(compute)
+            d2h.wait_event(fin)
+            with torch.cuda.stream(d2h):
+                for r in part:
+                    n = r.data.numel()
+                    if out is not None:
+                        host = out[off:off + n].view(r.data.shape)
+                    else:
+                        host = torch.empty(r.data.shape, dtype=r.data.dtype).pin_memory()
+                    host.copy_(r.data, non_blocking=True)
+                    r.data.record_stream(d2h)
+                    r.data = host
+                    off += n
+            results += part
+        d2h.synchronize()
+        self.launches = launches
+        self.host_bytes_out = off * 8
+        return results
 
     def _side_warnings(self, lay, peaks):
         msgs = []

@@ -43,8 +43,43 @@ def as_index_tensor(values, device):
 
 
 # ---- K2 -------------------------------------------------------------------------------------------
-def peak_index(x, offsets, lengths, height=0.12589, max_len=None):
-    """First-peak index of every segment ``x[offsets[r] : offsets[r]+lengths[r]]`` (relative to the segment)."""
+_win_cache = {}
+
+
+def _dev_window(win, device):
+    """Small host-built window -> cached device tensor (keyed by content)."""
+    torch = _torch()
+    if win is None or isinstance(win, torch.Tensor):
+        return win
+    arr = np.ascontiguousarray(win, dtype=np.float64)
+    if arr.size == 0:
+        return None
+    key = (arr.tobytes(), str(device))
+    t = _win_cache.get(key)
+    if t is None:
+        if len(_win_cache) > 64:
+            _win_cache.clear()
+        t = _win_cache[key] = torch.as_tensor(arr, device=device)
+    return t
+
+
+def make_view(device, shift=None, valid_lo=None, valid_hi=None, fade_in=None):
+    """(ctypes impb_view or None, keep-alive tensors).  See include/impb.h."""
+    if shift is None and valid_lo is None and valid_hi is None and fade_in is None:
+        return None, ()
+    sh = None if shift is None else as_index_tensor(shift, device)
+    lo = None if valid_lo is None else as_index_tensor(valid_lo, device)
+    hi = None if valid_hi is None else as_index_tensor(valid_hi, device)
+    fi = _dev_window(fade_in, device)
+    v = _lib.View(None if sh is None else sh.data_ptr(), None if lo is None else lo.data_ptr(),
+                  None if hi is None else hi.data_ptr(), None if fi is None else fi.data_ptr(),
+                  0 if fi is None else fi.numel())
+    return v, (sh, lo, hi, fi)
+
+
+def peak_index(x, offsets, lengths, height=0.12589, max_len=None, view=None):
+    """First-peak index of every segment ``x[offsets[r] : offsets[r]+lengths[r]]`` (relative to the segment).
+    ``view`` = dict(shift=, valid_lo=, valid_hi=, fade_in=) evaluates it on the shifted / faded view instead."""
     torch = _torch()
     x = x.contiguous()
     assert x.dtype == torch.float64 and x.is_cuda
@@ -54,15 +89,17 @@ def peak_index(x, offsets, lengths, height=0.12589, max_len=None):
     out = torch.empty(batch, dtype=torch.int64, device=x.device)
     if max_len is None:
         max_len = int(lengths.max().item()) if batch else 0
+    v, keep = make_view(x.device, **(view or {}))
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().impb_peak_index(_lib.context(_dev(x)).handle, x.data_ptr(), _i64(offsets), _i64(lengths),
-                                              float(height), out.data_ptr(), batch, int(max_len), _stream(x)),
-                   "impb_peak_index")
+                                              None if v is None else C.addressof(v), float(height), out.data_ptr(),
+                                              batch, int(max_len), _stream(x)), "impb_peak_index")
+    del keep
     return out
 
 
 # ---- K4 -------------------------------------------------------------------------------------------
-def lundeby(x, offsets, lengths, fs, max_len=None):
+def lundeby(x, offsets, lengths, fs, max_len=None, view=None):
     """decay_params of every segment -> (peak, knee, noise_db, window) tensors (indices relative to the segment)."""
     torch = _torch()
     x = x.contiguous()
@@ -76,15 +113,18 @@ def lundeby(x, offsets, lengths, fs, max_len=None):
     noise = torch.empty(batch, dtype=torch.float64, device=x.device)
     if max_len is None:
         max_len = int(lengths.max().item()) if batch else 0
+    v, keep = make_view(x.device, **(view or {}))
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().impb_lundeby(_lib.context(_dev(x)).handle, x.data_ptr(), _i64(offsets), _i64(lengths),
-                                           int(fs), peak.data_ptr(), knee.data_ptr(), noise.data_ptr(), win.data_ptr(),
-                                           batch, int(max_len), _stream(x)), "impb_lundeby")
+                                           None if v is None else C.addressof(v), int(fs), peak.data_ptr(),
+                                           knee.data_ptr(), noise.data_ptr(), win.data_ptr(), batch, int(max_len),
+                                           _stream(x)), "impb_lundeby")
+    del keep
     return peak, knee, noise, win
 
 
 # ---- K6 -------------------------------------------------------------------------------------------
-def xcorr_lag(x, a_offsets, a_lengths, b_offsets, b_lengths, max_seg_len=None):
+def xcorr_lag(x, a_offsets, a_lengths, b_offsets, b_lengths, max_seg_len=None, fade_in=None):
     torch = _torch()
     x = x.contiguous()
     a_offsets, a_lengths = as_index_tensor(a_offsets, x.device), as_index_tensor(a_lengths, x.device)
@@ -93,10 +133,12 @@ def xcorr_lag(x, a_offsets, a_lengths, b_offsets, b_lengths, max_seg_len=None):
     out = torch.empty(batch, dtype=torch.int64, device=x.device)
     if max_seg_len is None:
         max_seg_len = int(max(a_lengths.max().item(), b_lengths.max().item())) if batch else 0
+    fi = _dev_window(fade_in, x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().impb_xcorr_lag(_lib.context(_dev(x)).handle, x.data_ptr(), _i64(a_offsets),
-                                             _i64(a_lengths), _i64(b_offsets), _i64(b_lengths), out.data_ptr(), batch,
-                                             int(max_seg_len), _stream(x)), "impb_xcorr_lag")
+                                             _i64(a_lengths), _i64(b_offsets), _i64(b_lengths),
+                                             None if fi is None else fi.data_ptr(), 0 if fi is None else fi.numel(),
+                                             out.data_ptr(), batch, int(max_seg_len), _stream(x)), "impb_xcorr_lag")
     return out
 
 
@@ -113,8 +155,8 @@ def gather_window(src, src_start, out_len, shift=None, valid_lo=None, valid_hi=N
     shift_t = None if shift is None else as_index_tensor(shift, dev)
     lo_t = None if valid_lo is None else as_index_tensor(valid_lo, dev)
     hi_t = None if valid_hi is None else as_index_tensor(valid_hi, dev)
-    fi = None if fade_in is None or len(fade_in) == 0 else torch.as_tensor(np.asarray(fade_in, np.float64), device=dev)
-    fo = None if fade_out is None or len(fade_out) == 0 else torch.as_tensor(np.asarray(fade_out, np.float64), device=dev)
+    fi = _dev_window(fade_in, dev)
+    fo = _dev_window(fade_out, dev)
     if out is None:
         out = torch.empty((batch, int(out_len)), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):

@@ -43,6 +43,18 @@ typedef struct impb_ctx impb_ctx;
 typedef struct impb_plan impb_plan;
 typedef struct impb_fft impb_fft;
 
+/* Optional per-row "view" for the crop/align kernels: the array the reference would hold after crop_heads'
+ * fade-in and a chain of ImpulseResponse.shift calls, as index arithmetic over the untouched samples
+ *   v[j] = fade_in[j - shift] * x[offset + j - shift]   for valid_lo <= j < valid_hi,   0 elsewhere
+ * (fade_in applies where j - shift < fade_in_len).  Every pointer may be NULL (no shift / all valid / no fade). */
+typedef struct impb_view {
+  const int64_t* shift;
+  const int64_t* valid_lo;
+  const int64_t* valid_hi;
+  const double* fade_in;
+  int64_t fade_in_len;
+} impb_view;
+
 IMPB_API uint32_t impb_version(void);
 IMPB_API int32_t impb_ctx_create(int32_t device, impb_ctx** out);
 IMPB_API void impb_ctx_destroy(impb_ctx* ctx);
@@ -79,22 +91,24 @@ IMPB_API int32_t impb_deconv_launches_per_execute(const impb_plan* plan, int64_t
  * x[offsets[r] : offsets[r] + lengths[r]]; peak_out[r] is relative to the segment start; max_len = the
  * longest segment (grid sizing only); height must be > 0.  Bit-exact. */
 IMPB_API int32_t impb_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,
-                        double height, int64_t* peak_out, int64_t batch, int64_t max_len, void* stream);
+                        const impb_view* view, double height, int64_t* peak_out, int64_t batch, int64_t max_len,
+                        void* stream);
 
 /* ---- K4: Lundeby decay parameters ----------------------------------------------------------------
  * Replaces decay.decay_params(), core/decay.py:44-260 (called by HRIR.crop_tails, core/hrir.py:627-636).
  * peak_out / knee_out are relative to the segment start. */
-IMPB_API int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths, int32_t fs,
-                     int64_t* peak_out, int64_t* knee_out, double* noise_db_out, int64_t* win_out,
-                     int64_t batch, int64_t max_len, void* stream);
+IMPB_API int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,
+                     const impb_view* view, int32_t fs, int64_t* peak_out, int64_t* knee_out, double* noise_db_out,
+                     int64_t* win_out, int64_t batch, int64_t max_len, void* stream);
 
 /* ---- K6: onset cross-correlation lag ---------------------------------------------------------------
  * Replaces the scipy.signal.correlate(..., 'full') + argmax of HRIR.align_ipsilateral_all,
  * core/hrir.py:932-948.  a, b: [batch] segments of x given by offsets/lengths (<= max_seg_len samples);
- * lag_out[r] = np.arange(-len(a)+1, len(a))[np.argmax(correlate(a, b, 'full'))], first maximum on ties. */
+ * lag_out[r] = np.arange(-len(a)+1, len(a))[np.argmax(correlate(a, b, 'full'))], first maximum on ties.
+ * fade_in (nullable): crop_heads' rising window, applied to the first fade_in_len samples of both segments. */
 IMPB_API int32_t impb_xcorr_lag(impb_ctx* ctx, const double* x, const int64_t* a_offsets, const int64_t* a_lengths,
-                       const int64_t* b_offsets, const int64_t* b_lengths, int64_t* lag_out, int64_t batch,
-                       int64_t max_seg_len, void* stream);
+                       const int64_t* b_offsets, const int64_t* b_lengths, const double* fade_in,
+                       int64_t fade_in_len, int64_t* lag_out, int64_t batch, int64_t max_seg_len, void* stream);
 
 /* ---- K3+K5+K7+K16: fused gather / window --------------------------------------------------------------
  * Replaces the slicing, ImpulseResponse.shift (core/impulse_response.py:92-108), Hann fade-in of
