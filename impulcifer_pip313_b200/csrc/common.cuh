@@ -60,7 +60,7 @@ struct Plan2D {
 };
 // smallest-cost N = N1*N2 >= n_min (exact = true: N must equal n_min) for element type of `elem_bytes`
 // (8 = double, 4 = float); false if impossible.
-bool plan_2d(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, Plan2D* out);
+bool plan_2d(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, Plan2D* out, bool allow_half_tile = false);
 
 // quarter-wave (or full) twiddle table of a sub-plan in double precision: (cos, sin) pairs
 std::vector<double> subplan_table(const SubPlan& sp);

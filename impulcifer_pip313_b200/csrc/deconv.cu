@@ -210,18 +210,23 @@ IMPB_FX_DISPATCH(fx_fwd_async, k_fx_fwd_async)
 IMPB_FX_DISPATCH(fx_inv, k_fx_inv)
 IMPB_FX_DISPATCH(fx_conv, k_fx_conv)
 
-template <typename T, int TILE> struct DeconvEngine {
+template <typename T> struct DeconvEngine {
   Fft2D<T> fft;
   cx_t<T>* hs = nullptr;
   int device = 0;
+  static constexpr int FULL = TileOf<T>::value;  // 8 (f64) / 16 (f32)
 
   int launch(const DeconvArgs<T>& a, int pairs, cudaStream_t st) const {
+    return fft.p.tile == FULL ? launch_t<FULL>(a, pairs, st) : launch_t<FULL / 2>(a, pairs, st);
+  }
+
+  template <int TILE> int launch_t(const DeconvArgs<T>& a, int pairs, cudaStream_t st) const {
     int rc;
     static const bool no_fixed = getenv("IMPB_NO_FIXED") != nullptr;
-    if (fft.col_fixed && fft.row_fixed && !no_fixed) {
+    if (TILE == FULL && fft.col_fixed && fft.row_fixed && !no_fixed) {
       const Plan2D& p = fft.p;
       static const bool no_async = getenv("IMPB_NO_ASYNC") != nullptr;
-      if constexpr (sizeof(T) == 8) {
+      if constexpr (sizeof(T) == 8 && TILE == FULL) {
         if (a.in_fmt == IMPB_FMT_F64 && !no_async) {
           rc = fx_fwd_async<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
                                      DeconvColIn<T, TILE, true>{a});
@@ -252,8 +257,8 @@ struct impb_plan {
   impb_ctx* ctx = nullptr;
   int precision = 64;
   int64_t M = 0, L = 0, s = 0;  // s = (M-1)/2: start of the 'same' slice in the full convolution
-  DeconvEngine<double, 8> e64;
-  DeconvEngine<float, 16> e32;
+  DeconvEngine<double> e64;
+  DeconvEngine<float> e32;
   int64_t chunk_pairs = 1;
   bool has64 = false, has32 = false;
 };
@@ -269,11 +274,11 @@ static int build_spectrum(impb_plan* pl, const double* inv_host) {
     f64 = &pl->e64.fft;
   } else {
     Plan2D pd = target;
-    pd.tile = 8;
+    pd.tile = target.tile / 2;  // the FP32 plan was derived from an FP64 plan of half its tile width
     pd.threads = 512;
-    if (!make_subplan(N1, 8, 512, &pd.col) || !make_subplan(N2, 8, 512, &pd.row)) return IMPB_EUNSUPPORTED;
-    pd.smem_col = tile_smem_bytes<double>(pd.col, 8);
-    pd.smem_row = tile_smem_bytes<double>(pd.row, 8);
+    if (!make_subplan(N1, pd.tile, 512, &pd.col) || !make_subplan(N2, pd.tile, 512, &pd.row)) return IMPB_EUNSUPPORTED;
+    pd.smem_col = tile_smem_bytes<double>(pd.col, pd.tile);
+    pd.smem_row = tile_smem_bytes<double>(pd.row, pd.tile);
     if (std::max(pd.smem_col, pd.smem_row) > pl->ctx->smem_optin) {
       set_error("FP32 plan %dx%d does not fit the FP64 spectrum builder", N1, N2);
       return IMPB_EUNSUPPORTED;
@@ -291,10 +296,13 @@ static int build_spectrum(impb_plan* pl, const double* inv_host) {
   DeconvArgs<double> a{};
   a.ws = ws; a.tw = f64->tw; a.hs = nullptr; a.N = (int64_t)N; a.N1 = N1; a.N2 = N2;
   a.rec = d_h; a.ld_in = pl->M; a.len = pl->M; a.nrows = 1; a.row0 = 0; a.in_fmt = IMPB_FMT_F64;
-  int rc = f64->col_fwd<8>(DeconvColIn<double, 8>{a}, 1, 0);
-  if (!rc) {
-    RowPlain<double, 8> rp{ws, ws, nullptr, (int64_t)N, N1, N2, 0, 0};
-    rc = f64->row_fwd<8>(rp, 1, 0);
+  int rc;
+  if (f64->p.tile == 8) {
+    rc = f64->col_fwd<8>(DeconvColIn<double, 8>{a}, 1, 0);
+    if (!rc) rc = f64->row_fwd<8>(RowPlain<double, 8>{ws, ws, nullptr, (int64_t)N, N1, N2, 0, 0}, 1, 0);
+  } else {
+    rc = f64->col_fwd<4>(DeconvColIn<double, 4>{a}, 1, 0);
+    if (!rc) rc = f64->row_fwd<4>(RowPlain<double, 4>{ws, ws, nullptr, (int64_t)N, N1, N2, 0, 0}, 1, 0);
   }
   if (!rc) {
     const int thr = 256;
@@ -302,18 +310,20 @@ static int build_spectrum(impb_plan* pl, const double* inv_host) {
     const double scale = 1.0 / (double)N;
     if (pl->precision == 64) {
       const int R = target.row.radix[target.row.nst - 1];
-      const size_t total = (size_t)((N1 + 7) / 8) * 8 * N2;
+      const int tl = target.tile;
+      const size_t total = (size_t)((N1 + tl - 1) / tl) * tl * N2;
       IMPB_CUDA(cudaMalloc(&pl->e64.hs, total * sizeof(double2)));
       k_spec_layout<double><<<(unsigned)((total + thr - 1) / thr), thr>>>(nat, pl->e64.hs, pl->e64.fft.perm_col,
-                                                                       pl->e64.fft.perm_row, N1, N2, 8, R, scale,
-                                                                       (pl->e64.fft.col_fixed && pl->e64.fft.row_fixed && !getenv("IMPB_NO_FIXED")) ? 1 : 0);
+                                                                       pl->e64.fft.perm_row, N1, N2, tl, R, scale,
+                                                                       (tl == 8 && pl->e64.fft.col_fixed && pl->e64.fft.row_fixed && !getenv("IMPB_NO_FIXED")) ? 1 : 0);
     } else {
       const int R = target.row.radix[target.row.nst - 1];
-      const size_t total = (size_t)((N1 + 15) / 16) * 16 * N2;
+      const int tl = target.tile;
+      const size_t total = (size_t)((N1 + tl - 1) / tl) * tl * N2;
       IMPB_CUDA(cudaMalloc(&pl->e32.hs, total * sizeof(float2)));
       k_spec_layout<float><<<(unsigned)((total + thr - 1) / thr), thr>>>(nat, pl->e32.hs, pl->e32.fft.perm_col,
-                                                                      pl->e32.fft.perm_row, N1, N2, 16, R, scale,
-                                                                      (pl->e32.fft.col_fixed && pl->e32.fft.row_fixed && !getenv("IMPB_NO_FIXED")) ? 1 : 0);
+                                                                      pl->e32.fft.perm_row, N1, N2, tl, R, scale,
+                                                                      (tl == 16 && pl->e32.fft.col_fixed && pl->e32.fft.row_fixed && !getenv("IMPB_NO_FIXED")) ? 1 : 0);
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) rc = cuda_fail(e, "inverse-filter spectrum build");
@@ -343,7 +353,7 @@ int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, in
   const int64_t n_min = std::max<int64_t>(std::max(L + (M - 1) - pl->s, pl->s + L), 16);
   Plan2D p;
   // both precisions are planned against the FP64 shared-memory limit (the spectrum is built in FP64)
-  if (!plan_2d(ctx, n_min, false, 8, &p)) {
+  if (!plan_2d(ctx, n_min, false, 8, &p, /*allow_half_tile=*/true)) {
     set_error("no 2-pass FFT plan for n >= %lld", (long long)n_min);
     delete pl;
     return IMPB_EUNSUPPORTED;
@@ -354,14 +364,14 @@ int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, in
     pl->has64 = true;
   } else {
     Plan2D pf = p;
-    pf.tile = 16;
+    pf.tile = 2 * p.tile;
     pf.threads = p.threads;
-    if (!make_subplan(p.N1, 16, pf.threads, &pf.col) || !make_subplan(p.N2, 16, pf.threads, &pf.row)) {
+    if (!make_subplan(p.N1, pf.tile, pf.threads, &pf.col) || !make_subplan(p.N2, pf.tile, pf.threads, &pf.row)) {
       delete pl;
       return IMPB_EUNSUPPORTED;
     }
-    pf.smem_col = tile_smem_bytes<float>(pf.col, 16);
-    pf.smem_row = tile_smem_bytes<float>(pf.row, 16);
+    pf.smem_col = tile_smem_bytes<float>(pf.col, pf.tile);
+    pf.smem_row = tile_smem_bytes<float>(pf.row, pf.tile);
     rc = pl->e32.fft.init(pf);
     pl->has32 = true;
   }

@@ -178,8 +178,17 @@ static bool is_5smooth(int64_t n) {
   return n == 1;
 }
 
-bool plan_2d(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, Plan2D* out) {
+static bool plan_2d_tile(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, int tile, Plan2D* out);
+
+bool plan_2d(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, Plan2D* out, bool allow_half_tile) {
+  // full tile = 128-byte HBM segments; transforms whose sub-FFTs do not fit shared memory at that width
+  // (192 kHz sweeps) fall back to half-width tiles (64-byte segments)
   const int tile = 64 / elem_bytes;
+  if (plan_2d_tile(ctx, n_min, exact, elem_bytes, tile, out)) return true;
+  return allow_half_tile && plan_2d_tile(ctx, n_min, exact, elem_bytes, tile / 2, out);
+}
+
+static bool plan_2d_tile(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, int tile, Plan2D* out) {
   const size_t cx = 2 * (size_t)elem_bytes;
   const size_t smem_max = (ctx && ctx->smem_optin) ? ctx->smem_optin : (size_t)227 * 1024;
   const size_t smem_two = ((ctx && ctx->smem_per_sm) ? ctx->smem_per_sm : (size_t)228 * 1024) / 2 - 1024;
@@ -293,7 +302,7 @@ int32_t impb_plan_probe(int64_t n_min, int32_t exact, int32_t elem_bytes, int64_
                         int32_t* radices_col, int32_t* radices_row) {
   if ((elem_bytes != 8 && elem_bytes != 4) || n_min < 4) return IMPB_EINVAL;
   impb::Plan2D p;
-  if (!impb::plan_2d(nullptr, n_min, exact != 0, elem_bytes, &p)) {
+  if (!impb::plan_2d(nullptr, n_min, exact != 0, elem_bytes, &p, true)) {
     impb::set_error("no plan for n=%lld", (long long)n_min);
     return IMPB_EUNSUPPORTED;
   }

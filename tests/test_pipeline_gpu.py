@@ -253,3 +253,93 @@ def test_repeat_runs_bitwise_deterministic(T, est48, synth_rec):
     a = disp.process(batch)[0].data.cpu().numpy()
     for _ in range(2):
         assert np.array_equal(a, disp.process(batch)[0].data.cpu().numpy())
+
+
+def test_process_host_matches_process(T, est48, synth_rec):
+    """Host-buffer entry point (chunked H2D / compute / D2H overlap) == device-resident entry point, bit for bit."""
+    from impulcifer_pip313_b200 import BatchDispatcher, synth
+    disp = BatchDispatcher(est48, synth.LAYOUT_71)
+    recs = np.stack([synth_rec, synth_rec[:, ::-1].copy() * 0 + synth_rec * 0.5, synth_rec * 0.25])
+    dev = disp.process(T.from_numpy(recs).cuda())
+    host_in = T.from_numpy(recs).pin_memory()
+    out = T.empty(sum(r.data.numel() for r in dev) + 16, dtype=T.float64).pin_memory()
+    got = disp.process_host(host_in, out=out, chunk_sets=2)
+    assert [r.tail_ind for r in got] == [r.tail_ind for r in dev]
+    for a, b in zip(got, dev):
+        assert not a.data.is_cuda and np.array_equal(a.data.numpy(), b.data.cpu().numpy())
+    pcm = T.from_numpy(np.rint(recs * 2 ** 31).astype(np.int32)).pin_memory()
+    got_pcm = disp.process_host(pcm, chunk_sets=1)
+    ref_pcm = disp.process(T.from_numpy(np.rint(recs * 2 ** 31) / 2 ** 31).cuda())
+    for a, b in zip(got_pcm, ref_pcm):
+        assert np.array_equal(a.data.numpy(), b.data.cpu().numpy())
+
+
+def test_truehd_11ch_layout_batched(T, est48):
+    """BASELINE config 4 shape: TrueHD 11-channel layout (22 responses per set) through the dispatcher."""
+    from impulcifer_pip313_b200 import BatchDispatcher, synth
+    fs = 48000
+    rec = synth.recording_set(est48.test_signal, fs, synth.LAYOUT_TRUEHD_11, seed=5)
+    assert rec.shape == (2, 4399970)
+    disp = BatchDispatcher(est48, synth.LAYOUT_TRUEHD_11)
+    res = disp.process(T.from_numpy(rec[None]).cuda())[0]
+    assert len(res.names) == 22 and res.names[:2] == ['FL-left', 'FL-right'] and res.names[-1] == 'TBR-right'
+    P, _, _ = O.sweep_parameters(fs)
+    irs = O.open_recording(rec, fs, synth.LAYOUT_TRUEHD_11, est48.inverse_filter, fs)
+    O.crop_heads(irs, fs)
+    O.align_ipsilateral_all(irs, fs)
+    O.align_onset_groups_peak_leftref(irs)
+    assert res.tail_ind == O.crop_tails(irs, fs, len(est48), P, fs)
+    got = res.as_dict()
+    for s in irs:
+        for e in irs[s]:
+            assert rel_peak_err(got[s][e], irs[s][e]) < 1e-9, (s, e)
+    # TrueHD output layout: "<speaker>-left, <speaker>-right" rows in TRUEHD_11CH_ORDER
+    order = [f'{s}-{e}' for s in synth.LAYOUT_TRUEHD_11 for e in ('left', 'right')]
+    m = O.track_matrix(got, order)
+    assert m.shape == (22, res.tail_ind) and np.array_equal(m[3], got['FR']['right'])
+
+
+def test_192khz_resample_smooth_minphase(T):
+    """BASELINE config 3 shape: 192 kHz sweep (L = 1 746 783, half-width tile plan) -> deconvolution -> crop ->
+    resample to 48 kHz -> 1/3-octave smoothing -> minimum-phase FIR, each step against the oracle."""
+    from impulcifer_pip313_b200 import ImpulseResponse, ImpulseResponseEstimator
+    fs = 192000
+    est = ImpulseResponseEstimator(min_duration=5.0, fs=fs)
+    assert len(est) == 1362783
+    rng = np.random.default_rng(4)
+    L = 2 * fs + len(est)
+    h = np.zeros(60000)
+    h[500] = 1.0
+    h[501:] = 0.05 * rng.standard_normal(59499) * 10 ** (-3 * np.arange(59499) / (fs * 0.2))
+    rec = np.zeros((2, L))
+    nfft = 1 << 21
+    seg = np.fft.irfft(np.fft.rfft(est.test_signal, nfft) * np.fft.rfft(h, nfft), nfft)[:L]
+    rec[0], rec[1] = 0.3 * seg, 0.2 * np.roll(seg, 40)
+    rec += 1e-5 * rng.standard_normal(rec.shape)
+    plan = est.plan(L)
+    assert plan.nfft >= 2428174
+    got = est.estimate_batch(rec)
+    ref = np.stack([O.estimate(r, est.inverse_filter) for r in rec])
+    assert rel_peak_err(got, ref) < 1e-9
+    ir = ImpulseResponse(got[0], fs)
+    pk = ir.peak_index()
+    assert pk == O.peak_index(ref[0])
+    ir.crop_head()
+    knee = ir.decay_params()[1]
+    assert knee == O.decay_params(O.crop_head(ref[0], fs), fs)[1]
+    n_keep = 4 * 21600
+    ir.data = ir.data[:n_keep]
+    ref_c = O.crop_head(ref[0], fs)[:n_keep]
+    ir.resample(48000)
+    ref_r = O.resample(ref_c, 48000, fs)
+    assert ir.fs == 48000 and len(ir) == len(ref_r) == 21600
+    assert rel_peak_err(ir.data, ref_r) < 1e-9
+    fr = ir.frequency_response()
+    f, raw = O.frequency_response(ref_r, 48000)
+    assert np.max(np.abs(fr.raw - raw)) < 1e-6
+    fr.smoothen_fractional_octave(window_size=1 / 3)
+    assert np.max(np.abs(fr.smoothed - O.smoothen_fractional_octave(f, fr.raw, 1 / 3))) < 1e-9
+    fr.equalization = -(fr.smoothed - np.mean(fr.smoothed))
+    fir = fr.minimum_phase_impulse_response(fs=48000, f_res=5, normalize=False)
+    ref_fir = O.minimum_phase_impulse_response(f, fr.equalization, fs=48000, f_res=5, normalize=False)
+    assert fir.shape == (9600,) and rel_peak_err(fir, ref_fir) < 5e-6
