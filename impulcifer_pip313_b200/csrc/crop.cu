@@ -70,14 +70,30 @@ __global__ void k_peak_init(PeakScratch* s, int64_t batch) {
   }
 }
 
+// grid = (rows, chunks): block (r, k) owns the contiguous samples [k*C, (k+1)*C) of row r.  Chunk index is the
+// SLOW grid dimension, so blocks are scheduled front-to-back over all rows and the peak search below can drop
+// every chunk behind an already published peak with a single read.
+__device__ __forceinline__ void chunk_bounds(int64_t n, int64_t* lo, int64_t* hi) {
+  int64_t C = (n + gridDim.y - 1) / gridDim.y;
+  C = (C + 255) & ~(int64_t)255;
+  *lo = (int64_t)blockIdx.y * C;
+  *hi = min(n, *lo + C);
+}
+
 __global__ void __launch_bounds__(256) k_absmax(const double* __restrict__ x, const ViewArgs va, int64_t r0,
                                                 PeakScratch* __restrict__ s) {
-  const int r = blockIdx.y;
+  const int64_t r = blockIdx.x;
   const RowView p(x, va, r0 + r);
-  const int64_t n = p.n;
+  int64_t lo, hi;
+  chunk_bounds(p.n, &lo, &hi);
+  if (lo >= hi) return;
   double m = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    m = fmax(m, fabs(p[i]));
+  int64_t i = lo + threadIdx.x;
+  for (; i + 768 < hi; i += 1024) {  // four independent loads in flight per thread
+    const double a0 = p[i], a1 = p[i + 256], a2 = p[i + 512], a3 = p[i + 768];
+    m = fmax(fmax(m, fmax(fabs(a0), fabs(a1))), fmax(fabs(a2), fabs(a3)));
+  }
+  for (; i < hi; i += 256) m = fmax(m, fabs(p[i]));
   for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   __shared__ double sm[8];
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
@@ -109,19 +125,20 @@ __device__ __forceinline__ bool peak_at(const RowView& p, int64_t n, int64_t i, 
 
 __global__ void __launch_bounds__(256) k_first_peak(const double* __restrict__ x, const ViewArgs va, int64_t r0,
                                                     double height, PeakScratch* __restrict__ s) {
-  const int r = blockIdx.y;
+  const int64_t r = blockIdx.x;
   const RowView p(x, va, r0 + r);
   const int64_t n = p.n;
   const double m = __longlong_as_double((long long)s[r].max_bits);
   if (!(m >= kEps)) return;
+  int64_t lo, hi;
+  chunk_bounds(n, &lo, &hi);
+  if (lo >= hi) return;
+  // nothing in this chunk can beat an already published earlier peak
+  // (first_argmax is only consulted when no peak exists at all, so it need not be complete then)
+  const unsigned long long cur = *((volatile unsigned long long*)&s[r].first_peak);
+  if (cur != kNoIndex && cur < (unsigned long long)lo) return;
   const double guard = 0.999 * height * m;
-  for (int64_t base = blockIdx.x * (int64_t)blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
-    // nothing at or after `base` can beat an already published earlier peak
-    // (first_argmax is only consulted when no peak exists at all, so it need not be complete then)
-    const unsigned long long cur = *((volatile unsigned long long*)&s[r].first_peak);
-    if (cur != kNoIndex && cur < (unsigned long long)base) return;
-    const int64_t i = base + threadIdx.x;
-    if (i >= n) continue;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
     const double v = p[i];
     const double av = fabs(v);
     if (av == m) atomicMin(&s[r].first_argmax, (unsigned long long)i);
@@ -147,11 +164,12 @@ int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double he
   const int thr = 256;
   k_peak_init<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, batch);
   // enough blocks per segment to fill the machine for small batches, few for large ones
-  int64_t per_seg = (4 * (int64_t)ctx->sm_count + batch - 1) / batch;
-  per_seg = std::max<int64_t>(1, std::min<int64_t>(per_seg, (max_len_hint + thr * 8 - 1) / (thr * 8)));
-  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
-    const int nb = (int)std::min<int64_t>(65535, batch - b0);
-    dim3 grid((unsigned)per_seg, nb);
+  // ~16 samples per thread
+  int64_t chunks = std::max<int64_t>(1, (max_len_hint + thr * 16 - 1) / (thr * 16));
+  chunks = std::min<int64_t>(chunks, 4096);
+  for (int64_t b0 = 0; b0 < batch; b0 += (int64_t)1 << 30) {
+    const int64_t nb = std::min<int64_t>((int64_t)1 << 30, batch - b0);
+    dim3 grid((unsigned)nb, (unsigned)chunks);
     k_absmax<<<grid, thr, 0, st>>>(x, va, b0, scratch + b0);
     k_first_peak<<<grid, thr, 0, st>>>(x, va, b0, height, scratch + b0);
   }
@@ -167,11 +185,14 @@ int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double he
 constexpr int LB_THREADS = 512;
 constexpr int LB_MAXWIN = 4096;
 
+constexpr int LB_MAXBLK = 3072;  // partial sums of the squared window: blocks of bs = 32, 64, ... samples
+
 struct LundebyShared {
   double red[LB_THREADS / 32];
   double bcast[4];
   long long ibcast[4];
   double win[LB_MAXWIN];
+  double blk[LB_MAXBLK];
 };
 
 __device__ __forceinline__ double block_sum(double v, LundebyShared& sh) {
@@ -201,6 +222,8 @@ struct SqView {  // squared, peak-normalised analysis segment  sq[i] = (v[pk+i] 
   int64_t pk;
   double mx;
   bool norm;
+  const double* blk;  // shared-memory sums of aligned blocks of `bs` samples (nullptr: not built)
+  int bs;
   __device__ __forceinline__ double operator()(int64_t i) const {
     const double s = (*p)[pk + i];
     const double v = norm ? __ddiv_rn(s, mx) : s;
@@ -208,10 +231,55 @@ struct SqView {  // squared, peak-normalised analysis segment  sq[i] = (v[pk+i] 
   }
 };
 
-__device__ __forceinline__ double range_mean(const SqView& sq, int64_t a, int64_t b, LundebyShared& sh) {
+// Every statistic of decay_params is a mean of sq over a contiguous range.  The samples are read (and divided)
+// ONCE into per-block partial sums kept in shared memory; a range sum is then whole blocks from shared memory
+// plus at most 2*bs edge samples from HBM.  No prefix-sum differences are taken, so there is no cancellation.
+__device__ void build_block_sums(SqView& sq, int64_t ns, LundebyShared& sh) {
+  int bs = 32;
+  while ((ns + bs - 1) / bs > LB_MAXBLK) bs <<= 1;
+  const int nblk = (int)((ns + bs - 1) / bs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = LB_THREADS / 32;
+  for (int k0 = warp; k0 < nblk; k0 += 4 * NW) {  // four blocks per warp iteration: independent loads in flight
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u * NW;
+      if (k < nblk) {
+        const int64_t a = (int64_t)k * bs, b = min(ns, a + bs);
+        for (int64_t i = a + lane; i < b; i += 32) acc[u] += sq(i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      for (int o = 16; o; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      const int k = k0 + u * NW;
+      if (lane == 0 && k < nblk) sh.blk[k] = acc[u];
+    }
+  }
+  __syncthreads();
+  sq.blk = sh.blk;
+  sq.bs = bs;
+}
+
+// partial (per-thread) sum of sq over [a, b) for threads `tid` of `nthr` cooperating threads
+__device__ __forceinline__ double range_partial(const SqView& sq, int64_t a, int64_t b, int tid, int nthr) {
   double acc = 0.0;
-  for (int64_t i = a + threadIdx.x; i < b; i += LB_THREADS) acc += sq(i);
-  return block_sum(acc, sh) / (double)(b - a);
+  if (!sq.blk) {
+    for (int64_t i = a + tid; i < b; i += nthr) acc += sq(i);
+    return acc;
+  }
+  const int64_t bs = sq.bs;
+  const int64_t a_up = min(b, (a + bs - 1) / bs * bs);
+  const int64_t b_dn = max(a_up, b / bs * bs);
+  for (int64_t i = a + tid; i < a_up; i += nthr) acc += sq(i);
+  for (int64_t k = a_up / bs + tid; k < b_dn / bs; k += nthr) acc += sq.blk[k];
+  for (int64_t i = b_dn + tid; i < b; i += nthr) acc += sq(i);
+  return acc;
+}
+
+__device__ __forceinline__ double range_mean(const SqView& sq, int64_t a, int64_t b, LundebyShared& sh) {
+  return block_sum(range_partial(sq, a, b, threadIdx.x, LB_THREADS), sh) / (double)(b - a);
 }
 
 __device__ __forceinline__ double db10(double v) { return 10.0 * log10(fmax(v, kEps)); }
@@ -220,9 +288,8 @@ __device__ __forceinline__ double db10(double v) { return 10.0 * log10(fmax(v, k
 __device__ void fill_windows(const SqView& sq, int nwin, int64_t w, LundebyShared& sh) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = warp; k < nwin; k += LB_THREADS / 32) {
-    double acc = 0.0;
     const int64_t a = (int64_t)k * w;
-    for (int64_t i = lane; i < w; i += 32) acc += sq(a + i);
+    double acc = range_partial(sq, a, a + w, lane, 32);
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) sh.win[k] = db10(acc / (double)w);
   }
@@ -272,7 +339,8 @@ __global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict
                                                         const int64_t* __restrict__ peaks, int64_t* __restrict__ peak_out,
                                                         int64_t* __restrict__ knee_out, double* __restrict__ noise_out,
                                                         int64_t* __restrict__ win_out) {
-  __shared__ LundebyShared sh;
+  extern __shared__ __align__(16) unsigned char lb_smem[];
+  LundebyShared& sh = *reinterpret_cast<LundebyShared*>(lb_smem);
   const int r = blockIdx.x;
   const RowView ir(x, va, r0 + r);
   const int64_t n_ir = ir.n;
@@ -288,9 +356,18 @@ __global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict
   const int64_t stop = min(pk + (int64_t)(2 * fs), n_ir);
   const int64_t ns = stop - pk;  // >= 1 because pk <= n_ir - 1
   double mx = 0.0;
-  for (int64_t i = threadIdx.x; i < ns; i += LB_THREADS) mx = fmax(mx, fabs(ir[pk + i]));
+  {
+    int64_t i = threadIdx.x;
+    for (; i + 3 * LB_THREADS < ns; i += 4 * LB_THREADS) {
+      const double a0 = ir[pk + i], a1 = ir[pk + i + LB_THREADS], a2 = ir[pk + i + 2 * LB_THREADS],
+                   a3 = ir[pk + i + 3 * LB_THREADS];
+      mx = fmax(fmax(mx, fmax(fabs(a0), fabs(a1))), fmax(fabs(a2), fabs(a3)));
+    }
+    for (; i < ns; i += LB_THREADS) mx = fmax(mx, fabs(ir[pk + i]));
+  }
   mx = block_max(mx, sh);
-  SqView sq{&ir, pk, mx, mx >= kEps};
+  SqView sq{&ir, pk, mx, mx >= kEps, nullptr, 32};
+  build_block_sums(sq, ns, sh);
   const double step = ns > 1 ? ((double)ns / (double)fs) / (double)(ns - 1) : 0.0;  // linspace(0, ns/fs, ns)
   const double t_last = (double)(ns - 1) * step;
 
@@ -573,12 +650,14 @@ int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, con
   const ViewArgs va = make_view(offsets, lengths, view);
   int rc = run_peak_index(ctx, x, va, 0.12589, peaks, batch, std::max<int64_t>(max_len, 1), st);
   if (!rc) {
-    for (int64_t b0 = 0; b0 < batch && !rc; b0 += 1 << 30) {
+    cudaError_t e = cudaFuncSetAttribute(k_lundeby, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(LundebyShared));
+    for (int64_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += (int64_t)1 << 30) {
       const int64_t nb = std::min<int64_t>((int64_t)1 << 30, batch - b0);
-      k_lundeby<<<(unsigned)nb, LB_THREADS, 0, st>>>(x, va, b0, fs, peaks + b0, peak_out + b0, knee_out + b0,
-                                                    noise_db_out + b0, win_out + b0);
+      k_lundeby<<<(unsigned)nb, LB_THREADS, sizeof(LundebyShared), st>>>(x, va, b0, fs, peaks + b0, peak_out + b0,
+                                                                        knee_out + b0, noise_db_out + b0, win_out + b0);
     }
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) rc = cuda_fail(e, "k_lundeby");
   }
   cudaFreeAsync(peaks, st);

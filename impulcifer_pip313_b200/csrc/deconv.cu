@@ -261,6 +261,12 @@ struct impb_plan {
   DeconvEngine<float> e32;
   int64_t chunk_pairs = 1;
   bool has64 = false, has32 = false;
+  // optional intra-call concurrency: chunks are issued round-robin on `nstreams` internal streams (each with its
+  // own workspace slice) so that the tail of one launch triple overlaps the head of the next
+  int nstreams = 1;
+  cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr;
+  cudaEvent_t join_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 static int build_spectrum(impb_plan* pl, const double* inv_host) {
@@ -386,6 +392,14 @@ int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, in
   int64_t chunk = (int64_t)((size_t)1 << 30) / (int64_t)(p.N * cx);
   if (const char* e = getenv("IMPB_CHUNK_PAIRS")) chunk = atoll(e);
   pl->chunk_pairs = std::max<int64_t>(1, std::min<int64_t>(chunk, 32768));
+  if (const char* e = getenv("IMPB_STREAMS")) pl->nstreams = std::max(1, std::min(4, atoi(e)));
+  if (pl->nstreams > 1) {
+    cudaEventCreateWithFlags(&pl->fork_ev, cudaEventDisableTiming);
+    for (int i = 0; i < pl->nstreams; ++i) {
+      cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&pl->join_ev[i], cudaEventDisableTiming);
+    }
+  }
   *out = pl;
   return IMPB_OK;
 }
@@ -393,6 +407,11 @@ int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, in
 void impb_deconv_plan_destroy(impb_plan* pl) {
   if (!pl) return;
   DeviceGuard g(pl->ctx->device);
+  for (int i = 0; i < 4; ++i) {
+    if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
+    if (pl->join_ev[i]) cudaEventDestroy(pl->join_ev[i]);
+  }
+  if (pl->fork_ev) cudaEventDestroy(pl->fork_ev);
   if (pl->has64) { pl->e64.fft.release(); cudaFree(pl->e64.hs); }
   if (pl->has32) { pl->e32.fft.release(); cudaFree(pl->e32.hs); }
   delete pl;
@@ -411,7 +430,7 @@ int64_t impb_deconv_workspace_bytes(const impb_plan* pl, int64_t batch) {
   if (!pl || batch < 1) return 0;
   const Plan2D& p = pl->precision == 64 ? pl->e64.fft.p : pl->e32.fft.p;
   const int64_t pairs = std::min<int64_t>((batch + 1) / 2, pl->chunk_pairs);
-  return pairs * p.N * (int64_t)(pl->precision == 64 ? sizeof(double2) : sizeof(float2));
+  return pl->nstreams * pairs * p.N * (int64_t)(pl->precision == 64 ? sizeof(double2) : sizeof(float2));
 }
 
 int32_t impb_deconv_launches_per_execute(const impb_plan* pl, int64_t batch) {
@@ -434,13 +453,23 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
   DeviceGuard g(pl->ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t pairs = (batch + 1) / 2;
-  for (int64_t p0 = 0; p0 < pairs; p0 += pl->chunk_pairs) {
+  const int ns = pl->nstreams;
+  const cudaStream_t user = st;
+  if (ns > 1) {
+    IMPB_CUDA(cudaEventRecord(pl->fork_ev, user));
+    for (int i = 0; i < ns; ++i) IMPB_CUDA(cudaStreamWaitEvent(pl->streams[i], pl->fork_ev, 0));
+  }
+  const int64_t slice_pairs = std::min<int64_t>(pairs, pl->chunk_pairs);
+  int64_t chunk_idx = 0;
+  for (int64_t p0 = 0; p0 < pairs; p0 += pl->chunk_pairs, ++chunk_idx) {
     const int np = (int)std::min<int64_t>(pl->chunk_pairs, pairs - p0);
+    const int si = ns > 1 ? (int)(chunk_idx % ns) : 0;
+    if (ns > 1) st = pl->streams[si];
     int rc;
     if (pl->precision == 64) {
       DeconvArgs<double> a{};
       const Plan2D& p = pl->e64.fft.p;
-      a.ws = (double2*)workspace; a.tw = pl->e64.fft.tw; a.hs = pl->e64.hs;
+      a.ws = (double2*)workspace + (size_t)si * slice_pairs * p.N; a.tw = pl->e64.fft.tw; a.hs = pl->e64.hs;
       a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
       a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = 1;
@@ -448,13 +477,19 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
     } else {
       DeconvArgs<float> a{};
       const Plan2D& p = pl->e32.fft.p;
-      a.ws = (float2*)workspace; a.tw = pl->e32.fft.tw; a.hs = pl->e32.hs;
+      a.ws = (float2*)workspace + (size_t)si * slice_pairs * p.N; a.tw = pl->e32.fft.tw; a.hs = pl->e32.hs;
       a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
       a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = out_f64 ? 1 : 0;
       rc = pl->e32.launch(a, np, st);
     }
     if (rc) return rc;
+  }
+  if (ns > 1) {
+    for (int i = 0; i < ns; ++i) {
+      IMPB_CUDA(cudaEventRecord(pl->join_ev[i], pl->streams[i]));
+      IMPB_CUDA(cudaStreamWaitEvent(user, pl->join_ev[i], 0));
+    }
   }
   return IMPB_OK;
 }

@@ -125,6 +125,31 @@ class BatchDispatcher:
             groups = [g for g in ONSET_GROUPS if g[0] in spk_list]
             lay['groups'] = groups
             lay['gl'] = torch.as_tensor([row_of[f"{g[0]}-left"] for g in groups], device=device)
+            # which rows a positive / negative ipsilateral lag of pair k shifts (ref core/hrir.py:936-955)
+            pos_rows, pos_k, neg_rows, neg_k = [], [], [], []
+            for k, (a, b) in enumerate(pairs):
+                if a == b:
+                    pos_rows.append(row_of[f"{a}-right"]); pos_k.append(k)
+                    neg_rows.append(row_of[f"{a}-left"]); neg_k.append(k)
+                else:
+                    for sd in ('left', 'right'):
+                        pos_rows.append(row_of[f"{b}-{sd}"]); pos_k.append(k)
+                        neg_rows.append(row_of[f"{a}-{sd}"]); neg_k.append(k)
+            for name, v in (('pos_rows', pos_rows), ('pos_k', pos_k), ('neg_rows', neg_rows), ('neg_k', neg_k)):
+                lay[name] = torch.as_tensor(v, device=device, dtype=torch.int64)
+            # rows moved by the onset alignment of group g (every group but FL/FR) (ref core/hrir.py:981-1001)
+            g_rows, g_of_row = [], []
+            for gi, g in enumerate(groups):
+                if g == ("FL", "FR"):
+                    continue
+                for spk in g:
+                    if spk in spk_list:
+                        for sd in ('left', 'right'):
+                            g_rows.append(row_of[f"{spk}-{sd}"]); g_of_row.append(gi)
+            lay['g_rows'] = torch.as_tensor(g_rows, device=device, dtype=torch.int64)
+            lay['g_of_row'] = torch.as_tensor(g_of_row, device=device, dtype=torch.int64)
+            lay['g_ref'] = [i for i, g in enumerate(groups) if g[0] == 'FL'][0] if 'FL' in spk_list else -1
+            lay['set_rows'] = torch.arange(len(plan), device=device, dtype=torch.int64)
         self._layout = lay
         return lay
 
@@ -184,16 +209,8 @@ class BatchDispatcher:
                 lb = torch.clamp(n1v[:, lay['pb']], max=seg).reshape(-1)
                 lags = ops.xcorr_lag(flatE, off1[ra], la, off1[rb], lb, max_seg_len=seg, fade_in=window_in).view(S, -1)
                 launches += 1
-                for k, (a, b) in enumerate(lay['pairs']):
-                    lag = lags[:, k]
-                    pos, neg = torch.clamp(lag, min=0), torch.clamp(-lag, min=0)
-                    if a == b:
-                        shift[:, lay['row_of'][f"{a}-right"]] += pos
-                        shift[:, lay['row_of'][f"{a}-left"]] += neg
-                    else:
-                        for sd in ('left', 'right'):
-                            shift[:, lay['row_of'][f"{b}-{sd}"]] += pos
-                            shift[:, lay['row_of'][f"{a}-{sd}"]] += neg
+                shift.index_add_(1, lay['pos_rows'], torch.clamp(lags, min=0)[:, lay['pos_k']])
+                shift.index_add_(1, lay['neg_rows'], torch.clamp(-lags, min=0)[:, lay['neg_k']])
             shift = shift.reshape(-1)
             lo = torch.clamp(shift, min=0)
             hi = torch.maximum(torch.minimum(n1 + shift, n1), lo)
@@ -205,15 +222,8 @@ class BatchDispatcher:
                                     view=dict(shift=shift[rg], valid_lo=lo[rg], valid_hi=hi[rg],
                                               fade_in=window_in)).view(S, -1)
                 launches += 4
-                ref_col = [i for i, g in enumerate(lay['groups']) if g[0] == 'FL'][0]
-                for gi, g in enumerate(lay['groups']):
-                    if g == ("FL", "FR"):
-                        continue
-                    d = gp[:, gi] - gp[:, ref_col]
-                    for spk in g:
-                        if spk in lay['speakers']:
-                            for sd in ('left', 'right'):
-                                shift2[:, lay['row_of'][f"{spk}-{sd}"]] -= d
+                d = gp - gp[:, lay['g_ref']:lay['g_ref'] + 1]
+                shift2.index_add_(1, lay['g_rows'], -d[:, lay['g_of_row']])
             elif 'FL' not in lay['speakers']:
                 raise RuntimeError("Cannot find FL left channel reference for onset alignment.")
             shift2 = shift2.reshape(-1)
@@ -232,8 +242,9 @@ class BatchDispatcher:
             seconds_per_octave = len(est) / est.fs / est.n_octaves
             fade_out = 2 * int(fs * seconds_per_octave * (1 / 24))
             window_out = hann(fade_out)[fade_out // 2:]
-            tails = [int(min(n1_h[s].min(), next_fast_len(int(knees_h[s].max())))) for s in range(S)]
+            tails = np.minimum(n1_h.min(axis=1), next_fast_len(knees_h.max(axis=1))).tolist()
             results = [None] * S
+            side_msgs = self._side_warnings(lay, peaks_h)
             for tail in sorted(set(tails)):
                 if tail < len(window_out):
                     raise ValueError("negative dimensions are not allowed")
@@ -244,8 +255,7 @@ class BatchDispatcher:
                                         fade_in=window_in, fade_out=window_out).view(len(sets), n, tail)
                 launches += 1
                 for k, s in enumerate(sets):
-                    results[s] = SetResult(lay['names'], out[k], tail, peaks_h[s], crop_h[s], knees_h[s],
-                                           self._side_warnings(lay, peaks_h[s]))
+                    results[s] = SetResult(lay['names'], out[k], tail, peaks_h[s], crop_h[s], knees_h[s], side_msgs[s])
         self.launches = launches
         return results
 
@@ -304,16 +314,20 @@ class BatchDispatcher:
         return results
 
     def _side_warnings(self, lay, peaks):
-        msgs = []
-        for k, spk in enumerate(lay['speakers']):
-            pl, pr = int(peaks[lay['row_of'][f"{spk}-left"]]), int(peaks[lay['row_of'][f"{spk}-right"]])
-            if pl < pr and lay['side_code'][k] == 'right':
-                msgs.append(f"Warning: {spk} measurement has lower delay to left ear than to right ear.")
-            elif pl >= pr and lay['side_code'][k] == 'left':
-                msgs.append(f"Warning: {spk} measurement has lower delay to right ear than to left ear.")
-        for m in msgs:
-            warnings.warn(m)
-        return msgs
+        """Wrong-side ITD warnings of crop_heads (ref core/hrir.py:578-606) for all sets: [S][...] messages."""
+        li, ri = lay['left'].tolist(), lay['right'].tolist()
+        pl, pr = peaks[:, li], peaks[:, ri]
+        is_right = np.array([c == 'right' for c in lay['side_code']])
+        is_left = np.array([c == 'left' for c in lay['side_code']])
+        bad = ((pl < pr) & is_right[None, :]) | ((pl >= pr) & is_left[None, :])
+        out = [[] for _ in range(peaks.shape[0])]
+        for s, k in zip(*np.nonzero(bad)):
+            spk = lay['speakers'][k]
+            first, second = ('left', 'right') if pl[s, k] < pr[s, k] else ('right', 'left')
+            msg = f"Warning: {spk} measurement has lower delay to {first} ear than to {second} ear."
+            warnings.warn(msg)
+            out[s].append(msg)
+        return out
 
     # ---- per-IR frequency-response post-processing -----------------------------------------------------------
     def postprocess(self, results, window_size=1 / 3, f_res=5, normalize=False):

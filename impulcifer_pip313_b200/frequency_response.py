@@ -65,23 +65,37 @@ def sigmoid(frequency, f_lower, f_upper, a_normal=0.0, a_treble=1.0):
     return a * -(a_normal - a_treble) + a_normal
 
 
-def next_fast_len(target: int) -> int:
-    """scipy.fftpack.next_fast_len: smallest 2^a 3^b 5^c >= target."""
-    target = int(target)
-    if target <= 6:
-        return max(target, 1)
-    best = 1 << (target - 1).bit_length()
-    p5 = 1
-    while p5 < best:
-        p35 = p5
-        while p35 < best:
-            q = -(-target // p35)
-            cand = (1 << max(q - 1, 0).bit_length()) * p35
-            if target <= cand < best:
-                best = cand
-            p35 *= 3
-        p5 *= 5
-    return best
+_SMOOTH5 = None
+
+
+def _smooth5_table():
+    """Sorted 5-smooth numbers up to 2**26 (host constant, built once)."""
+    global _SMOOTH5
+    if _SMOOTH5 is None:
+        lim = 1 << 26
+        vals = []
+        p5 = 1
+        while p5 <= lim:
+            p35 = p5
+            while p35 <= lim:
+                v = p35
+                while v <= lim:
+                    vals.append(v)
+                    v *= 2
+                p35 *= 3
+            p5 *= 5
+        _SMOOTH5 = np.array(sorted(vals), dtype=np.int64)
+    return _SMOOTH5
+
+
+def next_fast_len(target):
+    """scipy.fftpack.next_fast_len: smallest 2^a 3^b 5^c >= target (scalar or array)."""
+    tab = _smooth5_table()
+    t = np.maximum(np.asarray(target, dtype=np.int64), 1)
+    if np.any(t > tab[-1]):
+        raise ValueError("length too large")
+    out = tab[np.searchsorted(tab, t, side='left')]
+    return int(out) if out.ndim == 0 else out
 
 
 # ---- batched device entry points ------------------------------------------------------------------------
