@@ -31,10 +31,10 @@ SIGNATURES = {
     "impb_deconv_plan_destroy": (None, [c_vp]),
     "impb_deconv_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "impb_deconv_plan_info": (c_i32, [c_vp, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
-    "impb_deconv_execute": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64,
-                                    c_vp, c_vp]),
+    "impb_deconv_execute": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp,
+                                    c_i64, c_vp, c_vp]),
     "impb_deconv_launches_per_execute": (c_i32, [c_vp, c_i64]),
-    "impb_peak_index": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_i64, c_i64, c_vp]),
+    "impb_peak_index": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_i64, c_i64, c_vp]),
     "impb_lundeby": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "impb_xcorr_lag": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "impb_gather_window": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp,

@@ -157,12 +157,24 @@ __global__ void k_peak_final(const PeakScratch* __restrict__ s, int64_t* __restr
   out[i] = r;
 }
 
+__global__ void k_peak_seed(PeakScratch* s, const double* __restrict__ known_max, int64_t batch) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < batch) {
+    s[i].max_bits = (unsigned long long)__double_as_longlong(known_max[i]);
+    s[i].first_peak = kNoIndex;
+    s[i].first_argmax = kNoIndex;
+  }
+}
+
 int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double height, int64_t* peak_out, int64_t batch,
-                   int64_t max_len_hint, cudaStream_t st) {
+                   int64_t max_len_hint, cudaStream_t st, const double* known_max = nullptr) {
   PeakScratch* scratch = nullptr;
   IMPB_CUDA(cudaMallocAsync(&scratch, sizeof(PeakScratch) * batch, st));
   const int thr = 256;
-  k_peak_init<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, batch);
+  if (known_max)
+    k_peak_seed<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, known_max, batch);
+  else
+    k_peak_init<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, batch);
   // enough blocks per segment to fill the machine for small batches, few for large ones
   // ~16 samples per thread
   int64_t chunks = std::max<int64_t>(1, (max_len_hint + thr * 16 - 1) / (thr * 16));
@@ -170,7 +182,7 @@ int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double he
   for (int64_t b0 = 0; b0 < batch; b0 += (int64_t)1 << 30) {
     const int64_t nb = std::min<int64_t>((int64_t)1 << 30, batch - b0);
     dim3 grid((unsigned)nb, (unsigned)chunks);
-    k_absmax<<<grid, thr, 0, st>>>(x, va, b0, scratch + b0);
+    if (!known_max) k_absmax<<<grid, thr, 0, st>>>(x, va, b0, scratch + b0);
     k_first_peak<<<grid, thr, 0, st>>>(x, va, b0, height, scratch + b0);
   }
   k_peak_final<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, peak_out, batch);
@@ -622,8 +634,8 @@ static ViewArgs make_view(const int64_t* offsets, const int64_t* lengths, const 
 }
 
 int32_t impb_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,
-                        const impb_view* view, double height, int64_t* peak_out, int64_t batch, int64_t max_len,
-                        void* stream) {
+                        const impb_view* view, const double* known_max, double height, int64_t* peak_out,
+                        int64_t batch, int64_t max_len, void* stream) {
   if (!ctx || !x || !offsets || !lengths || !peak_out || batch < 0 || !(height > 0.0)) {
     set_error("impb_peak_index: bad argument");
     return IMPB_EINVAL;
@@ -631,7 +643,7 @@ int32_t impb_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, 
   if (batch == 0) return IMPB_OK;
   DeviceGuard g(ctx->device);
   return run_peak_index(ctx, x, make_view(offsets, lengths, view), height, peak_out, batch,
-                        std::max<int64_t>(max_len, 1), (cudaStream_t)stream);
+                        std::max<int64_t>(max_len, 1), (cudaStream_t)stream, known_max);
 }
 
 int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,

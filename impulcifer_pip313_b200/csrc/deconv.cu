@@ -46,6 +46,7 @@ template <typename T> struct DeconvArgs {
   void* out;
   int64_t ld_out, out_start, out_len;
   int out_f64;
+  unsigned long long* absmax;  // optional [nrows]: bit pattern of max |out[r, :]| (atomicMax; zeroed by the caller)
 };
 
 __device__ __forceinline__ double load_sample(const void* p, int fmt, int64_t i) {
@@ -127,6 +128,11 @@ template <typename T, int TILE> struct DeconvColOut {
     return a.ws[(size_t)b * a.N + (size_t)e * a.N2 + n2];
   }
   __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v) const {
+    T m0 = 0, m1 = 0;
+    store(b, t, e, c, v, m0, m1);
+  }
+  // also folds |value as stored| into the caller's running maxima
+  __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v, T& mx_re, T& mx_im) const {
     const int n2 = t * TILE + c;
     const int64_t j = (int64_t)e * a.N2 + n2 - a.out_start;
     if (n2 >= a.N2 || j < 0 || j >= a.out_len) return;
@@ -137,11 +143,35 @@ template <typename T, int TILE> struct DeconvColOut {
       if (rb < a.nrows) o[rb * a.ld_out + j] = (double)v.y;
     } else {
       float* o = reinterpret_cast<float*>(a.out);
+      v.x = (T)(float)v.x;
+      v.y = (T)(float)v.y;
       o[ra * a.ld_out + j] = (float)v.x;
       if (rb < a.nrows) o[rb * a.ld_out + j] = (float)v.y;
     }
+    mx_re = fmax(mx_re, fabs(v.x));
+    mx_im = fmax(mx_im, fabs(v.y));
+  }
+  __device__ __forceinline__ bool tracks_max() const { return a.absmax != nullptr; }
+  __device__ __forceinline__ void publish_max(int b, T mx_re, T mx_im) const {
+    const int64_t ra = a.row0 + 2 * (int64_t)b, rb = ra + 1;
+    atomicMax(a.absmax + ra, (unsigned long long)__double_as_longlong((double)mx_re));
+    if (rb < a.nrows) atomicMax(a.absmax + rb, (unsigned long long)__double_as_longlong((double)mx_im));
   }
 };
+
+// max |row| of an already written output (generic-engine plans, where the column pass does not track it)
+template <typename O>
+__global__ void __launch_bounds__(256) k_row_absmax(const O* __restrict__ out, int64_t ld, int64_t n,
+                                                    unsigned long long* __restrict__ absmax) {
+  const int64_t r = blockIdx.x;
+  const O* p = out + r * ld;
+  int64_t C = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t lo = (int64_t)blockIdx.y * C, hi = min(n, lo + C);
+  double m = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) m = fmax(m, fabs((double)p[i]));
+  for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(absmax + r, (unsigned long long)__double_as_longlong(m));
+}
 
 // spectrum of the inverse filter: scrambled [p1][p2] -> natural order
 __global__ void k_spec_to_natural(const double2* __restrict__ ws, double2* __restrict__ nat, const int* __restrict__ perm1,
@@ -247,7 +277,17 @@ template <typename T> struct DeconvEngine {
     }
     if ((rc = fft.template col_fwd<TILE>(DeconvColIn<T, TILE>{a}, pairs, st))) return rc;
     if ((rc = fft.template row_conv<TILE>(DeconvRow<T, TILE>{a}, pairs, st))) return rc;
-    return fft.template col_inv<TILE>(DeconvColOut<T, TILE>{a}, pairs, st);
+    if ((rc = fft.template col_inv<TILE>(DeconvColOut<T, TILE>{a}, pairs, st))) return rc;
+    if (a.absmax) {  // the generic column pass does not track maxima: one extra read of the rows just written
+      const int64_t r0 = a.row0, nr = std::min<int64_t>(2 * (int64_t)pairs, a.nrows - r0);
+      const dim3 grid((unsigned)nr, (unsigned)std::max<int64_t>(1, std::min<int64_t>(a.out_len / 4096, 1024)));
+      if (a.out_f64)
+        k_row_absmax<double><<<grid, 256, 0, st>>>((const double*)a.out + r0 * a.ld_out, a.ld_out, a.out_len, a.absmax + r0);
+      else
+        k_row_absmax<float><<<grid, 256, 0, st>>>((const float*)a.out + r0 * a.ld_out, a.ld_out, a.out_len, a.absmax + r0);
+      IMPB_CUDA(cudaGetLastError());
+    }
+    return IMPB_OK;
   }
 };
 
@@ -441,7 +481,7 @@ int32_t impb_deconv_launches_per_execute(const impb_plan* pl, int64_t batch) {
 
 int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_offsets, int64_t ld_in, int32_t in_fmt,
                             int64_t len, void* out, int64_t ld_out, int32_t out_f64, int64_t out_offset, int64_t out_len,
-                            int64_t batch, void* workspace, void* stream) {
+                            double* absmax_out, int64_t batch, void* workspace, void* stream) {
   if (!pl || !rec || !out || !workspace || batch < 0 || len < 0 || len > pl->L || (!in_offsets && ld_in < len) ||
       out_offset < 0 ||
       out_len < 0 || out_offset + out_len > len || ld_out < out_len || in_fmt < 0 || in_fmt > 2) {
@@ -452,6 +492,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
   if (batch == 0 || out_len == 0) return IMPB_OK;
   DeviceGuard g(pl->ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (absmax_out) IMPB_CUDA(cudaMemsetAsync(absmax_out, 0, sizeof(double) * batch, st));
   const int64_t pairs = (batch + 1) / 2;
   const int ns = pl->nstreams;
   const cudaStream_t user = st;
@@ -473,6 +514,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
       a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
       a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = 1;
+      a.absmax = (unsigned long long*)absmax_out;
       rc = pl->e64.launch(a, np, st);
     } else {
       DeconvArgs<float> a{};
@@ -481,6 +523,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
       a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
       a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = out_f64 ? 1 : 0;
+      a.absmax = (unsigned long long*)absmax_out;
       rc = pl->e32.launch(a, np, st);
     }
     if (rc) return rc;

@@ -197,8 +197,10 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
   const int t = blockIdx.x, b = blockIdx.y;
+  // running max |re|, |im| of what this thread stores: the per-row max|x| the peak search needs comes for free
+  T mx_re = (T)0, mx_im = (T)0;
   auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
-  auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
+  auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v, mx_re, mx_im); };
   auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
   fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false>(nullptr, gl, ss, NoPost{});
@@ -206,6 +208,26 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true, false>(tw1, sl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, true, false>(tw0, sl, gs, NoPost{});
+  if (f.tracks_max()) {
+    __syncthreads();  // the tile is free: reuse it for the block reduction
+    T* red = reinterpret_cast<T*>(smem_raw);
+    for (int o = 16; o; o >>= 1) {
+      mx_re = fmax(mx_re, __shfl_xor_sync(0xffffffffu, mx_re, o));
+      mx_im = fmax(mx_im, __shfl_xor_sync(0xffffffffu, mx_im, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[2 * (threadIdx.x >> 5)] = mx_re;
+      red[2 * (threadIdx.x >> 5) + 1] = mx_im;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < NT / 32; ++w) {
+        mx_re = fmax(mx_re, red[2 * w]);
+        mx_im = fmax(mx_im, red[2 * w + 1]);
+      }
+      f.publish_max(b, mx_re, mx_im);
+    }
+  }
 }
 
 // row pass: forward, x spectrum, inverse.  tw0r / tw1r are the [p-1][np] (transposed) stage tables.

@@ -175,7 +175,8 @@ class BatchDispatcher:
             # 1. deconvolution of every column of every set (K1)
             row_offs = (set_base * (n_tracks * n_samples) + lay['offs'][None, :]).reshape(-1)
             plan = est.plan(L, precision)
-            E = plan.execute(recordings.reshape(-1), length=L, row_offsets=row_offs)
+            e_max = torch.empty(B, dtype=torch.float64, device=dev)
+            E = plan.execute(recordings.reshape(-1), length=L, row_offsets=row_offs, absmax=e_max)
             if E.dtype != torch.float64:
                 E = E.to(torch.float64)
             launches += plan.launches(B)
@@ -183,8 +184,8 @@ class BatchDispatcher:
             rows = torch.arange(B, device=dev, dtype=torch.int64)
             full = torch.full((B,), L, device=dev, dtype=torch.int64)
             # 2. first peaks (K2) and the pairwise head crop (ref core/hrir.py:573-606), integer ops on device
-            peaks = ops.peak_index(flatE, rows * L, full, max_len=L)
-            launches += 4
+            peaks = ops.peak_index(flatE, rows * L, full, max_len=L, known_max=e_max)
+            launches += 3
             pk = peaks.view(S, n)
             pl, pr = pk[:, lay['left']], pk[:, lay['right']]
             first = torch.where(pl < pr, pl, pr)

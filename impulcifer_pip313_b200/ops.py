@@ -77,7 +77,7 @@ def make_view(device, shift=None, valid_lo=None, valid_hi=None, fade_in=None):
     return v, (sh, lo, hi, fi)
 
 
-def peak_index(x, offsets, lengths, height=0.12589, max_len=None, view=None):
+def peak_index(x, offsets, lengths, height=0.12589, max_len=None, view=None, known_max=None):
     """First-peak index of every segment ``x[offsets[r] : offsets[r]+lengths[r]]`` (relative to the segment).
     ``view`` = dict(shift=, valid_lo=, valid_hi=, fade_in=) evaluates it on the shifted / faded view instead."""
     torch = _torch()
@@ -92,8 +92,9 @@ def peak_index(x, offsets, lengths, height=0.12589, max_len=None, view=None):
     v, keep = make_view(x.device, **(view or {}))
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().impb_peak_index(_lib.context(_dev(x)).handle, x.data_ptr(), _i64(offsets), _i64(lengths),
-                                              None if v is None else C.addressof(v), float(height), out.data_ptr(),
-                                              batch, int(max_len), _stream(x)), "impb_peak_index")
+                                              None if v is None else C.addressof(v),
+                                              None if known_max is None else known_max.data_ptr(), float(height),
+                                              out.data_ptr(), batch, int(max_len), _stream(x)), "impb_peak_index")
     del keep
     return out
 

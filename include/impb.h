@@ -72,6 +72,8 @@ IMPB_API const char* impb_last_error(void); /* thread-local */
  * how the track/column split of core/hrir.py:194-216 is consumed without a gather copy.  Row r of
  * out ([batch, ld_out] f64 for precision 64, f32 for precision 32 unless out_f64 != 0) receives
  *   convolve(rec[r, :len], inverse_filter, 'same')[out_offset : out_offset + out_len].
+ * absmax_out (nullable, device double[batch]) receives max |out[r, :]|, tracked by the final column pass for
+ * free; impb_peak_index accepts it as known_max and then skips its own max pass.
  */
 IMPB_API int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, int64_t M, int64_t L,
                                 int32_t precision, impb_plan** out);
@@ -80,7 +82,8 @@ IMPB_API int64_t impb_deconv_workspace_bytes(const impb_plan* plan, int64_t batc
 IMPB_API int32_t impb_deconv_plan_info(const impb_plan* plan, int64_t* nfft, int64_t* n1, int64_t* n2);
 IMPB_API int32_t impb_deconv_execute(impb_plan* plan, const void* rec, const int64_t* in_offsets, int64_t ld_in,
                             int32_t in_fmt, int64_t len, void* out, int64_t ld_out, int32_t out_f64,
-                            int64_t out_offset, int64_t out_len, int64_t batch, void* workspace, void* stream);
+                            int64_t out_offset, int64_t out_len, double* absmax_out, int64_t batch,
+                            void* workspace, void* stream);
 /* name and launch count of the kernels one execute() issues (bench.py gpu_launches accounting) */
 IMPB_API int32_t impb_deconv_launches_per_execute(const impb_plan* plan, int64_t batch);
 
@@ -89,10 +92,11 @@ IMPB_API int32_t impb_deconv_launches_per_execute(const impb_plan* plan, int64_t
  * core/decay.py:12-41: m = max|x|; if m < 1e-20 -> start; first strict local maximum (plateau midpoint,
  * scipy _local_maxima_1d) of x/m or -x/m that is >= height; else argmax|x|.  Segment r is
  * x[offsets[r] : offsets[r] + lengths[r]]; peak_out[r] is relative to the segment start; max_len = the
- * longest segment (grid sizing only); height must be > 0.  Bit-exact. */
+ * longest segment (grid sizing only); height must be > 0; known_max (nullable, device double[batch]) = max|segment|
+ * if the caller already has it (it must be exact: it is the normalisation divisor).  Bit-exact. */
 IMPB_API int32_t impb_peak_index(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,
-                        const impb_view* view, double height, int64_t* peak_out, int64_t batch, int64_t max_len,
-                        void* stream);
+                        const impb_view* view, const double* known_max, double height, int64_t* peak_out,
+                        int64_t batch, int64_t max_len, void* stream);
 
 /* ---- K4: Lundeby decay parameters ----------------------------------------------------------------
  * Replaces decay.decay_params(), core/decay.py:44-260 (called by HRIR.crop_tails, core/hrir.py:627-636).
