@@ -66,3 +66,16 @@ def write_wav(file_path, fs, data, bit_depth=32):
     else:
         q = quantize_pcm(data, bit_depth)
     wavfile.write(file_path, int(fs), q)
+
+
+def magnitude_response(x, fs):
+    """Reference ``core/audio_io.py:100-113``: ``(f, 20*log10|rfft(x)|)`` for the first ``ceil(n/2)`` bins,
+    computed on the device (K8).  No CPU path: lengths that are not 5-smooth are rejected by the plan."""
+    import torch
+    from . import ops
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    nfft = len(x)
+    half = int(np.ceil(nfft / 2))
+    dev = torch.device("cuda", int(os.environ.get("IMPULCIFER_B200_DEVICE", "0")))
+    mag = ops.magnitude_db(torch.from_numpy(x).to(dev)).cpu().numpy()[0]
+    return np.arange(half) * (fs / nfft), mag

@@ -355,6 +355,50 @@ class BatchDispatcher:
         return out
 
 
+def equalization_firs(items, room_frs, hp_left, hp_right, eq_left, eq_right, target, common_freq, estimator_fs,
+                      max_gain=40, f_res=5):
+    """Batched ``process_equalization_worker`` (reference ``core/parallel_workers.py:69-131``) — the work the
+    reference maps over a ProcessPoolExecutor at ``core/pipeline.py:674-688``.
+
+    ``items``: [(speaker, side), ...].  Returns ``[(speaker, side, fir), ...]`` in input order, like
+    ``parallel_map`` does.  The error curves are summed on the host exactly as the worker does; the four
+    Savitzky-Golay blends of ``smoothen_heavy_light`` and the minimum-phase design run as ONE launch each over all
+    items; ``FrequencyResponse.equalize`` (kink set + k=2 spline) stays per item on the host."""
+    from .frequency_response import FrequencyResponse
+    items = list(items)
+    if not items:
+        return []
+    freq = np.asarray(common_freq, dtype=np.float64)
+    frs = []
+    for speaker, side in items:
+        fr = FrequencyResponse(name=f'{speaker}-{side} eq', frequency=freq.copy(), raw=0, error=0)
+        if room_frs is not None and speaker in room_frs and side in room_frs[speaker]:
+            fr.error += room_frs[speaker][side].error
+        hp_eq = hp_left if side == 'left' else hp_right
+        if hp_eq is not None:
+            fr.error += hp_eq.error
+        eq = eq_left if side == 'left' else eq_right
+        if eq is not None and hasattr(eq, 'error'):
+            fr.error += eq.error
+        fr.error -= target.raw
+        frs.append(fr)
+    err = np.stack([fr.error for fr in frs])
+    raw = np.stack([fr.raw for fr in frs])
+    if np.any(np.isnan(err)) or np.any(np.isnan(raw)):
+        raise ValueError('NaN values present, cannot smoothen!')
+    # smoothen_heavy_light for every item at once (reference autoeq/frequency_response.py:1181-1239)
+    light = smoothen_batch(freq, err, 1 / 6, 1, 1 / 3, 1, 100, 10000)
+    heavy = smoothen_batch(freq, err, 1 / 3, 1, 1.3, 1, 1000, 6000)
+    both = smoothen_batch(freq, np.concatenate([raw, np.maximum(light, heavy)]), 1 / 3, 1, 1 / 3, 1, 100, 10000)
+    n = len(frs)
+    for i, fr in enumerate(frs):
+        fr.smoothed, fr.error_smoothed = both[i], both[n + i]
+        fr.equalize(max_gain=max_gain, treble_f_lower=10000, treble_f_upper=estimator_fs / 2)
+    firs = minimum_phase_batch(freq, np.stack([fr.equalization for fr in frs]), fs=estimator_fs, f_res=f_res,
+                               normalize=False)
+    return [(spk, side, firs[i]) for i, (spk, side) in enumerate(items)]
+
+
 class DeviceShard:
     """Partition of recording sets over ranks (one process per GPU).  Sets are independent and never split
     (crop_heads / align / crop_tails / normalize couple all responses of a set), so the

@@ -13,7 +13,9 @@ metrics, CSV I/O ...) keeps running the reference's code on top of them:
     HRIR                      <- hrir.HRIR                          , core.hrir.HRIR
     FrequencyResponse         <- frequency_response.FrequencyResponse, autoeq.frequency_response.FrequencyResponse
 
-and rebinds every already-imported module attribute that still points at the reference classes.
+and rebinds every already-imported module attribute that still points at the reference classes.  The EQ stage's
+``parallel_map(process_equalization_worker, ...)`` call (core/pipeline.py:674-688) is routed to
+``dispatcher.equalization_firs``; every other ``parallel_map`` use keeps the reference's pools.
 Nothing in the reference tree is edited.  See INTEGRATION.md.
 """
 from __future__ import annotations
@@ -66,6 +68,24 @@ def install(verbose: bool = False):
             if isinstance(v, type) and v in mapping:
                 d[k] = mapping[v]
                 rebound += 1
+    # the process pool of the EQ stage (core/pipeline.py:674-688) -> one batched launch per stage
+    from core import parallel_utils as ref_pu
+    pool_map = ref_pu.parallel_map
+
+    def parallel_map(func, items, max_workers=None, initializer=None, initargs=(), **kw):
+        if getattr(func, '__name__', '') == 'process_equalization_worker' and len(initargs) == 8:
+            from .dispatcher import equalization_firs
+            return equalization_firs(list(items), *initargs)
+        return pool_map(func, items, max_workers, initializer, initargs, **kw)
+
+    parallel_map.__doc__ = pool_map.__doc__
+    parallel_map.__wrapped__ = pool_map
+    for mod in list(sys.modules.values()):
+        d = getattr(mod, '__dict__', None)
+        if d and d.get('parallel_map') is pool_map:
+            d['parallel_map'] = parallel_map
+            rebound += 1
+    _installed.update(parallel_map=parallel_map)
     _installed.update(ImpulseResponseEstimator=ImpulseResponseEstimator, ImpulseResponse=ImpulseResponse, HRIR=HRIR,
                       FrequencyResponse=FrequencyResponse, rebound=rebound)
     if verbose:

@@ -31,3 +31,7 @@ def test_install_rebinds_reference_classes():
     assert est.estimate.__func__.__module__.startswith('impulcifer_pip313_b200')
     assert hasattr(est, 'sweep_sequence')  # reference-only method reachable through the merged class
     assert sys.modules['core.room_correction'].__dict__.get('HRIR', got['HRIR']) is got['HRIR']
+    # the EQ process pool is routed to the batched device path, everything else keeps the reference pool
+    from core import parallel_utils
+    assert parallel_utils.parallel_map is got['parallel_map']
+    assert parallel_utils.parallel_map(abs, [-1, -2, 3], use_threads=True) == [1, 2, 3]

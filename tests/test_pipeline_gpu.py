@@ -343,3 +343,33 @@ def test_192khz_resample_smooth_minphase(T):
     fir = fr.minimum_phase_impulse_response(fs=48000, f_res=5, normalize=False)
     ref_fir = O.minimum_phase_impulse_response(f, fr.equalization, fs=48000, f_res=5, normalize=False)
     assert fir.shape == (9600,) and rel_peak_err(fir, ref_fir) < 5e-6
+
+
+def test_equalization_firs_batch_matches_worker_golden(T):
+    """The batched replacement of process_equalization_worker (core/parallel_workers.py:69-131): same FIRs, same
+    input order as parallel_map, one launch per stage for all (speaker, side) items."""
+    from impulcifer_pip313_b200 import FrequencyResponse
+    from impulcifer_pip313_b200.dispatcher import equalization_firs
+    g = load('synth71_golden.npz')
+    f = g['fr_frequency']
+    fs = 48000
+    names = [str(n).split('-') for n in g['fr_names']]
+    # golden: error = raw - mean(raw) per item, target 0  ->  feed it as the room error of each (speaker, side)
+    room = {}
+    for (s, e), raw in zip(names, g['fr_raw']):
+        room.setdefault(s, {})[e] = FrequencyResponse(name='room', frequency=f, raw=raw, error=raw - np.mean(raw))
+    target = FrequencyResponse(name='target', frequency=f, raw=np.zeros(len(f)))
+    out = equalization_firs([(s, e) for s, e in names], room, None, None, None, None, target, f, fs)
+    assert [(s, e) for s, e, _ in out] == [(s, e) for s, e in names]
+    for i, (_, _, fir) in enumerate(out):
+        assert fir.shape == (9600,) and rel_peak_err(fir, g['eqw_fir'][i]) < 5e-6
+
+
+def test_magnitude_response_function(T):
+    from impulcifer_pip313_b200.audio_io import magnitude_response
+    x = np.random.default_rng(8).standard_normal(21600) * np.exp(-np.arange(21600) / 3000.0)
+    f, m = magnitude_response(x, 48000)
+    fo, mo = O.magnitude_response(x, 48000)
+    assert np.array_equal(f, fo) and np.max(np.abs(m - mo)) < 1e-8
+    with pytest.raises(Exception):
+        magnitude_response(np.ones(2 * 3 * 7 * 11 * 13), 48000)  # not 5-smooth: rejected, never approximated
