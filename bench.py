@@ -95,7 +95,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sets", type=int, default=int(os.environ.get("BENCH_SETS", "32")),
+    ap.add_argument("--sets", type=int, default=int(os.environ.get("BENCH_SETS", "64")),
                     help="recording sets per GPU per step")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--no-cpu-baseline", action="store_true")

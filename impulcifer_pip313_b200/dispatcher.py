@@ -261,7 +261,7 @@ class BatchDispatcher:
         return results
 
     # ---- host buffers in, host buffers out ------------------------------------------------------------------
-    def process_host(self, recordings, out=None, chunk_sets=8, precision=None):
+    def process_host(self, recordings, out=None, chunk_sets=None, precision=None):
         """``process`` for recordings that live in (pinned) HOST memory: ``[S, n_tracks, n_samples]`` float64,
         float32 or int32 PCM (the samples of a PCM WAV exactly as stored; scaled by 2^-31 inside K1).
 
@@ -270,6 +270,8 @@ class BatchDispatcher:
         ``SetResult`` with ``data`` in host memory (views of ``out`` if a pinned float64 buffer is passed)."""
         import torch
         S = recordings.shape[0]
+        if chunk_sets is None:
+            chunk_sets = int(__import__('os').environ.get("IMPULCIFER_B200_CHUNK_SETS", "8"))
         dev = torch.device("cuda", self.estimator.device)
         key = (tuple(recordings.shape), recordings.dtype, chunk_sets)
         st = getattr(self, "_host_state", None)

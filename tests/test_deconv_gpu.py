@@ -119,3 +119,34 @@ def test_demo_recording_golden(torch_cuda):
     rec = inp['room-FC-left.wav'].astype(np.float64) / 2 ** 31
     y = est.estimate(rec[96000:])
     assert_ck(y, gold['est_ck_FC-left'], rel=1e-8)
+
+
+def test_full_size_properties(torch_cuda):
+    """Size-independent properties at the headline size (L = 391 270): time-shift equivariance, homogeneity,
+    empty input, and agreement of the three input formats."""
+    torch = torch_cuda
+    est = _est(5.0, 48000)
+    L = 2 * est.fs + len(est)
+    rng = np.random.default_rng(21)
+    x = np.zeros(L)
+    x[40000:40000 + len(est)] = est.test_signal * 0.4
+    x += 1e-4 * rng.standard_normal(L)
+    y = est.estimate(x)
+    assert y.shape == (L,) and y.dtype == np.float64
+    # delaying the recording by d samples delays the response by d (samples pushed past the end are lost)
+    d = 777
+    xd = np.concatenate([np.zeros(d), x[:-d]])
+    yd = est.estimate(xd)
+    pk = int(np.argmax(np.abs(y)))
+    assert int(np.argmax(np.abs(yd))) == pk + d
+    assert rel_peak_err(yd[pk + d - 2000:pk + d + 20000], y[pk - 2000:pk + 20000]) < 1e-9
+    # homogeneity
+    assert rel_peak_err(est.estimate(-2.5 * x), -2.5 * y) < 1e-12
+    # empty recording
+    assert est.estimate(np.zeros(0)).shape == (0,)
+    # f32 and int32-PCM containers of exactly representable samples give the f64 result
+    q = np.rint(x * 2 ** 23) / 2 ** 23            # 24-bit samples: exact in f32 and in PCM_32
+    ref = est.estimate_batch(q[None, :])[0]
+    got32 = est.estimate_batch(torch.from_numpy(q.astype(np.float32)[None, :]).cuda()).cpu().numpy()[0]
+    gotpcm = est.estimate_batch(torch.from_numpy(np.rint(q * 2 ** 31).astype(np.int32)[None, :]).cuda()).cpu().numpy()[0]
+    assert np.array_equal(got32, ref) and np.array_equal(gotpcm, ref)

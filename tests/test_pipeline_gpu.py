@@ -373,3 +373,26 @@ def test_magnitude_response_function(T):
     assert np.array_equal(f, fo) and np.max(np.abs(m - mo)) < 1e-8
     with pytest.raises(Exception):
         magnitude_response(np.ones(2 * 3 * 7 * 11 * 13), 48000)  # not 5-smooth: rejected, never approximated
+
+
+def test_ragged_recording_clipped_last_column(T, est48):
+    """A file whose last column is clipped (still >= one sweep) keeps that column at its own length
+    (reference core/hrir.py:194-216); both columns go through the batched path with different lengths."""
+    from impulcifer_pip313_b200 import HRIR
+    fs = 48000
+    rng = np.random.default_rng(12)
+    n_samples = 96000 + 391270 + 350000
+    rec = 1e-4 * rng.standard_normal((1, n_samples))
+    for start, g in ((96000 + 30000, 0.5), (96000 + 391270 + 20000, 0.3)):
+        rec[0, start:start + len(est48)] += g * est48.test_signal
+    h = HRIR(est48)
+    h.ingest(rec, fs, ['FL', 'FR'], side='left')
+    irs = O.open_recording(rec, fs, ['FL', 'FR'], est48.inverse_filter, fs, side='left')
+    assert len(h.irs['FL']['left']) == 391270 and len(h.irs['FR']['left']) == 350000
+    for s in ('FL', 'FR'):
+        assert rel_peak_err(h.irs[s]['left'].data, irs[s]['left']) < 1e-9
+        assert h.irs[s]['left'].peak_index() == O.peak_index(irs[s]['left'])
+    with pytest.raises(ValueError, match="Sampling rate"):
+        h.ingest(rec, 44100, ['FL', 'FR'], side='left')
+    with pytest.raises(ValueError, match="No valid columns"):
+        h.ingest(rec[:, :96000 + 1000], fs, ['FL'], side='left')
