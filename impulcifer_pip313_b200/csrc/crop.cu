@@ -347,8 +347,76 @@ __device__ int64_t nearest_t(double t, double step, int64_t ns) {
   return best;
 }
 
+// ---- grid-wide passes feeding k_lundeby: the two full reads of the analysis window [pk, pk + 2 s) ----------------
+__device__ __forceinline__ int lb_block_size(int64_t ns) {
+  int bs = 32;
+  while ((ns + bs - 1) / bs > LB_MAXBLK) bs <<= 1;
+  return bs;
+}
+
+// max |v[pk + i]|, i < ns, grid = (rows, chunks)
+__global__ void __launch_bounds__(256) k_lb_segmax(const double* __restrict__ x, const ViewArgs va, int64_t r0, int fs,
+                                                   const int64_t* __restrict__ peaks,
+                                                   unsigned long long* __restrict__ segmax) {
+  const int64_t r = blockIdx.x;
+  const RowView ir(x, va, r0 + r);
+  if (ir.n < 10) return;
+  const int64_t pk = peaks[r];
+  const int64_t ns = min(pk + (int64_t)(2 * fs), ir.n) - pk;
+  int64_t lo, hi;
+  chunk_bounds(ns, &lo, &hi);
+  if (lo >= hi) return;
+  double m = 0.0;
+  int64_t i = lo + threadIdx.x;
+  for (; i + 768 < hi; i += 1024) {
+    const double a0 = ir[pk + i], a1 = ir[pk + i + 256], a2 = ir[pk + i + 512], a3 = ir[pk + i + 768];
+    m = fmax(fmax(m, fmax(fabs(a0), fabs(a1))), fmax(fabs(a2), fabs(a3)));
+  }
+  for (; i < hi; i += 256) m = fmax(m, fabs(ir[pk + i]));
+  for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(segmax + r, (unsigned long long)__double_as_longlong(m));
+}
+
+// blk[r][k] = sum of sq over the k-th aligned block of bs samples (one warp per block), grid = (rows, chunks)
+__global__ void __launch_bounds__(256) k_lb_blocksums(const double* __restrict__ x, const ViewArgs va, int64_t r0, int fs,
+                                                      const int64_t* __restrict__ peaks,
+                                                      const unsigned long long* __restrict__ segmax,
+                                                      double* __restrict__ blk) {
+  const int64_t r = blockIdx.x;
+  const RowView ir(x, va, r0 + r);
+  if (ir.n < 10) return;
+  const int64_t pk = peaks[r];
+  const int64_t ns = min(pk + (int64_t)(2 * fs), ir.n) - pk;
+  const int bs = lb_block_size(ns);
+  const int nblk = (int)((ns + bs - 1) / bs);
+  const double mx = __longlong_as_double((long long)segmax[r]);
+  const SqView sq{&ir, pk, mx, mx >= kEps, nullptr, bs};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (nblk + gridDim.y - 1) / gridDim.y;
+  const int k_end = min(nblk, (int)(blockIdx.y + 1) * per);
+  for (int k0 = blockIdx.y * per + warp; k0 < k_end; k0 += 32) {  // 8 warps x 4 blocks in flight
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u * 8;
+      if (k < k_end) {
+        const int64_t a = (int64_t)k * bs, b = min(ns, a + bs);
+        for (int64_t i = a + lane; i < b; i += 32) acc[u] += sq(i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      for (int o = 16; o; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      const int k = k0 + u * 8;
+      if (lane == 0 && k < k_end) blk[(size_t)r * LB_MAXBLK + k] = acc[u];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict__ x, const ViewArgs va, int64_t r0, int fs,
-                                                        const int64_t* __restrict__ peaks, int64_t* __restrict__ peak_out,
+                                                        const int64_t* __restrict__ peaks,
+                                                        const unsigned long long* __restrict__ segmax,
+                                                        const double* __restrict__ blk_g, int64_t* __restrict__ peak_out,
                                                         int64_t* __restrict__ knee_out, double* __restrict__ noise_out,
                                                         int64_t* __restrict__ win_out) {
   extern __shared__ __align__(16) unsigned char lb_smem[];
@@ -367,19 +435,15 @@ __global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict
   const int64_t pk = peaks[r];
   const int64_t stop = min(pk + (int64_t)(2 * fs), n_ir);
   const int64_t ns = stop - pk;  // >= 1 because pk <= n_ir - 1
-  double mx = 0.0;
+  // the two full reads of the window (max, block sums of sq) were done by grid-wide kernels
+  const double mx = __longlong_as_double((long long)segmax[r]);
+  SqView sq{&ir, pk, mx, mx >= kEps, sh.blk, lb_block_size(ns)};
   {
-    int64_t i = threadIdx.x;
-    for (; i + 3 * LB_THREADS < ns; i += 4 * LB_THREADS) {
-      const double a0 = ir[pk + i], a1 = ir[pk + i + LB_THREADS], a2 = ir[pk + i + 2 * LB_THREADS],
-                   a3 = ir[pk + i + 3 * LB_THREADS];
-      mx = fmax(fmax(mx, fmax(fabs(a0), fabs(a1))), fmax(fabs(a2), fabs(a3)));
-    }
-    for (; i < ns; i += LB_THREADS) mx = fmax(mx, fabs(ir[pk + i]));
+    const int nblk = (int)((ns + sq.bs - 1) / sq.bs);
+    const double* mine = blk_g + (size_t)r * LB_MAXBLK;
+    for (int k = threadIdx.x; k < nblk; k += LB_THREADS) sh.blk[k] = mine[k];
+    __syncthreads();
   }
-  mx = block_max(mx, sh);
-  SqView sq{&ir, pk, mx, mx >= kEps, nullptr, 32};
-  build_block_sums(sq, ns, sh);
   const double step = ns > 1 ? ((double)ns / (double)fs) / (double)(ns - 1) : 0.0;  // linspace(0, ns/fs, ns)
   const double t_last = (double)(ns - 1) * step;
 
@@ -664,12 +728,24 @@ int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, con
   if (!rc) {
     cudaError_t e = cudaFuncSetAttribute(k_lundeby, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(LundebyShared));
-    for (int64_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += (int64_t)1 << 30) {
-      const int64_t nb = std::min<int64_t>((int64_t)1 << 30, batch - b0);
-      k_lundeby<<<(unsigned)nb, LB_THREADS, sizeof(LundebyShared), st>>>(x, va, b0, fs, peaks + b0, peak_out + b0,
-                                                                        knee_out + b0, noise_db_out + b0, win_out + b0);
+    const int64_t rows_per = std::min<int64_t>(batch, 16384);  // 24 KB of block sums per row
+    unsigned long long* segmax = nullptr;
+    double* blk = nullptr;
+    if (e == cudaSuccess) e = cudaMallocAsync(&segmax, sizeof(unsigned long long) * rows_per, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&blk, sizeof(double) * LB_MAXBLK * rows_per, st);
+    const unsigned chunks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((2 * (int64_t)fs + 4095) / 4096, 256));
+    for (int64_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += rows_per) {
+      const int64_t nb = std::min<int64_t>(rows_per, batch - b0);
+      e = cudaMemsetAsync(segmax, 0, sizeof(unsigned long long) * nb, st);
+      k_lb_segmax<<<dim3((unsigned)nb, chunks), 256, 0, st>>>(x, va, b0, fs, peaks + b0, segmax);
+      k_lb_blocksums<<<dim3((unsigned)nb, chunks), 256, 0, st>>>(x, va, b0, fs, peaks + b0, segmax, blk);
+      k_lundeby<<<(unsigned)nb, LB_THREADS, sizeof(LundebyShared), st>>>(x, va, b0, fs, peaks + b0, segmax, blk,
+                                                                        peak_out + b0, knee_out + b0, noise_db_out + b0,
+                                                                        win_out + b0);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
+    if (segmax) cudaFreeAsync(segmax, st);
+    if (blk) cudaFreeAsync(blk, st);
     if (e != cudaSuccess) rc = cuda_fail(e, "k_lundeby");
   }
   cudaFreeAsync(peaks, st);

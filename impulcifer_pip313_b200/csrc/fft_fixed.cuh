@@ -15,6 +15,10 @@
 namespace impb {
 
 constexpr int kTripUnroll = IMPB_TRIP_UNROLL;
+#ifndef IMPB_PREFETCH
+#define IMPB_PREFETCH 0
+#endif
+constexpr bool kPrefetch = IMPB_PREFETCH != 0;
 
 template <int R0_, int R1_, int R2_> struct Radix3 {
   static constexpr int R0 = R0_, R1 = R1_, R2 = R2_;
@@ -61,13 +65,25 @@ __device__ __forceinline__ void fx_twiddles(const cx_t<T>* __restrict__ tw, int 
 // multiplier per OUTPUT element (four-step twiddle); it is fetched at the top of the trip so that its latency
 // hides behind the butterfly instead of sitting in front of the store.
 struct NoPost {};
-template <typename T, int TILE, int NT, int S, int LEN, int R, bool INV, bool ROW, class LD, class ST, class POST>
+template <typename T, int TILE, int NT, int S, int LEN, int R, bool INV, bool ROW, bool PF = false, class LD, class ST,
+          class POST>
 __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, ST st, POST post) {
   constexpr int STRIDE = LEN / R;
   constexpr int PER_COL = S / R;
   constexpr int ITEMS = PER_COL * TILE;
   constexpr int TRIPS = (ITEMS + NT - 1) / NT;
   constexpr bool HAS_POST = !std::is_same<POST, NoPost>::value;
+  // PF (stages that read HBM): the operands of trip it+1 are requested before trip it is computed
+  cx_t<T> xn[PF ? R : 1];
+  if constexpr (PF) {
+    int c, j;
+    fx_decode<ROW, TILE, PER_COL>(threadIdx.x, c, j);
+    const int base = (j / STRIDE) * LEN + (j % STRIDE);
+    if ((ITEMS % NT) == 0 || threadIdx.x < ITEMS) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) xn[q] = ld(base + q * STRIDE, c);
+    }
+  }
 #pragma unroll kTripUnroll
   for (int it = 0; it < TRIPS; ++it) {
     const int w = threadIdx.x + it * NT;
@@ -82,8 +98,21 @@ __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, 
       for (int p = 0; p < R; ++p) m[p] = post(base + p * STRIDE, c);
     }
     cx_t<T> x[R];
+    if constexpr (PF) {
 #pragma unroll
-    for (int q = 0; q < R; ++q) x[q] = ld(base + q * STRIDE, c);
+      for (int q = 0; q < R; ++q) x[q] = xn[q];
+      const int w2 = w + NT;
+      if (it + 1 < TRIPS && ((ITEMS % NT) == 0 || w2 < ITEMS)) {
+        int c2, j2;
+        fx_decode<ROW, TILE, PER_COL>(w2, c2, j2);
+        const int base2 = (j2 / STRIDE) * LEN + (j2 % STRIDE);
+#pragma unroll
+        for (int q = 0; q < R; ++q) xn[q] = ld(base2 + q * STRIDE, c2);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < R; ++q) x[q] = ld(base + q * STRIDE, c);
+    }
     if (STRIDE > 1) {
       cx_t<T> wv[R];
       fx_twiddles<T, R, ROW, STRIDE>(tw, np, wv);
@@ -203,7 +232,7 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v, mx_re, mx_im); };
   auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
-  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false>(nullptr, gl, ss, NoPost{});
+  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false, kPrefetch>(nullptr, gl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true, false>(tw1, sl, ss, NoPost{});
   __syncthreads();
@@ -244,7 +273,7 @@ k_fx_conv(const cx_t<T>* __restrict__ tw0r, const cx_t<T>* __restrict__ tw1r, co
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<true, TILE, RX::S>(e, c)] = v; };
   auto pw = [&](int q, int w) -> cx_t<T> { return f.pw(t, RX::R2, ITEMS_MID, q, w); };
   auto post = [&](int e, int c) -> cx_t<T> { return f.post(t, e, c); };
-  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, true>(tw0r, gl, ss, NoPost{});
+  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, true, kPrefetch>(tw0r, gl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false, true>(tw1r, sl, ss, NoPost{});
   __syncthreads();
