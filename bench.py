@@ -91,11 +91,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_first_load = None   # set by the caller when the GPU starts doing the benchmark's work
+        self.t_timed = (None, None)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -103,13 +105,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0, t1 = self.t_timed
+        in_timed = 0
+        for ts, r in self.rows:
+            # samples taken while this process kept the GPU busy with the benchmark workload (warm-up steps
+            # run the same work as the timed steps); the short timed region alone can fall between two samples
+            if self.t_first_load is not None and ts < self.t_first_load:
+                continue
+            if t1 is not None and ts > t1 + 0.05:
+                continue
+            if t0 is not None and t0 <= ts <= t1 + 0.05:
+                in_timed += 1
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -121,7 +133,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_in_timed_region": in_timed,
+                "window": "warm-up + timed steps (same workload), nvidia-smi every 50 ms"}
 
 
 def measured_peak():
@@ -227,22 +240,31 @@ def main():
     def step():
         return disp.process(batch)
 
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)  # let nvidia-smi come up before the GPU gets busy
+    sampler.t_first_load = time.time()
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+    # keep the device under the same load until the sampler has seen it for a while
+    t_hold = time.time()
+    while rank == 0 and time.time() - t_hold < 0.4:
         res = step()
     tails = sorted({r.tail_ind for r in res})
     out_bytes = sum(r.data.numel() * 8 for r in res)
     launches_per_step = disp.launches
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_a = time.time()
     e0.record()
     for _ in range(args.steps):
         res = step()
     e1.record()
     barrier()
+    sampler.t_timed = (t_a, time.time())
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
