@@ -179,8 +179,47 @@ class HRIR:
         ref_len = len(next(iter(by_name.values())))
         return np.vstack([by_name.get(ch, np.zeros(ref_len)) for ch in track_order])
 
+    def pcm_frames(self, track_order=None, bit_depth=32):
+        """Interleaved PCM frames ``[n, n_tracks]`` exactly as ``write_wav`` stores them (gather in track order,
+        quantise, interleave on the device); host numpy int array."""
+        if track_order is None:
+            track_order = HEXADECAGONAL_TRACK_ORDER
+        if bit_depth not in (16, 24, 32):
+            raise ValueError('Invalid bit depth. Accepted values are 16, 24 and 32.')
+        named = {track_name(spk, side): ir for spk, side, ir in self._all()}
+        if not named:
+            raise ValueError("No impulse responses available for WAV output.")
+        ref_len = len(next(iter(named.values())))
+        present = [named[ch] for ch in track_order if ch in named]
+        if any(len(ir) != ref_len for ir in present):
+            raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
+        flat, offs, _ = _pack(present) if present else (None, [], [])
+        it = iter(offs)
+        row_offsets = [next(it) if ch in named else -1 for ch in track_order]
+        if flat is None:
+            return np.zeros((ref_len, len(track_order)), dtype=np.int16 if bit_depth == 16 else np.int32)
+        return ops.pack_tracks(flat, row_offsets, ref_len, bit_depth).cpu().numpy()
+
     def write_wav(self, file_path, track_order=None, bit_depth=32):
-        write_wav(file_path, self.fs, self.track_matrix(track_order), bit_depth=bit_depth)
+        """Reference :426-455 + core/audio_io.py:82-97.  Frames are packed on the device; the RIFF container is
+        written on the host (soundfile when importable, else scipy.io.wavfile)."""
+        import os
+        frames = self.pcm_frames(track_order, bit_depth)
+        d = os.path.dirname(file_path)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        if frames.shape[0] < frames.shape[1]:
+            # the reference transposes only when tracks outnumber samples' worth of rows (shape[1] > shape[0]);
+            # with fewer samples than tracks it would write the matrix untransposed: keep that quirk
+            write_wav(file_path, self.fs, self.track_matrix(track_order), bit_depth=bit_depth)
+            return
+        try:
+            import soundfile as sf
+            sub = {16: "PCM_16", 24: "PCM_24", 32: "PCM_32"}[bit_depth]
+            sf.write(file_path, frames if bit_depth != 24 else frames << 8, samplerate=self.fs, subtype=sub)
+        except ImportError:
+            from scipy.io import wavfile
+            wavfile.write(file_path, int(self.fs), frames if bit_depth != 24 else frames << 8)
 
     # ---- normalisation ------------------------------------------------------------------------------------
     def normalize(self, peak_target=-0.1, avg_target=None):

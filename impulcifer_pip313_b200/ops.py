@@ -382,3 +382,21 @@ def window_resample(x, taps, up, down, decay=None):
             None if tp is None else tp.data_ptr(), 0 if tp is None else tp.numel(), int(up) // g, int(down) // g,
             out.data_ptr(), n_out, batch, _stream(x)), "impb_window_resample")
     return out
+
+
+# ---- output packing -----------------------------------------------------------------------------------
+def pack_tracks(src, row_offsets, n, bit_depth=32):
+    """Interleaved PCM frames [n, n_tracks] (int32, or int16 for 16 bit) from track rows inside flat ``src``.
+    ``row_offsets[t]`` = element offset of track t, -1 = silent track."""
+    torch = _torch()
+    src = src.contiguous()
+    offs = as_index_tensor(row_offsets, src.device)
+    n_tracks = offs.numel()
+    if bit_depth not in (16, 24, 32):
+        raise ValueError('Invalid bit depth. Accepted values are 16, 24 and 32.')
+    out = torch.empty((int(n), n_tracks), dtype=torch.int16 if bit_depth == 16 else torch.int32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib().impb_pack_tracks(_lib.context(_dev(src)).handle, src.data_ptr(), _i64(offs), int(n),
+                                               n_tracks, int(bit_depth), out.data_ptr(), _stream(src)),
+                   "impb_pack_tracks")
+    return out

@@ -184,6 +184,14 @@ IMPB_API int32_t impb_window_resample(impb_ctx* ctx, const double* src, int64_t 
                              const double* taps, int64_t ntaps, int32_t up, int32_t down, double* dst,
                              int64_t ld_dst, int64_t batch, void* stream);
 
+/* ---- output packing (next-row component) -------------------------------------------------------
+ * Replaces the np.vstack / transpose / libsndfile PCM conversion of HRIR.write_wav (core/hrir.py:426-455) and
+ * audio_io.write_wav (core/audio_io.py:82-97).  row_offsets: device int64[n_tracks], element offset of each
+ * track's n samples inside src, or -1 for a silent (missing) track.  dst: interleaved [n][n_tracks] frames,
+ * int16 for bit_depth 16, int32 for 24 (value range +-2^23) and 32.  Rounding: lrint(x * 2^(bits-1)), clipped. */
+IMPB_API int32_t impb_pack_tracks(impb_ctx* ctx, const double* src, const int64_t* row_offsets, int64_t n,
+                         int32_t n_tracks, int32_t bit_depth, void* dst, void* stream);
+
 /* ceil(n * up / down) after reducing up/down by their gcd: the row length impb_window_resample writes */
 IMPB_API int64_t impb_resample_out_len(int64_t n, int32_t up, int32_t down);
 

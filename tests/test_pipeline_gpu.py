@@ -396,3 +396,29 @@ def test_ragged_recording_clipped_last_column(T, est48):
         h.ingest(rec, 44100, ['FL', 'FR'], side='left')
     with pytest.raises(ValueError, match="No valid columns"):
         h.ingest(rec[:, :96000 + 1000], fs, ['FL'], side='left')
+
+
+def test_pcm_packing_matches_host_quantiser_and_golden(T, est48):
+    """Device track gather + PCM quantise + interleave == host np.rint path, for 16/24/32 bit, incl. silent tracks,
+    ties (round half to even) and clipping; 32-bit frames of the demo set == room-responses.wav (see above)."""
+    from impulcifer_pip313_b200 import HRIR, ImpulseResponse
+    from impulcifer_pip313_b200.audio_io import quantize_pcm
+    from impulcifer_pip313_b200.constants import HESUVI_TRACK_ORDER
+    rng = np.random.default_rng(31)
+    n = 5000
+    h = HRIR(est48)
+    h.irs = {}
+    for spk in ('FL', 'FR', 'FC', 'SL'):
+        h.irs[spk] = {}
+        for side in ('left', 'right'):
+            x = rng.standard_normal(n) * 0.3
+            x[:8] = [1.0, -1.0, 1.5, -1.5, 0.5 / 2 ** 31, 1.5 / 2 ** 31, 2.5 / 2 ** 15, -0.5 / 2 ** 23]
+            h.irs[spk][side] = ImpulseResponse(x, 48000)
+    for order in (None, HESUVI_TRACK_ORDER):
+        m = h.track_matrix(order)
+        for bits in (16, 24, 32):
+            frames = h.pcm_frames(order, bits)
+            assert frames.shape == (n, m.shape[0])
+            assert np.array_equal(frames, quantize_pcm(m, bits).T), (bits,)
+    with pytest.raises(ValueError, match="Invalid bit depth"):
+        h.pcm_frames(None, 20)
