@@ -184,6 +184,7 @@ def main():
                     help="recording sets per GPU per step")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -293,6 +294,27 @@ def main():
         k1.append(a.elapsed_time(b))
     k1_ms = float(np.mean(k1))
     del k1_out
+    # FP32 fast path of the same kernel (f32 samples in, f32 out; -90 dB parity class), for reference
+    fp32 = None
+    if args.precision == 64 and not args.no_fp32:
+        plan32 = est.plan(L, precision=32)
+        x32 = batch.to(torch.float32)
+        o32 = torch.empty((B, L), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            plan32.execute(x32.reshape(-1), out=o32, length=L, row_offsets=row_offs)
+        torch.cuda.synchronize()
+        t32 = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            plan32.execute(x32.reshape(-1), out=o32, length=L, row_offsets=row_offs)
+            b.record()
+            torch.cuda.synchronize()
+            t32.append(a.elapsed_time(b))
+        ms32 = float(np.mean(t32))
+        fp32 = {"k1_ms_per_launch": ms32, "k1_ir_per_s": B / (ms32 / 1e3), "algorithmic_bytes_per_ir": 8 * L,
+                "achieved_gbs": B * 8 * L / (ms32 / 1e3) / 1e9}
+        del x32, o32, plan32
     bytes_per_ir = (8 + (8 if args.precision == 64 else 4)) * L
     peak, peak_src = measured_peak()
     achieved = B * bytes_per_ir / (k1_ms / 1e3) / 1e9
@@ -360,6 +382,9 @@ def main():
             line["roofline"]["traffic"] = tr.get("dram_bytes_per_ir", 0) * B
         except Exception:
             pass
+        if fp32 is not None:
+            fp32["frac_of_peak"] = fp32["achieved_gbs"] / peak
+            line["fp32_fast_path"] = fp32
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -256,8 +256,9 @@ template <typename T> struct DeconvEngine {
     if (TILE == FULL && fft.col_fixed && fft.row_fixed && !no_fixed) {
       const Plan2D& p = fft.p;
       static const bool no_async = getenv("IMPB_NO_ASYNC") != nullptr;
-      if constexpr (sizeof(T) == 8 && TILE == FULL) {
-        if (a.in_fmt == IMPB_FMT_F64 && !no_async) {
+      if constexpr (TILE == FULL) {
+        // the staged copy moves raw samples: the input must already be in the tile's arithmetic type
+        if (a.in_fmt == (sizeof(T) == 8 ? IMPB_FMT_F64 : IMPB_FMT_F32) && !no_async) {
           rc = fx_fwd_async<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
                                      DeconvColIn<T, TILE, true>{a});
         } else {

@@ -40,7 +40,11 @@ template <bool ROW, int TILE, int PER_COL> __device__ __forceinline__ void fx_de
   if (ROW) { j = w % PER_COL; c = w / PER_COL; } else { c = w % TILE; j = w / TILE; }
 }
 template <bool ROW, int TILE, int S> __device__ __forceinline__ int fx_smem(int e, int c) {
-  return ROW ? c * S + (e ^ ((e >> 3) & 7)) : e * TILE + (c ^ (e & (TILE - 1)));
+  if (!ROW) return e * TILE + (c ^ (e & (TILE - 1)));
+  if (TILE == 8) return c * S + (e ^ ((e >> 3) & 7));  // 16-byte elements: 8 slots per 128 B, quarter-warps
+  // 8-byte elements (FP32 tiles): a half-warp must cover 16 distinct slots for strides 96, 8 and 1
+  const int v = e >> 4;
+  return c * S + (e ^ (v & 7) ^ (((v >> 1) & 1) << 3));
 }
 
 // Stage twiddles w_p = exp(-2 pi i np p / LEN), p = 1..R-1, from the power-of-two entries of the table only
@@ -186,15 +190,17 @@ k_fx_fwd(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
 // the tile is in flight at once and none of them occupies a register, so the pass is bound by HBM bandwidth
 // instead of (trips x HBM latency).  F::src(b, t, e, c, which) returns the address of the real sample that
 // becomes the re (which = 0) / im (which = 1) part of element (e, c), or nullptr for a zero.
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+template <int BYTES> __device__ __forceinline__ void cp_async_n(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+  if (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 
 template <typename T, int TILE, int NT, class RX, class F>
 __global__ void __launch_bounds__(NT, 2)
 k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
-  static_assert(sizeof(T) == 8, "cp.async staging is written for FP64 tiles");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
   const int t = blockIdx.x, b = blockIdx.y;
@@ -203,8 +209,8 @@ k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1,
     T* dst = reinterpret_cast<T*>(&tile[fx_smem<false, TILE, RX::S>(e, c)]);
     const T* re = f.src(b, t, e, c, 0);
     const T* im = f.src(b, t, e, c, 1);
-    if (re) cp_async_8(dst, re); else dst[0] = (T)0;
-    if (im) cp_async_8(dst + 1, im); else dst[1] = (T)0;
+    if (re) cp_async_n<sizeof(T)>(dst, re); else dst[0] = (T)0;
+    if (im) cp_async_n<sizeof(T)>(dst + 1, im); else dst[1] = (T)0;
   }
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
