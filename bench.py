@@ -315,6 +315,23 @@ def main():
         fp32 = {"k1_ms_per_launch": ms32, "k1_ir_per_s": B / (ms32 / 1e3), "algorithmic_bytes_per_ir": 8 * L,
                 "achieved_gbs": B * 8 * L / (ms32 / 1e3) / 1e9}
         del x32, o32, plan32
+    # secondary: per-IR frequency-response post-processing on the cropped responses of one step
+    for _ in range(2):
+        post = disp.postprocess(res)
+    torch.cuda.synchronize()
+    tp = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        post = disp.postprocess(res)
+        b.record()
+        torch.cuda.synchronize()
+        tp.append(a.elapsed_time(b))
+    fr_ms = float(np.mean(tp))
+    fr_post = {"value": S * N_IRS / (fr_ms / 1e3), "unit": "IR/s", "ms_per_step": fr_ms, "fir_taps": int(post[0][3].shape[1]),
+               "what": "frequency_response + smoothen_fractional_octave(1/3) + minimum_phase_impulse_response(f_res=5) "
+                       "per cropped IR (BatchDispatcher.postprocess), device resident, one GPU"}
+    del post
     bytes_per_ir = (8 + (8 if args.precision == 64 else 4)) * L
     peak, peak_src = measured_peak()
     achieved = B * bytes_per_ir / (k1_ms / 1e3) / 1e9
@@ -382,6 +399,7 @@ def main():
             line["roofline"]["traffic"] = tr.get("dram_bytes_per_ir", 0) * B
         except Exception:
             pass
+        line["fr_postprocess"] = fr_post
         if fp32 is not None:
             fp32["frac_of_peak"] = fp32["achieved_gbs"] / peak
             line["fp32_fast_path"] = fp32
