@@ -43,6 +43,7 @@ SIGNATURES = {
     "impb_fft_destroy": (None, [c_vp]),
     "impb_fft_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "impb_magnitude_db": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "impb_magnitude_lin": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "impb_loglerp": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "impb_savgol_blend": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp,
                                   c_vp, c_vp, c_i64, c_i64, c_vp]),

@@ -22,6 +22,8 @@ TRUEHD_13CH_ORDER = ['FL', 'FR', 'FC', 'BL', 'BR', 'SL', 'SR', 'TFL', 'TFR', 'TS
 CHANNEL_LAYOUT_MAP = {11: TRUEHD_11CH_ORDER, 13: TRUEHD_13CH_ORDER}
 
 SPEAKER_DELAYS = {s: 0 for s in SPEAKER_NAMES}
+# SPL change relative to the middle of the head (reference core/constants.py:80-83: all zero)
+IR_ROOM_SPL = {s: {'left': 0.0, 'right': 0.0} for s in SPEAKER_NAMES}
 
 IPSILATERAL_PAIRS = (("FL", "FR"), ("SL", "SR"), ("BL", "BR"), ("TFL", "TFR"), ("TSL", "TSR"), ("TBL", "TBR"),
                      ("FC", "FC"), ("WL", "WR"))

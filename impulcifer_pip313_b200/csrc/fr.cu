@@ -1,5 +1,6 @@
 // Per-IR frequency-response post-processing on the device.
 //   impb_magnitude_db   audio_io.magnitude_response                      core/audio_io.py:100-113
+//   impb_magnitude_lin  abs(rfft(seg, n=nfft)) of the direct-sound windows    core/microphone_deviation_correction.py:130-133
 //   impb_loglerp        InterpolatedUnivariateSpline(log10 f, y, k=1)    autoeq/frequency_response.py:874-894
 //   impb_savgol_blend   FrequencyResponse._smoothen_fractional_octave    autoeq/frequency_response.py:1060-1105
 //   impb_minphase_fir   firwin2 + minimum_phase(homomorphic, half=True)  autoeq/frequency_response.py:672-680,
@@ -72,6 +73,14 @@ struct MagDbOp {
   int64_t ld, half;
   __device__ __forceinline__ void operator()(int b, size_t, int64_t k, double2 v) const {
     if (k < half) out[(size_t)b * ld + k] = 20.0 * log10(hypot(v.x, v.y));
+  }
+};
+
+struct MagLinOp {  // |X[k]| for k < nbins (natural order)
+  double* out;
+  int64_t ld, nbins;
+  __device__ __forceinline__ void operator()(int b, size_t, int64_t k, double2 v) const {
+    if (k < nbins) out[(size_t)b * ld + k] = hypot(v.x, v.y);
   }
 };
 
@@ -391,6 +400,30 @@ int32_t impb_magnitude_db(impb_fft* f, const double* x, int64_t ld_x, double* ma
     if (rc) return rc;
     RowFwdOp<MagDbOp> ro{ws + (size_t)b0 * p.N, p.N, p.N1, p.N2, f->f.perm_col, f->f.perm_row,
                          MagDbOp{mag_out + (size_t)b0 * ld_out, ld_out, half}};
+    if ((rc = f->f.row_fwd<TILE>(ro, nb, st))) return rc;
+  }
+  return IMPB_OK;
+}
+
+int32_t impb_magnitude_lin(impb_fft* f, const double* x, int64_t ld_x, int64_t n_valid, double* mag_out, int64_t ld_out,
+                           int64_t n_bins, int64_t batch, void* workspace, void* stream) {
+  if (!f || !x || !mag_out || !workspace || batch < 0 || n_valid < 0 || n_valid > f->n || ld_x < n_valid || n_bins < 0 ||
+      n_bins > f->n / 2 + 1 || ld_out < n_bins) {
+    set_error("impb_magnitude_lin: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0 || n_bins == 0) return IMPB_OK;
+  DeviceGuard g(f->ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const Plan2D& p = f->f.p;
+  double2* ws = (double2*)workspace;
+  for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+    const int nb = (int)std::min<int64_t>(32768, batch - b0);
+    RealColIn ci{x + (size_t)b0 * ld_x, ld_x, n_valid, ws + (size_t)b0 * p.N, f->f.tw, p.N, p.N2};
+    int rc = f->f.col_fwd<TILE>(ci, nb, st);
+    if (rc) return rc;
+    RowFwdOp<MagLinOp> ro{ws + (size_t)b0 * p.N, p.N, p.N1, p.N2, f->f.perm_col, f->f.perm_row,
+                          MagLinOp{mag_out + (size_t)b0 * ld_out, ld_out, n_bins}};
     if ((rc = f->f.row_fwd<TILE>(ro, nb, st))) return rc;
   }
   return IMPB_OK;

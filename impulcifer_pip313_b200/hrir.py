@@ -22,7 +22,7 @@ from . import ops
 from .audio_io import read_wav, write_wav
 from .constants import (HEXADECAGONAL_TRACK_ORDER, IPSILATERAL_PAIRS, ONSET_GROUPS, SPEAKER_DELAYS, SPEAKER_NAMES,
                         speaker_side, track_name)
-from .frequency_response import next_fast_len
+from .frequency_response import FrequencyResponse, next_fast_len
 from .impulse_response import ImpulseResponse, resample_taps
 
 
@@ -420,6 +420,7 @@ class HRIR:
 
     # ---- EQ / resample ------------------------------------------------------------------------------------------
     def equalize(self, fir):
+        """Reference :858-888.  Responses of equal length that take the same filter share one K1 launch."""
         if isinstance(fir, list):
             if isinstance(fir[0], np.ndarray):
                 fir = np.vstack(fir)
@@ -429,8 +430,106 @@ class HRIR:
                 fir = np.vstack([fir[0].data, fir[1].data]) if len(fir) > 1 else fir[0].data.copy()
         if len(fir.shape) == 1 or fir.shape[0] == 1:
             fir = np.tile(fir, (2, 1))
-        for _, side, ir in self._all():
-            ir.equalize(fir[0] if side == "left" else fir[1])
+        self._equalize_rows([(ir, fir[0] if side == "left" else fir[1]) for _, side, ir in self._all()])
+
+    @staticmethod
+    def _equalize_rows(work):
+        """``ir.equalize(fir)`` for every (ir, fir) of ``work``, batched by (filter, length)."""
+        import torch
+        from .dispatcher import fft_convolve_full
+        groups = {}
+        for ir, fir in work:
+            fir = np.ascontiguousarray(fir, dtype=np.float64)
+            groups.setdefault((fir.tobytes(), len(ir)), (fir, []))[1].append(ir)
+        for fir, irs in groups.values():
+            out = fft_convolve_full(torch.stack([ir.device_data() for ir in irs]), fir)
+            for k, ir in enumerate(irs):
+                ir._set_device(out[k])
+
+    # ---- channel balance (next row, SURVEY.md 8f rank 3) -------------------------------------------------------
+    def channel_balance_firs(self, left_fr, right_fr, method):
+        """Left / right FIR pair that evens out the two ears.  Reference ``core/hrir.py:655-762``; every smoothing
+        and minimum-phase design below runs on the device through the ``FrequencyResponse`` shim."""
+        fs = self.fs
+        nyq_int = int(round(fs / 2))
+
+        def impulse(n):
+            u = np.zeros(n)
+            u[0] = 1.0
+            return u
+
+        def band_level(fr, band):  # reference get_center_value (:43-76) for a two-frequency band
+            sel = np.logical_and(fr.frequency >= band[0], fr.frequency <= band[1])
+            return -np.mean(fr.raw[sel])
+
+        def fixed_gain(gain_db):
+            n = int(round(fs * 0.1))
+            return [impulse(n), impulse(n) * 10 ** (gain_db / 20)]
+
+        if method == "mids":
+            return fixed_gain(band_level(right_fr, [100, 3000]) - band_level(left_fr, [100, 3000]))
+        if method == "trend":
+            trend = FrequencyResponse(name="trend", frequency=left_fr.frequency, raw=left_fr.raw - right_fr.raw)
+            trend.smoothen_fractional_octave(window_size=2, treble_f_lower=20000, treble_f_upper=nyq_int)
+            right_fr.equalization = trend.smoothed
+            fir = right_fr.minimum_phase_impulse_response(fs=fs, normalize=False)
+            return [impulse(len(fir)), fir]
+        if method in ("left", "right"):
+            ref, subj = (left_fr, right_fr) if method == "left" else (right_fr, left_fr)
+            ref.smoothen_fractional_octave(window_size=1 / 3, treble_f_lower=20000, treble_f_upper=nyq_int)
+            subj.raw += ref.center([100, 10000])
+            subj.target = ref.smoothed
+            subj.error = subj.raw - subj.target
+            subj.smoothen_heavy_light()
+            subj.equalize(max_gain=15, treble_f_lower=20000, treble_f_upper=fs / 2)
+            fir = subj.minimum_phase_impulse_response(fs=fs, normalize=False)
+            return [impulse(len(fir)), fir] if method == "left" else [fir, impulse(len(fir))]
+        if method in ("avg", "min"):
+            gain = (band_level(left_fr, [100, 10000]) + band_level(right_fr, [100, 10000])) / 2
+            for fr in (left_fr, right_fr):
+                fr.raw += gain
+                fr.smoothen_fractional_octave(window_size=1 / 3, treble_f_lower=20000, treble_f_upper=23999)
+            goal = (left_fr.raw + right_fr.raw) / 2 if method == "avg" else np.min([left_fr.raw, right_fr.raw], axis=0)
+            firs = []
+            for fr in (left_fr, right_fr):
+                fr.target = goal
+                fr.error = fr.raw - fr.target
+                fr.smoothen_fractional_octave(window_size=1 / 3, treble_f_lower=20000, treble_f_upper=23999)
+                fr.equalize(max_gain=15, treble_f_lower=2000, treble_f_upper=fs / 2)
+                firs.append(fr.minimum_phase_impulse_response(fs=fs, normalize=False))
+            return firs
+        try:
+            return fixed_gain(float(method))
+        except ValueError:
+            raise ValueError(f'"{method}" is not valid value for channel balance method.')
+
+    def correct_channel_balance(self, method):
+        """Reference ``core/hrir.py:764-799``: per ipsilateral group, the mean left / mean right responses give the
+        FIR pair which is then applied to every response of the group.  The means, the magnitude responses of all
+        groups (one K8 launch) and the FIR application (one K1 launch per filter) run on the device."""
+        import torch
+        from .constants import IPSILATERAL_PAIRS
+        from .room_correction import frequency_responses
+        eqir = HRIR(self.estimator)
+        groups = [[a] if a == b else [a, b] for a, b in IPSILATERAL_PAIRS]
+        groups = [g for g in groups if all(ch in self.irs for ch in g)]
+        means = []
+        for g in groups:
+            for side in ("left", "right"):
+                rows = torch.stack([self.irs[ch][side].device_data() for ch in g])
+                # np.mean(np.vstack(rows), axis=0): pairwise sum over at most two rows, then one division
+                acc = rows[0].clone()
+                for r in rows[1:]:
+                    acc += r
+                means.append(ImpulseResponse(acc / float(len(g)), self.fs))
+        curves = frequency_responses(means)
+        work = []
+        for k, g in enumerate(groups):
+            firs = self.channel_balance_firs(curves[2 * k], curves[2 * k + 1], method)
+            for ch in g:
+                work += [(self.irs[ch]["left"], firs[0]), (self.irs[ch]["right"], firs[1])]
+        self._equalize_rows(work)
+        return eqir
 
     def resample(self, fs):
         items = [ir for _, _, ir in self._all()]

@@ -5,8 +5,8 @@
     import impulcifer; impulcifer.main(dir_path=..., test_signal='default')
 
 ``install()`` builds three classes that put this package's device-backed methods IN FRONT of the reference's
-own classes in the MRO, so everything outside the hot path (plotting mix-ins, channel balance, README
-metrics, CSV I/O ...) keeps running the reference's code on top of them:
+own classes in the MRO, so everything outside the hot path (plotting mix-ins, README metrics, CSV I/O ...)
+keeps running the reference's code on top of them:
 
     ImpulseResponseEstimator  <- estimator.ImpulseResponseEstimator , core.impulse_response_estimator.*
     ImpulseResponse           <- impulse_response.ImpulseResponse   , core.impulse_response.ImpulseResponse
@@ -15,7 +15,9 @@ metrics, CSV I/O ...) keeps running the reference's code on top of them:
 
 and rebinds every already-imported module attribute that still points at the reference classes.  The EQ stage's
 ``parallel_map(process_equalization_worker, ...)`` call (core/pipeline.py:674-688) is routed to
-``dispatcher.equalization_firs``; every other ``parallel_map`` use keeps the reference's pools.
+``dispatcher.equalization_firs``; every other ``parallel_map`` use keeps the reference's pools.  The module-level
+room-correction and microphone-mismatch functions are replaced by their batched twins (``room_correction.py``,
+``microphone_deviation.py``).
 Nothing in the reference tree is edited.  See INTEGRATION.md.
 """
 from __future__ import annotations
@@ -55,18 +57,51 @@ def install(verbose: bool = False):
         __doc__ = RefEst.__doc__
 
     # the shim modules construct these classes themselves: point them at the merged ones
+    from . import microphone_deviation, room_correction
     hrir.ImpulseResponse = ImpulseResponse
     impulse_response.FrequencyResponse = FrequencyResponse
+    for shim_mod in (hrir, room_correction, microphone_deviation):
+        shim_mod.FrequencyResponse = FrequencyResponse
 
     mapping = {RefEst: ImpulseResponseEstimator, RefIR: ImpulseResponse, RefHRIR: HRIR, RefFR: FrequencyResponse}
+
+    # next-row components: the batched room / microphone chains replace the module-level
+    # functions of core/room_correction.py:185-306 and core/microphone_deviation_correction.py
+    from core import microphone_deviation_correction as ref_md
+    from core import room_correction as ref_rc
+
+    def _calculate_generic_room_correction(irs, target, mic_calibration=None, method='average', limit=1000,
+                                           collect_raws=False):
+        got = room_correction.calculate_generic_room_correction(irs, target, mic_calibration=mic_calibration,
+                                                                method=method, limit=limit, collect_raws=collect_raws)
+        return got if collect_raws else (got, [])
+
+    class MicrophoneMatchingCorrector(microphone_deviation.MicrophoneMatchingCorrector,
+                                      ref_md.MicrophoneMatchingCorrector):
+        __doc__ = ref_md.MicrophoneMatchingCorrector.__doc__
+
+    mapping.update({
+        ref_rc.calculate_specific_room_corrections: room_correction.calculate_specific_room_corrections,
+        ref_rc._calculate_generic_room_correction: _calculate_generic_room_correction,
+        ref_rc._correction_limit_mask: room_correction.correction_limit_mask,
+        ref_md.MicrophoneMatchingCorrector: MicrophoneMatchingCorrector,
+        ref_md.apply_microphone_deviation_correction_to_hrir:
+            microphone_deviation.apply_microphone_deviation_correction_to_hrir,
+    })
     rebound = 0
     for mod in list(sys.modules.values()):
         d = getattr(mod, '__dict__', None)
         if not d or getattr(mod, '__name__', '').startswith('impulcifer_pip313_b200'):
             continue
         for k, v in list(d.items()):
-            if isinstance(v, type) and v in mapping:
-                d[k] = mapping[v]
+            if not (isinstance(v, type) or callable(v)):
+                continue
+            try:
+                new = mapping.get(v)
+            except TypeError:  # unhashable callable
+                continue
+            if new is not None:
+                d[k] = new
                 rebound += 1
     # the process pool of the EQ stage (core/pipeline.py:674-688) -> one batched launch per stage
     from core import parallel_utils as ref_pu

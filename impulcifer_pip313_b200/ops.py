@@ -231,6 +231,23 @@ def magnitude_db(x):
     return out
 
 
+def magnitude_lin(x, nfft, n_bins=None):
+    """|rfft(x, n=nfft)|[:n_bins] for every row of ``x`` ([batch, n_valid <= nfft] float64 CUDA)."""
+    torch = _torch()
+    if x.dim() == 1:
+        x = x[None, :]
+    x = x.contiguous()
+    batch, n_valid = x.shape
+    n_bins = nfft // 2 + 1 if n_bins is None else int(n_bins)
+    plan = fft_plan(int(nfft), _dev(x))
+    out = torch.empty((batch, n_bins), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = plan.workspace(batch)
+        _lib.check(_lib.lib().impb_magnitude_lin(plan.handle, x.data_ptr(), n_valid, n_valid, out.data_ptr(), n_bins,
+                                                 n_bins, batch, ws.data_ptr(), _stream(x)), "impb_magnitude_lin")
+    return out
+
+
 # ---- K10 ------------------------------------------------------------------------------------------
 def loglerp(logf_in, y, logf_out):
     """Piecewise-linear interpolation of rows of ``y`` from grid ``logf_in`` to ``logf_out`` (log10 Hz)."""

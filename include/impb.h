@@ -142,6 +142,12 @@ IMPB_API void impb_fft_destroy(impb_fft* fft);
 IMPB_API int32_t impb_magnitude_db(impb_fft* fft, const double* x, int64_t ld_x, double* mag_out, int64_t ld_out,
                           int64_t batch, void* workspace, void* stream);
 IMPB_API int64_t impb_fft_workspace_bytes(const impb_fft* fft, int64_t batch);
+/* Linear twin used by the interaural microphone-mismatch estimator (next row): replaces
+ * np.abs(scipy.fft.rfft(seg, n=nfft)) in MicrophoneMatchingCorrector._windowed_power,
+ * core/microphone_deviation_correction.py:130-133.  Rows hold n_valid <= n samples (zero-padded to the
+ * plan length n); bins 0 .. n_bins-1 (n_bins <= n/2+1) are written. */
+IMPB_API int32_t impb_magnitude_lin(impb_fft* fft, const double* x, int64_t ld_x, int64_t n_valid, double* mag_out,
+                           int64_t ld_out, int64_t n_bins, int64_t batch, void* workspace, void* stream);
 
 /* ---- K10: log-frequency linear interpolation ----------------------------------------------------------
  * Replaces InterpolatedUnivariateSpline(log10 f, y, k=1)(log10 f_out) of FrequencyResponse.interpolate,

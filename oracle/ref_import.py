@@ -101,6 +101,13 @@ def load():
     _loaded = True
 
 
+def module(name):
+    """Import one more module of the reference by dotted name (e.g. ``core.room_correction``)."""
+    import importlib
+    load()
+    return importlib.import_module(name)
+
+
 def modules():
     """Return the reference's hot-path modules as a namespace."""
     load()

@@ -11,6 +11,7 @@ stubs only, no arithmetic restated) and records what the reference itself comput
                          32 x 21600 int32) + per-IR peak / knee / crop integers + FC.wav HRIR chain
   synth71_golden.npz     reference results on the seeded synthetic 7.1 set (``synth.recording_set(seed=1234)``):
                          all integers, checksums of every IR, slices, FR / smoothing / min-phase vectors
+  room_chain_golden.npz  room / headphone FR chains, channel-balance FIRs, microphone-mismatch estimator on the same set
   small_cases.npz        tiny estimators from the reference's own tests (fs=2000/0.05 s, fs=48000/1 s)
 """
 import os
@@ -191,6 +192,115 @@ def synth71():
     print('synth71: tail', tail, 'peaks', gold['est_peaks'])
 
 
+
+def room_curves(frequency):
+    """Deterministic target / microphone-calibration curves on a frequency grid (shared with the GPU tests)."""
+    lf = np.log10(frequency)
+    target = -1.2 * (lf - 3.0) + 1.5 * np.exp(-((lf - 2.0) / 0.35) ** 2)
+    mic = 0.8 * np.sin(2.3 * lf) + 0.3 * (lf - 3.0) ** 2
+    return target, mic
+
+
+def room_chain():
+    """Next-row components on the seeded synthetic 7.1 set: room / headphone frequency-response
+    chains, channel-balance FIR design and the interaural microphone-mismatch estimator, all computed by the
+    reference's own functions."""
+    import copy
+    import tempfile
+    rc = ref_import.module('core.room_correction')
+    mdc = ref_import.module('core.microphone_deviation_correction')
+    est = IRE(min_duration=5.0, fs=48000)
+    rec = synth.recording_set(est.test_signal, est.fs, synth.LAYOUT_71, seed=1234)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, 'FL,FR,FC,SL,SR,BL,BR.wav')
+        wavfile.write(path, est.fs, np.rint(rec.T * 2 ** 31).astype(np.int32))
+        h = HRIR(est)
+        h.open_recording(path, synth.LAYOUT_71)
+    h.crop_heads()
+    h.align_ipsilateral_all()
+    h.align_onset_groups_peak_leftref()
+    h.crop_tails()
+    grid = FrequencyResponse.generate_frequencies(f_step=1.01, f_min=10, f_max=est.fs / 2)
+    t_raw, m_raw = room_curves(grid)
+    target = FrequencyResponse(name='room-target', frequency=grid.copy(), raw=t_raw.copy())
+    mic = FrequencyResponse(name='room-mic', frequency=grid.copy(), raw=m_raw.copy())
+    keys = [(s, e) for s in h.irs for e in ('left', 'right')]
+    gold = {'names': np.array([f'{s}-{e}' for s, e in keys]), 'frequency': grid}
+
+    # speaker-ear specific corrections (core/room_correction.py:185-212)
+    frs = rc.calculate_specific_room_corrections(h.copy(), target.copy(), mic_calibration=mic.copy(), limit=400)
+    gold['specific_raw'] = np.array([frs[s][e].raw for s, e in keys])
+    gold['specific_error'] = np.array([frs[s][e].error for s, e in keys])
+    gold['specific_target'] = np.array([frs[s][e].target for s, e in keys])
+    frs0 = rc.calculate_specific_room_corrections(h.copy(), target.copy(), mic_calibration=None, limit=0)
+    gold['specific_nolimit_error'] = np.array([frs0[s][e].error for s, e in keys])
+
+    # generic (speaker independent) correction from four responses (core/room_correction.py:234-299)
+    gen_keys = [('FL', 'left'), ('FR', 'right'), ('FC', 'left'), ('FC', 'right')]
+    gold['generic_names'] = np.array([f'{s}-{e}' for s, e in gen_keys])
+    for method in ('average', 'conservative'):
+        irs = [ImpulseResponse(h.irs[s][e].data.copy(), est.fs) for s, e in gen_keys]
+        fr = rc.calculate_generic_room_correction(irs, target.copy(), mic_calibration=mic.copy(), method=method,
+                                                  limit=1000)
+        for k in ('raw', 'error', 'error_smoothed', 'smoothed', 'target'):
+            gold[f'generic_{method}_{k}'] = np.asarray(getattr(fr, k)).copy()
+    irs = [ImpulseResponse(h.irs['FC']['left'].data.copy(), est.fs)]
+    fr = rc.calculate_generic_room_correction(irs, target.copy(), mic_calibration=None, method='average', limit=0)
+    gold['generic_single_error'] = fr.error.copy()
+    gold['generic_single_error_smoothed'] = fr.error_smoothed.copy()
+
+    # headphone compensation arithmetic (core/pipeline_stages.py:421-438), FL-left / FR-right as the two ears
+    left = h.irs['FL']['left'].frequency_response()
+    right = h.irs['FR']['right'].frequency_response()
+    gain = left.center([100, 10000])
+    right.raw += gain
+    zero = FrequencyResponse(name='zero', frequency=left.frequency, raw=np.zeros(len(left.frequency)))
+    left.compensate(zero, min_mean_error=False)
+    right.compensate(zero, min_mean_error=False)
+    gold['hp_gain'] = np.array(gain)
+    gold['hp_left_error'] = left.error.copy()
+    gold['hp_right_error'] = right.error.copy()
+
+    # channel balance (core/hrir.py:655-799)
+    methods = ['trend', 'left', 'right', 'avg', 'min', 'mids', '1.5']
+    gold['balance_methods'] = np.array(methods)
+    for method in methods:
+        hb = h.copy()
+        left_fr = ImpulseResponse(np.mean(np.vstack([hb.irs[s]['left'].data for s in ('FL', 'FR')]), axis=0),
+                                  est.fs).frequency_response()
+        right_fr = ImpulseResponse(np.mean(np.vstack([hb.irs[s]['right'].data for s in ('FL', 'FR')]), axis=0),
+                                   est.fs).frequency_response()
+        firs = hb.channel_balance_firs(left_fr, right_fr, method)
+        gold[f'balance_{method}_left_fir'] = np.asarray(firs[0], dtype=np.float64)
+        gold[f'balance_{method}_right_fir'] = np.asarray(firs[1], dtype=np.float64)
+        hb.correct_channel_balance(method)
+        gold[f'balance_{method}_ck'] = np.array([checksums(hb.irs[s][e].data) for s, e in keys])
+        gold[f'balance_{method}_len'] = np.array([len(hb.irs[s][e].data) for s, e in keys])
+
+    # interaural microphone mismatch (core/microphone_deviation_correction.py:106-276)
+    for anchor in ('auto', 'diffuse'):
+        c = mdc.MicrophoneMatchingCorrector(est.fs, anchor=anchor)
+        for s in h.irs:
+            li, ri = h.irs[s]['left'], h.irs[s]['right']
+            c.collect_speaker(s, li.data, ri.data, li.peak_index(), ri.peak_index())
+        if anchor == 'auto':
+            gold['mic_frequency'] = c.frequency.copy()
+            gold['mic_power_left'] = np.array([c.speaker_power[s]['left'] for s in h.irs])
+            gold['mic_power_right'] = np.array([c.speaker_power[s]['right'] for s in h.irs])
+        gold[f'mic_{anchor}_mismatch'] = c.estimate_interaural_mismatch().copy()
+        gold[f'mic_{anchor}_used'] = np.array(c.anchor_used)
+        lf, rf = c.design_correction_filters()
+        gold[f'mic_{anchor}_left_fir'] = lf.copy()
+        gold[f'mic_{anchor}_right_fir'] = rf.copy()
+    hm = h.copy()
+    mdc.apply_microphone_deviation_correction_to_hrir(hm, correction_strength=0.7, anchor='auto')
+    gold['mic_applied_ck'] = np.array([checksums(hm.irs[s][e].data) for s, e in keys])
+    gold['mic_applied_len'] = np.array([len(hm.irs[s][e].data) for s, e in keys])
+    np.savez_compressed(os.path.join(HERE, 'room_chain_golden.npz'), **gold)
+    print('room_chain: specific error rms', float(np.sqrt(np.mean(gold['specific_error'] ** 2))),
+          'mic anchor', gold['mic_auto_used'], 'balance trend fir', gold['balance_trend_right_fir'].shape)
+
+
 def small_cases():
     gold = {}
     rng = np.random.default_rng(7)
@@ -250,9 +360,10 @@ def small_cases():
 
 
 if __name__ == '__main__':
-    demo_room()
-    synth71()
-    small_cases()
+    only = sys.argv[1:]
+    for fn in (demo_room, synth71, room_chain, small_cases):
+        if not only or fn.__name__ in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')

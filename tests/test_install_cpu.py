@@ -22,7 +22,11 @@ def test_install_rebinds_reference_classes():
     assert h2.HRIR is got['HRIR'] and issubclass(h2.HRIR, old_hrir) and issubclass(h2.HRIR, shim_hrir.HRIR)
     # hot methods come from the shim, everything else from the reference
     assert h2.HRIR.crop_heads is shim_hrir.HRIR.crop_heads
-    assert h2.HRIR.correct_channel_balance is old_hrir.correct_channel_balance
+    assert h2.HRIR.correct_channel_balance is shim_hrir.HRIR.correct_channel_balance
+    assert h2.HRIR.plot is old_hrir.plot
+    from core import room_correction as rc2
+    assert rc2.calculate_specific_room_corrections.__module__.startswith('impulcifer_pip313_b200')
+    assert rc2._correction_limit_mask.__module__.startswith('impulcifer_pip313_b200')
     assert ir2.ImpulseResponse.peak_index.__module__.startswith('impulcifer_pip313_b200')
     assert hasattr(ir2.ImpulseResponse, 'plot_fr')  # plotting mix-in of the reference still there
     assert fr2.FrequencyResponse.minimum_phase_impulse_response.__module__.startswith('impulcifer_pip313_b200')
