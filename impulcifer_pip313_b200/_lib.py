@@ -43,6 +43,11 @@ SIGNATURES = {
     "impb_fft_destroy": (None, [c_vp]),
     "impb_fft_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "impb_magnitude_db": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "impb_decay_times_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "impb_decay_times": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "impb_segment_energy": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp]),
+    "impb_dft_bin_abs": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "impb_add_delayed": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "impb_magnitude_lin": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "impb_loglerp": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "impb_savgol_blend": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp,

@@ -32,9 +32,10 @@ _conv_lock = threading.Lock()
 _conv_plans = {}
 
 
-def fft_convolve_full(x, fir):
+def fft_convolve_full(x, fir, out_len=None):
     """``scipy.signal.convolve(x_row, fir, 'full')`` for every row of ``x`` (CUDA [B, n]) -> CUDA [B, n+m-1]
-    (``ImpulseResponse.equalize``, reference core/impulse_response.py:110-119; next-row component)."""
+    (``ImpulseResponse.equalize``, reference core/impulse_response.py:110-119; next-row component).
+    ``out_len``: keep only the first ``out_len`` samples of every row (a causal filter applied in place)."""
     import torch
     from .estimator import DeconvPlan
     fir = np.ascontiguousarray(fir, dtype=np.float64)
@@ -50,7 +51,7 @@ def fft_convolve_full(x, fir):
             plan = _conv_plans[key] = DeconvPlan(fir, total, 64, x.device.index or 0)
     padded = torch.zeros((x.shape[0], total), dtype=torch.float64, device=x.device)
     padded[:, s:s + n] = x
-    return plan.execute(padded)
+    return plan.execute(padded, out_len=out_len)
 
 
 @dataclass

@@ -446,6 +446,44 @@ class HRIR:
             for k, ir in enumerate(irs):
                 ir._set_device(out[k])
 
+    # ---- README metrics (next row) ---------------------------------------------------------
+    def calculate_reflection_levels(self, direct_sound_duration_ms=2, early_ref_start_ms=20, early_ref_end_ms=50,
+                                    late_ref_start_ms=50, late_ref_end_ms=150, epsilon=1e-12):
+        """Early / late reflection levels relative to the direct sound for every response.  Reference
+        ``core/hrir.py:1003-1090``; one K2 and one K18 launch for the whole set."""
+        items = self._all()
+        if not items:
+            return {}
+        flat, offs, lens = _pack([ir for _, _, ir in items])
+        peaks = ops.peak_index(flat, offs, lens, max_len=max(lens)).cpu().numpy()
+        n = np.asarray(lens, dtype=np.int64)
+
+        def at(ms):
+            return np.minimum(peaks + int(ms * self.fs / 1000), n)
+
+        lo = np.stack([peaks, at(early_ref_start_ms), at(late_ref_start_ms)], axis=1)
+        hi = np.stack([at(direct_sound_duration_ms), at(early_ref_end_ms), at(late_ref_end_ms)], axis=1)
+        ms = ops.segment_energy(flat, offs, lo, np.maximum(hi, lo))
+        out = {}
+        for (speaker, side, _), (direct, early, late) in zip(items, ms):
+            rms_direct = epsilon if np.isnan(direct) else np.sqrt(direct)
+            rms_direct = rms_direct if rms_direct > epsilon else epsilon
+            rms_early = 0 if np.isnan(early) else np.sqrt(early)
+            rms_late = 0 if np.isnan(late) else np.sqrt(late)
+            out.setdefault(speaker, {})[side] = {"early_db": 20 * np.log10(rms_early / rms_direct + epsilon),
+                                                 "late_db": 20 * np.log10(rms_late / rms_direct + epsilon)}
+        return out
+
+    def decay_times(self):
+        """``{speaker: {side: (EDT, RT20, RT30, RT60)}}`` for the whole set: one K4 + one K17 launch (the per-response
+        loop of the README writer, reference ``core/pipeline_stages.py:590-625``)."""
+        from .impulse_response import decay_times_batch
+        items = self._all()
+        out = {}
+        for (speaker, side, _), rt in zip(items, decay_times_batch([ir for _, _, ir in items])):
+            out.setdefault(speaker, {})[side] = rt
+        return out
+
     # ---- channel balance (next row, SURVEY.md 8f rank 3) -------------------------------------------------------
     def channel_balance_firs(self, left_fr, right_fr, method):
         """Left / right FIR pair that evens out the two ears.  Reference ``core/hrir.py:655-762``; every smoothing

@@ -129,6 +129,31 @@ class ImpulseResponse:
         pk, knee, noise, win = ops.lundeby(self.device_data(), [0], [n], self.fs, max_len=n)
         return int(pk.item()), int(knee.item()), float(noise.item()), int(win.item())
 
+    # ---- K17 -----------------------------------------------------------------------------------------
+    def decay_times(self, peak_ind=None, knee_point_ind=None, noise_floor=None, window_size=None):
+        """Reference :75-80 -> decay.decay_times (core/decay.py:263-352): ``(EDT, RT20, RT30, RT60)`` in seconds,
+        ``None`` where undefined."""
+        if peak_ind is None or knee_point_ind is None or noise_floor is None:
+            peak_ind, knee_point_ind, noise_floor, window_size = self.decay_params()
+        return decay_times_batch([self], [(peak_ind, knee_point_ind, noise_floor, window_size)])[0]
+
+    def decay_adjustment_params(self, target):
+        """``decay.decay_adjustment_params(data, fs, target)`` (core/decay.py:355-380): the
+        ``(window_start, half_window, knee_index, level_dB)`` tuple ``apply_decay_window`` takes, or None when the
+        response already decays faster than ``target`` seconds of RT60."""
+        peak, knee, noise, win = self.decay_params()
+        slope = None
+        for rt, level in zip(decay_times_batch([self], [(peak, knee, noise, win)])[0], (-10, -20, -30, -60)):
+            if not rt:
+                break
+            slope = level / rt
+        target_slope = -60 / target
+        if target_slope > slope:  # same TypeError as the reference when no decay time could be measured
+            return None
+        knee_time = knee / self.fs
+        start = peak + 2 * (self.fs // 1000)
+        return start, knee - start, knee, target_slope * knee_time - slope * knee_time
+
     def crop_head(self, head_ms=1):
         """Reference :82-90."""
         if len(self) == 0:
@@ -192,6 +217,33 @@ class ImpulseResponse:
             return FrequencyResponse(name="Frequency response (short IR)", frequency=grid, raw=np.zeros_like(grid))
         raw = frequency_response_batch(self.device_data()[None, :], self.fs).cpu().numpy()[0]
         return FrequencyResponse(name="Frequency response", frequency=grid, raw=raw)
+
+
+def decay_times_batch(irs, params=None):
+    """``[ir.decay_times(*p) for ir, p in zip(irs, params)]`` as one K4 (when ``params`` is None) and one K17
+    launch.  ``params``: per response ``(peak, knee, noise_floor_dB, window)`` as ``decay_params`` returns them.
+    -> list of ``(EDT, RT20, RT30, RT60)`` tuples with ``None`` for undefined entries."""
+    import torch
+    irs = list(irs)
+    if not irs:
+        return []
+    fs = irs[0].fs
+    if any(ir.fs != fs for ir in irs):
+        raise ValueError("decay_times_batch: all responses must share one sampling rate")
+    tens = [ir.device_data() for ir in irs]
+    lens = [int(t.shape[0]) for t in tens]
+    flat = torch.cat(tens) if len(tens) > 1 else tens[0]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    if params is None:
+        pk, kn, nf, wn = ops.lundeby(flat, offs, lens, fs, max_len=max(lens))
+        pk, kn, nf, wn = (t.cpu().numpy() for t in (pk, kn, nf, wn))
+    else:
+        pk = np.array([p[0] for p in params], dtype=np.int64)
+        kn = np.array([p[1] for p in params], dtype=np.int64)
+        nf = np.array([p[2] for p in params], dtype=np.float64)
+        wn = np.array([p[3] if p[3] is not None else 0 for p in params], dtype=np.int64)
+    out = ops.decay_times(flat, offs, lens, pk, kn, nf, wn, fs, max_len=max(lens))
+    return [tuple(None if np.isnan(v) else float(v) for v in row) for row in out]
 
 
 def frequency_response_batch(irs, fs):

@@ -16,8 +16,8 @@ keeps running the reference's code on top of them:
 and rebinds every already-imported module attribute that still points at the reference classes.  The EQ stage's
 ``parallel_map(process_equalization_worker, ...)`` call (core/pipeline.py:674-688) is routed to
 ``dispatcher.equalization_firs``; every other ``parallel_map`` use keeps the reference's pools.  The module-level
-room-correction and microphone-mismatch functions are replaced by their batched twins (``room_correction.py``,
-``microphone_deviation.py``).
+room-correction, microphone-mismatch, decay-time and virtual-bass functions are replaced by their batched twins
+(``room_correction.py``, ``microphone_deviation.py``, ``impulse_response.decay_times_batch``, ``virtual_bass.py``).
 Nothing in the reference tree is edited.  See INTEGRATION.md.
 """
 from __future__ import annotations
@@ -80,6 +80,25 @@ def install(verbose: bool = False):
                                       ref_md.MicrophoneMatchingCorrector):
         __doc__ = ref_md.MicrophoneMatchingCorrector.__doc__
 
+    # rank 4: decay analysis and virtual bass
+    from core import decay as ref_decay
+    from core import virtual_bass as ref_vb
+    from . import virtual_bass
+
+    def decay_times(data, fs, peak_ind=None, knee_point_ind=None, noise_floor=None, window_size=None):
+        return ImpulseResponse(data, fs).decay_times(peak_ind, knee_point_ind, noise_floor, window_size)
+
+    def decay_adjustment_params(data, fs, target):
+        return ImpulseResponse(data, fs).decay_adjustment_params(target)
+
+    decay_times.__doc__ = ref_decay.decay_times.__doc__
+    decay_adjustment_params.__doc__ = ref_decay.decay_adjustment_params.__doc__
+    mapping.update({
+        ref_decay.decay_times: decay_times,
+        ref_decay.decay_adjustment_params: decay_adjustment_params,
+        ref_vb.synthesize_virtual_bass: virtual_bass.synthesize_virtual_bass,
+        ref_vb.apply_virtual_bass_to_hrir: virtual_bass.apply_virtual_bass_to_hrir,
+    })
     mapping.update({
         ref_rc.calculate_specific_room_corrections: room_correction.calculate_specific_room_corrections,
         ref_rc._calculate_generic_room_correction: _calculate_generic_room_correction,

@@ -124,6 +124,74 @@ def lundeby(x, offsets, lengths, fs, max_len=None, view=None):
     return peak, knee, noise, win
 
 
+# ---- K17 / K18 -------------------------------------------------------------------------------------
+def decay_times(x, offsets, lengths, peaks, knees, noise_db, wins, fs, max_len=None):
+    """EDT / RT20 / RT30 / RT60 (seconds, NaN = undefined) for segments of the flat CUDA tensor ``x``; the four
+    parameter arrays are what ``lundeby`` returned.  -> numpy [batch, 4]."""
+    torch = _torch()
+    dev = x.device
+    offsets, lengths = as_index_tensor(offsets, dev), as_index_tensor(lengths, dev)
+    peaks, knees, wins = as_index_tensor(peaks, dev), as_index_tensor(knees, dev), as_index_tensor(wins, dev)
+    noise = torch.as_tensor(np.asarray(noise_db, dtype=np.float64), device=dev)
+    batch = offsets.numel()
+    if max_len is None:
+        max_len = int(lengths.max().item()) if batch else 0
+    out = torch.empty((batch, 4), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = _lib.lib().impb_decay_times_workspace_bytes(batch, int(max_len))
+        ws = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().impb_decay_times(_lib.context(_dev(x)).handle, x.data_ptr(), _i64(offsets), _i64(lengths),
+                                               _i64(peaks), _i64(knees), noise.data_ptr(), _i64(wins), int(fs),
+                                               out.data_ptr(), ws.data_ptr(), batch, int(max_len), _stream(x)),
+                   "impb_decay_times")
+    return out.cpu().numpy()
+
+
+def segment_energy(x, offsets, seg_lo, seg_hi):
+    """mean(x[offsets[r] + lo : offsets[r] + hi] ** 2) for every (row, segment); seg_lo / seg_hi: [batch, nseg]
+    integer arrays (row relative).  -> numpy [batch, nseg], NaN for empty ranges."""
+    torch = _torch()
+    dev = x.device
+    seg_lo = np.ascontiguousarray(seg_lo, dtype=np.int64)
+    seg_hi = np.ascontiguousarray(seg_hi, dtype=np.int64)
+    batch, nseg = seg_lo.shape
+    offsets = as_index_tensor(offsets, dev)
+    lo, hi = as_index_tensor(seg_lo.reshape(-1), dev), as_index_tensor(seg_hi.reshape(-1), dev)
+    out = torch.empty((batch, nseg), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_segment_energy(_lib.context(_dev(x)).handle, x.data_ptr(), _i64(offsets), _i64(lo),
+                                                  _i64(hi), nseg, out.data_ptr(), batch, _stream(x)),
+                   "impb_segment_energy")
+    return out.cpu().numpy()
+
+
+# ---- K19 / K20 -------------------------------------------------------------------------------------
+def dft_bin_abs(x, k):
+    """|rfft(row)[k]| for every row of the CUDA matrix ``x`` -> numpy [batch]."""
+    torch = _torch()
+    x = x.contiguous()
+    batch, n = x.shape
+    out = torch.empty(batch, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().impb_dft_bin_abs(_lib.context(_dev(x)).handle, x.data_ptr(), x.stride(0), n, int(k),
+                                               out.data_ptr(), batch, _stream(x)), "impb_dft_bin_abs")
+    return out.cpu().numpy()
+
+
+def add_delayed(dst, src, which, delay):
+    """dst[r, j] += src[which[r], j - delay[r]] in place (rows of ``src`` are zero outside their length)."""
+    torch = _torch()
+    assert dst.is_contiguous() and src.is_contiguous() and dst.dtype == torch.float64 and src.dtype == torch.float64
+    batch, n = dst.shape
+    wh = torch.as_tensor(np.asarray(which, dtype=np.int32), device=dst.device)
+    dl = as_index_tensor(delay, dst.device)
+    with torch.cuda.device(dst.device):
+        _lib.check(_lib.lib().impb_add_delayed(_lib.context(_dev(dst)).handle, dst.data_ptr(), dst.stride(0), n,
+                                               src.data_ptr(), src.stride(0), src.shape[1], src.shape[0],
+                                               wh.data_ptr(), _i64(dl), batch, _stream(dst)), "impb_add_delayed")
+    return dst
+
+
 # ---- K6 -------------------------------------------------------------------------------------------
 def xcorr_lag(x, a_offsets, a_lengths, b_offsets, b_lengths, max_seg_len=None, fade_in=None):
     torch = _torch()

@@ -105,6 +105,33 @@ IMPB_API int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* off
                      const impb_view* view, int32_t fs, int64_t* peak_out, int64_t* knee_out, double* noise_db_out,
                      int64_t* win_out, int64_t batch, int64_t max_len, void* stream);
 
+/* ---- K17: decay times (next row; feeds decay_adjustment_params of row a11) -------
+ * Replaces decay.decay_times(), core/decay.py:263-352: Schroeder backward integral from the peak to the
+ * knee, vertical offset against the moving average of the squared response, and the EDT / RT20 / RT30 /
+ * RT60 regression lines.  peak / knee / noise_db / win are what impb_lundeby returned for the same rows
+ * (knee absolute, like decay_params' second value).  out: [batch, 4] seconds, NaN where the reference
+ * returns None.  workspace: impb_decay_times_workspace_bytes(batch, max_len) bytes of device memory. */
+IMPB_API int64_t impb_decay_times_workspace_bytes(int64_t batch, int64_t max_len);
+IMPB_API int32_t impb_decay_times(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* lengths,
+                         const int64_t* peak, const int64_t* knee, const double* noise_db, const int64_t* win,
+                         int32_t fs, double* out, void* workspace, int64_t batch, int64_t max_len, void* stream);
+
+/* ---- K18: mean squares of index ranges -----------------------------------------------------------------
+ * The arithmetic of HRIR.calculate_reflection_levels(), core/hrir.py:1003-1090: for row r and segment q,
+ * out[r * nseg + q] = mean(x[offsets[r] + seg_lo : offsets[r] + seg_hi] ** 2), NaN for an empty range. */
+IMPB_API int32_t impb_segment_energy(impb_ctx* ctx, const double* x, const int64_t* offsets, const int64_t* seg_lo,
+                            const int64_t* seg_hi, int32_t nseg, double* out, int64_t batch, void* stream);
+
+/* ---- K19 / K20: virtual-bass helpers (next row) --------------------------------------
+ * impb_dft_bin_abs replaces _mag_at(), core/virtual_bass.py:47-58: out[r] = |sum_j x[r, j] exp(-2 pi i k j / n)|.
+ * impb_add_delayed replaces _delay_signal() (:29-44) and the final add (:173-174):
+ *   dst[r, j] += src[which[r], j - delay[r]]   for 0 <= j - delay[r] < src_len   (src: [n_src, src_ld]). */
+IMPB_API int32_t impb_dft_bin_abs(impb_ctx* ctx, const double* x, int64_t ld, int64_t n, int64_t k, double* out,
+                         int64_t batch, void* stream);
+IMPB_API int32_t impb_add_delayed(impb_ctx* ctx, double* dst, int64_t ld, int64_t n, const double* src, int64_t src_ld,
+                         int64_t src_len, int32_t n_src, const int32_t* which, const int64_t* delay, int64_t batch,
+                         void* stream);
+
 /* ---- K6: onset cross-correlation lag ---------------------------------------------------------------
  * Replaces the scipy.signal.correlate(..., 'full') + argmax of HRIR.align_ipsilateral_all,
  * core/hrir.py:932-948.  a, b: [batch] segments of x given by offsets/lengths (<= max_seg_len samples);

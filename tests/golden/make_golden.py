@@ -12,6 +12,7 @@ stubs only, no arithmetic restated) and records what the reference itself comput
   synth71_golden.npz     reference results on the seeded synthetic 7.1 set (``synth.recording_set(seed=1234)``):
                          all integers, checksums of every IR, slices, FR / smoothing / min-phase vectors
   room_chain_golden.npz  room / headphone FR chains, channel-balance FIRs, microphone-mismatch estimator on the same set
+  decay_chain_golden.npz decay times, reflection levels, decay-adjustment parameters, virtual bass on the same set
   small_cases.npz        tiny estimators from the reference's own tests (fs=2000/0.05 s, fs=48000/1 s)
 """
 import os
@@ -301,6 +302,74 @@ def room_chain():
           'mic anchor', gold['mic_auto_used'], 'balance trend fir', gold['balance_trend_right_fir'].shape)
 
 
+
+def _cropped_set(stage='final'):
+    import tempfile
+    est = IRE(min_duration=5.0, fs=48000)
+    rec = synth.recording_set(est.test_signal, est.fs, synth.LAYOUT_71, seed=1234)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, 'FL,FR,FC,SL,SR,BL,BR.wav')
+        wavfile.write(path, est.fs, np.rint(rec.T * 2 ** 31).astype(np.int32))
+        h = HRIR(est)
+        h.open_recording(path, synth.LAYOUT_71)
+    h.crop_heads()
+    if stage == 'heads':
+        return est, h
+    h.align_ipsilateral_all()
+    h.align_onset_groups_peak_leftref()
+    h.crop_tails()
+    return est, h
+
+
+def _rt(values):
+    return np.array([np.nan if v is None else float(v) for v in values])
+
+
+def decay_chain():
+    """Next-row components: decay times, reflection levels, decay-adjustment parameters and
+    virtual bass, computed by the reference on the seeded synthetic 7.1 set."""
+    decay = ref.decay
+    vb = ref_import.module('core.virtual_bass')
+    gold = {}
+    for stage in ('final', 'heads'):
+        est, h = _cropped_set(stage)
+        keys = [(s, e) for s in h.irs for e in ('left', 'right')]
+        gold['names'] = np.array([f'{s}-{e}' for s, e in keys])
+        params = [h.irs[s][e].decay_params() for s, e in keys]
+        gold[f'{stage}_params'] = np.array([[p[0], p[1], p[3]] for p in params])
+        gold[f'{stage}_noise'] = np.array([p[2] for p in params])
+        gold[f'{stage}_decay_times'] = np.array([_rt(h.irs[s][e].decay_times(*p)) for (s, e), p in zip(keys, params)])
+        gold[f'{stage}_len'] = np.array([len(h.irs[s][e].data) for s, e in keys])
+    # final set: README metrics and decay adjustment
+    refl = h_final_reflections = None
+    est, h = _cropped_set('final')
+    keys = [(s, e) for s in h.irs for e in ('left', 'right')]
+    refl = h.calculate_reflection_levels()
+    gold['reflection'] = np.array([[refl[s][e]['early_db'], refl[s][e]['late_db']] for s, e in keys])
+    refl2 = h.calculate_reflection_levels(direct_sound_duration_ms=1, early_ref_start_ms=5, early_ref_end_ms=300,
+                                          late_ref_start_ms=900, late_ref_end_ms=2000)
+    gold['reflection_clipped'] = np.array([[refl2[s][e]['early_db'], refl2[s][e]['late_db']] for s, e in keys])
+    adj = []
+    for target in (0.05, 0.15, 2.0):
+        for s, e in keys[:4]:
+            p = decay.decay_adjustment_params(h.irs[s][e].data, est.fs, target)
+            adj.append([target] + ([np.nan] * 4 if p is None else [float(v) for v in p]))
+    gold['decay_adjustment'] = np.array(adj)
+    # virtual bass
+    for tag, kw in (('default', {}), ('xo120_inv', dict(crossover_freq=120, invert_polarity=True, head_ms=0.5))):
+        hv = h.copy()
+        hv.irs['BR']['right'].data = hv.irs['BR']['right'].data[:-1000]  # exercises the zero-padding branch
+        vb.apply_virtual_bass_to_hrir(hv, **kw)
+        gold[f'vbass_{tag}_ck'] = np.array([checksums(hv.irs[s][e].data) for s, e in keys])
+        gold[f'vbass_{tag}_len'] = np.array([len(hv.irs[s][e].data) for s, e in keys])
+        gold[f'vbass_{tag}_FL_left'] = hv.irs['FL']['left'].data[:6000].copy()
+        gold[f'vbass_{tag}_FC_right'] = hv.irs['FC']['right'].data[:6000].copy()
+        gold[f'vbass_{tag}_BR_right_tail'] = hv.irs['BR']['right'].data[-3000:].copy()
+    np.savez_compressed(os.path.join(HERE, 'decay_chain_golden.npz'), **gold)
+    print('decay_chain: final RT', gold['final_decay_times'][0], 'heads RT', gold['heads_decay_times'][0],
+          'reflection', gold['reflection'][0], 'adj', gold['decay_adjustment'][:, 1])
+
+
 def small_cases():
     gold = {}
     rng = np.random.default_rng(7)
@@ -361,7 +430,7 @@ def small_cases():
 
 if __name__ == '__main__':
     only = sys.argv[1:]
-    for fn in (demo_room, synth71, room_chain, small_cases):
+    for fn in (demo_room, synth71, room_chain, decay_chain, small_cases):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):
