@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libimpulcifer_b200.so")
+# IMPB_LIB: developer override used to A/B differently compiled builds of the same sources (tools/)
+LIB_PATH = os.environ.get("IMPB_LIB") or os.path.join(_HERE, "libimpulcifer_b200.so")
 
 FMT_F64, FMT_F32, FMT_I32PCM = 0, 1, 2
 
@@ -32,7 +33,7 @@ SIGNATURES = {
     "impb_deconv_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "impb_deconv_plan_info": (c_i32, [c_vp, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "impb_deconv_execute": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp,
-                                    c_i64, c_vp, c_vp]),
+                                    c_vp, c_i64, c_vp, c_vp]),
     "impb_deconv_launches_per_execute": (c_i32, [c_vp, c_i64]),
     "impb_peak_index": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_i64, c_i64, c_vp]),
     "impb_lundeby": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
@@ -67,7 +68,8 @@ SIGNATURES = {
 
 class View(C.Structure):
     """``impb_view`` of include/impb.h (all members optional)."""
-    _fields_ = [("shift", c_vp), ("valid_lo", c_vp), ("valid_hi", c_vp), ("fade_in", c_vp), ("fade_in_len", c_i64)]
+    _fields_ = [("shift", c_vp), ("valid_lo", c_vp), ("valid_hi", c_vp), ("fade_in", c_vp), ("fade_in_len", c_i64),
+                ("hint_max", c_vp), ("hint_argmax", c_vp)]
 
 
 class ImpbError(RuntimeError):

@@ -31,6 +31,8 @@ struct ViewArgs {
   const int64_t* hi;       // nullable
   const double* fade;      // nullable: rising half window applied to source index m < fade_len
   int64_t fade_len;
+  const double* hint_max;      // nullable pair: max |src| over a superset of the view and one source index
+  const int64_t* hint_arg;     //                (relative to offsets[r]) where it is attained
 };
 
 struct RowView {
@@ -45,6 +47,12 @@ struct RowView {
     hi = a.hi ? a.hi[r] : n;
     fade = a.fade;
     fade_len = a.fade ? a.fade_len : 0;
+  }
+  // view index of the hinted maximum if that sample is part of the view with weight 1, else -1
+  __device__ __forceinline__ int64_t hinted(const ViewArgs& a, int64_t r) const {
+    if (!a.hint_max || !a.hint_arg) return -1;
+    const int64_t m = a.hint_arg[r], j = m + sh;
+    return (m >= fade_len && j >= lo && j < hi && j >= 0 && j < n) ? j : -1;
   }
   __device__ __forceinline__ double operator[](int64_t j) const {
     if (j < lo || j >= hi) return 0.0;
@@ -84,6 +92,11 @@ __global__ void __launch_bounds__(256) k_absmax(const double* __restrict__ x, co
                                                 PeakScratch* __restrict__ s) {
   const int64_t r = blockIdx.x;
   const RowView p(x, va, r0 + r);
+  if (p.hinted(va, r0 + r) >= 0) {  // the known maximum of the source survives in this view: no scan
+    if (blockIdx.y == 0 && threadIdx.x == 0)
+      s[r].max_bits = (unsigned long long)__double_as_longlong(va.hint_max[r0 + r]);
+    return;
+  }
   int64_t lo, hi;
   chunk_bounds(p.n, &lo, &hi);
   if (lo >= hi) return;
@@ -123,28 +136,33 @@ __device__ __forceinline__ bool peak_at(const RowView& p, int64_t n, int64_t i, 
   return true;
 }
 
+// grid = (rows, G): block (r, g) walks the chunks g, g + G, g + 2G ... of row r front to back and stops as soon as an
+// earlier chunk has published a peak, so a row whose onset lies in the first G chunks costs G blocks, not `nchunks`.
 __global__ void __launch_bounds__(256) k_first_peak(const double* __restrict__ x, const ViewArgs va, int64_t r0,
-                                                    double height, PeakScratch* __restrict__ s) {
+                                                    double height, PeakScratch* __restrict__ s, int nchunks) {
   const int64_t r = blockIdx.x;
   const RowView p(x, va, r0 + r);
   const int64_t n = p.n;
   const double m = __longlong_as_double((long long)s[r].max_bits);
   if (!(m >= kEps)) return;
-  int64_t lo, hi;
-  chunk_bounds(n, &lo, &hi);
-  if (lo >= hi) return;
-  // nothing in this chunk can beat an already published earlier peak
-  // (first_argmax is only consulted when no peak exists at all, so it need not be complete then)
-  const unsigned long long cur = *((volatile unsigned long long*)&s[r].first_peak);
-  if (cur != kNoIndex && cur < (unsigned long long)lo) return;
+  int64_t C = (n + nchunks - 1) / nchunks;
+  C = (C + 255) & ~(int64_t)255;
   const double guard = 0.999 * height * m;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
-    const double v = p[i];
-    const double av = fabs(v);
-    if (av == m) atomicMin(&s[r].first_argmax, (unsigned long long)i);
-    if (i < 1 || i > n - 2 || av < guard) continue;
-    int64_t mid;
-    if (peak_at(p, n, i, m, v > 0 ? 1.0 : -1.0, height, &mid)) atomicMin(&s[r].first_peak, (unsigned long long)mid);
+  for (int64_t k = blockIdx.y; k < nchunks; k += gridDim.y) {
+    const int64_t lo = k * C, hi = min(n, lo + C);
+    if (lo >= hi) return;
+    // nothing in this chunk (or any later one) can beat an already published earlier peak
+    // (first_argmax is only consulted when no peak exists at all, so it need not be complete then)
+    const unsigned long long cur = *((volatile unsigned long long*)&s[r].first_peak);
+    if (cur != kNoIndex && cur < (unsigned long long)lo) return;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+      const double v = p[i];
+      const double av = fabs(v);
+      if (av == m) atomicMin(&s[r].first_argmax, (unsigned long long)i);
+      if (i < 1 || i > n - 2 || av < guard) continue;
+      int64_t mid;
+      if (peak_at(p, n, i, m, v > 0 ? 1.0 : -1.0, height, &mid)) atomicMin(&s[r].first_peak, (unsigned long long)mid);
+    }
   }
 }
 
@@ -183,7 +201,8 @@ int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double he
     const int64_t nb = std::min<int64_t>((int64_t)1 << 30, batch - b0);
     dim3 grid((unsigned)nb, (unsigned)chunks);
     if (!known_max) k_absmax<<<grid, thr, 0, st>>>(x, va, b0, scratch + b0);
-    k_first_peak<<<grid, thr, 0, st>>>(x, va, b0, height, scratch + b0);
+    const dim3 pgrid((unsigned)nb, (unsigned)std::min<int64_t>(chunks, 8));
+    k_first_peak<<<pgrid, thr, 0, st>>>(x, va, b0, height, scratch + b0, (int)chunks);
   }
   k_peak_final<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, peak_out, batch);
   IMPB_CUDA(cudaGetLastError());
@@ -363,6 +382,12 @@ __global__ void __launch_bounds__(256) k_lb_segmax(const double* __restrict__ x,
   if (ir.n < 10) return;
   const int64_t pk = peaks[r];
   const int64_t ns = min(pk + (int64_t)(2 * fs), ir.n) - pk;
+  const int64_t jh = ir.hinted(va, r0 + r);
+  if (jh >= pk && jh < pk + ns) {  // the known maximum lies inside the analysis window
+    if (blockIdx.y == 0 && threadIdx.x == 0)
+      segmax[r] = (unsigned long long)__double_as_longlong(va.hint_max[r0 + r]);
+    return;
+  }
   int64_t lo, hi;
   chunk_bounds(ns, &lo, &hi);
   if (lo >= hi) return;
@@ -686,8 +711,9 @@ __global__ void __launch_bounds__(256) k_gather_window(const double* __restrict_
 extern "C" {
 
 static ViewArgs make_view(const int64_t* offsets, const int64_t* lengths, const impb_view* v) {
-  ViewArgs a{offsets, lengths, nullptr, nullptr, nullptr, nullptr, 0};
+  ViewArgs a{offsets, lengths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   if (v) {
+    if (v->hint_max && v->hint_argmax) { a.hint_max = v->hint_max; a.hint_arg = v->hint_argmax; }
     a.shift = v->shift;
     a.lo = v->valid_lo;
     a.hi = v->valid_hi;

@@ -47,6 +47,10 @@ template <typename T> struct DeconvArgs {
   int64_t ld_out, out_start, out_len;
   int out_f64;
   unsigned long long* absmax;  // optional [nrows]: bit pattern of max |out[r, :]| (atomicMax; zeroed by the caller)
+  // optional per-(row, column tile) candidates for argmax|out[r, :]|: value bits and output index
+  unsigned long long* cand_val;
+  int64_t* cand_idx;
+  int cand_tiles;
 };
 
 __device__ __forceinline__ double load_sample(const void* p, int fmt, int64_t i) {
@@ -129,10 +133,12 @@ template <typename T, int TILE> struct DeconvColOut {
   }
   __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v) const {
     T m0 = 0, m1 = 0;
-    store(b, t, e, c, v, m0, m1);
+    int i0 = 0, i1 = 0;
+    store(b, t, e, c, v, m0, m1, i0, i1);
   }
-  // also folds |value as stored| into the caller's running maxima
-  __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v, T& mx_re, T& mx_im) const {
+  // also folds |value as stored| (and where it was stored) into the caller's running maxima
+  __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v, T& mx_re, T& mx_im, int& ix_re,
+                                        int& ix_im) const {
     const int n2 = t * TILE + c;
     const int64_t j = (int64_t)e * a.N2 + n2 - a.out_start;
     if (n2 >= a.N2 || j < 0 || j >= a.out_len) return;
@@ -148,10 +154,20 @@ template <typename T, int TILE> struct DeconvColOut {
       o[ra * a.ld_out + j] = (float)v.x;
       if (rb < a.nrows) o[rb * a.ld_out + j] = (float)v.y;
     }
-    mx_re = fmax(mx_re, fabs(v.x));
-    mx_im = fmax(mx_im, fabs(v.y));
+    if (fabs(v.x) > mx_re) { mx_re = fabs(v.x); ix_re = (int)j; }
+    if (fabs(v.y) > mx_im) { mx_im = fabs(v.y); ix_im = (int)j; }
   }
   __device__ __forceinline__ bool tracks_max() const { return a.absmax != nullptr; }
+  __device__ __forceinline__ bool tracks_arg() const { return a.cand_val != nullptr; }
+  __device__ __forceinline__ void publish_arg(int b, int t, T mx_re, int ix_re, T mx_im, int ix_im) const {
+    const int64_t ra = a.row0 + 2 * (int64_t)b, rb = ra + 1;
+    a.cand_val[ra * a.cand_tiles + t] = (unsigned long long)__double_as_longlong((double)mx_re);
+    a.cand_idx[ra * a.cand_tiles + t] = ix_re;
+    if (rb < a.nrows) {
+      a.cand_val[rb * a.cand_tiles + t] = (unsigned long long)__double_as_longlong((double)mx_im);
+      a.cand_idx[rb * a.cand_tiles + t] = ix_im;
+    }
+  }
   __device__ __forceinline__ void publish_max(int b, T mx_re, T mx_im) const {
     const int64_t ra = a.row0 + 2 * (int64_t)b, rb = ra + 1;
     atomicMax(a.absmax + ra, (unsigned long long)__double_as_longlong((double)mx_re));
@@ -171,6 +187,35 @@ __global__ void __launch_bounds__(256) k_row_absmax(const O* __restrict__ out, i
   for (int64_t i = lo + threadIdx.x; i < hi; i += 256) m = fmax(m, fabs((double)p[i]));
   for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(absmax + r, (unsigned long long)__double_as_longlong(m));
+}
+
+// argmax from the per-tile candidates of the specialised final pass: smallest index whose value equals the row max
+__global__ void k_argmax_pick(const unsigned long long* __restrict__ absmax, const unsigned long long* __restrict__ cand_val,
+                              const int64_t* __restrict__ cand_idx, int tiles, int64_t* __restrict__ argmax, int64_t rows) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const unsigned long long m = absmax[r];
+  int64_t best = -1;
+  for (int t = 0; t < tiles; ++t)
+    if (cand_val[r * tiles + t] == m) {
+      const int64_t i = cand_idx[r * tiles + t];
+      if (best < 0 || i < best) best = i;
+    }
+  argmax[r] = best;
+}
+
+// generic-engine plans: argmax by one more read of the rows (absmax is final when this runs)
+template <typename O>
+__global__ void __launch_bounds__(256) k_row_argmax(const O* __restrict__ out, int64_t ld, int64_t n,
+                                                    const unsigned long long* __restrict__ absmax,
+                                                    unsigned long long* __restrict__ argmax) {
+  const int64_t r = blockIdx.x;
+  const O* p = out + r * ld;
+  const double m = __longlong_as_double((long long)absmax[r]);
+  int64_t C = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t lo = (int64_t)blockIdx.y * C, hi = min(n, lo + C);
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256)
+    if (fabs((double)p[i]) == m) atomicMin(argmax + r, (unsigned long long)i);
 }
 
 // spectrum of the inverse filter: scrambled [p1][p2] -> natural order
@@ -245,6 +290,10 @@ template <typename T> struct DeconvEngine {
   cx_t<T>* hs = nullptr;
   int device = 0;
   static constexpr int FULL = TileOf<T>::value;  // 8 (f64) / 16 (f32)
+
+  bool fixed_path() const {
+    return fft.p.tile == FULL && fft.col_fixed && fft.row_fixed && getenv("IMPB_NO_FIXED") == nullptr;
+  }
 
   int launch(const DeconvArgs<T>& a, int pairs, cudaStream_t st) const {
     return fft.p.tile == FULL ? launch_t<FULL>(a, pairs, st) : launch_t<FULL / 2>(a, pairs, st);
@@ -482,9 +531,9 @@ int32_t impb_deconv_launches_per_execute(const impb_plan* pl, int64_t batch) {
 
 int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_offsets, int64_t ld_in, int32_t in_fmt,
                             int64_t len, void* out, int64_t ld_out, int32_t out_f64, int64_t out_offset, int64_t out_len,
-                            double* absmax_out, int64_t batch, void* workspace, void* stream) {
+                            double* absmax_out, int64_t* argmax_out, int64_t batch, void* workspace, void* stream) {
   if (!pl || !rec || !out || !workspace || batch < 0 || len < 0 || len > pl->L || (!in_offsets && ld_in < len) ||
-      out_offset < 0 ||
+      out_offset < 0 || (argmax_out && !absmax_out) ||
       out_len < 0 || out_offset + out_len > len || ld_out < out_len || in_fmt < 0 || in_fmt > 2) {
     set_error("impb_deconv_execute: bad argument (len=%lld L=%lld out_offset=%lld out_len=%lld)", (long long)len,
               pl ? (long long)pl->L : 0LL, (long long)out_offset, (long long)out_len);
@@ -494,6 +543,15 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
   DeviceGuard g(pl->ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (absmax_out) IMPB_CUDA(cudaMemsetAsync(absmax_out, 0, sizeof(double) * batch, st));
+  // argmax: per-(row, tile) candidates from the specialised final pass, or one extra read for generic plans
+  const bool fixed = pl->precision == 64 ? pl->e64.fixed_path() : pl->e32.fixed_path();
+  const int cand_tiles = pl->precision == 64 ? pl->e64.fft.col_tiles() : pl->e32.fft.col_tiles();
+  unsigned long long* cand_val = nullptr;
+  int64_t* cand_idx = nullptr;
+  if (argmax_out && fixed) {
+    IMPB_CUDA(cudaMallocAsync(&cand_val, sizeof(unsigned long long) * batch * cand_tiles, st));
+    IMPB_CUDA(cudaMallocAsync(&cand_idx, sizeof(int64_t) * batch * cand_tiles, st));
+  }
   const int64_t pairs = (batch + 1) / 2;
   const int ns = pl->nstreams;
   const cudaStream_t user = st;
@@ -516,6 +574,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
       a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = 1;
       a.absmax = (unsigned long long*)absmax_out;
+      a.cand_val = cand_val; a.cand_idx = cand_idx; a.cand_tiles = cand_tiles;
       rc = pl->e64.launch(a, np, st);
     } else {
       DeconvArgs<float> a{};
@@ -525,6 +584,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
       a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = out_f64 ? 1 : 0;
       a.absmax = (unsigned long long*)absmax_out;
+      a.cand_val = cand_val; a.cand_idx = cand_idx; a.cand_tiles = cand_tiles;
       rc = pl->e32.launch(a, np, st);
     }
     if (rc) return rc;
@@ -533,6 +593,25 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
     for (int i = 0; i < ns; ++i) {
       IMPB_CUDA(cudaEventRecord(pl->join_ev[i], pl->streams[i]));
       IMPB_CUDA(cudaStreamWaitEvent(user, pl->join_ev[i], 0));
+    }
+  }
+  if (argmax_out) {
+    if (fixed) {
+      k_argmax_pick<<<(unsigned)((batch + 127) / 128), 128, 0, user>>>((const unsigned long long*)absmax_out, cand_val,
+                                                                       cand_idx, cand_tiles, argmax_out, batch);
+      IMPB_CUDA(cudaGetLastError());
+      IMPB_CUDA(cudaFreeAsync(cand_val, user));
+      IMPB_CUDA(cudaFreeAsync(cand_idx, user));
+    } else {
+      IMPB_CUDA(cudaMemsetAsync(argmax_out, 0xff, sizeof(int64_t) * batch, user));
+      const dim3 grid((unsigned)batch, (unsigned)std::max<int64_t>(1, std::min<int64_t>(out_len / 4096, 1024)));
+      if (pl->precision == 64 || out_f64)
+        k_row_argmax<double><<<grid, 256, 0, user>>>((const double*)out, ld_out, out_len,
+                                                     (const unsigned long long*)absmax_out, (unsigned long long*)argmax_out);
+      else
+        k_row_argmax<float><<<grid, 256, 0, user>>>((const float*)out, ld_out, out_len,
+                                                    (const unsigned long long*)absmax_out, (unsigned long long*)argmax_out);
+      IMPB_CUDA(cudaGetLastError());
     }
   }
   return IMPB_OK;

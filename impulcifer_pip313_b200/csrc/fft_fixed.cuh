@@ -50,14 +50,21 @@ template <bool ROW, int TILE, int S> __device__ __forceinline__ int fx_smem(int 
 // Stage twiddles w_p = exp(-2 pi i np p / LEN), p = 1..R-1, from the power-of-two entries of the table only
 // (w_1, w_2, w_4, w_8: 3-4 loads instead of R-1; the rest are single products of table values, <= 2 roundings).
 // Table layout: entry k of butterfly np holds w_(2^k):  column pass tw[np][k], row pass tw[k][np] (coalesced).
+#ifndef IMPB_TW_LOADS
+#define IMPB_TW_LOADS 1  // how many of the power-of-two entries are loaded; the rest are squared from the last one
+#endif
 template <typename T, int R, bool ROW, int STRIDE>
 __device__ __forceinline__ void fx_twiddles(const cx_t<T>* __restrict__ tw, int np, cx_t<T>* w) {
   constexpr int NB = (R > 8) ? 4 : (R > 4) ? 3 : (R > 2) ? 2 : 1;
+  constexpr int NL = NB < IMPB_TW_LOADS ? NB : IMPB_TW_LOADS;
   const cx_t<T>* twp = ROW ? tw + np : tw + np * NB;
   constexpr int TWS = ROW ? STRIDE : 1;
 #pragma unroll
-  for (int k = 0; k < NB; ++k)
-    if ((1 << k) < R) w[1 << k] = __ldg(twp + k * TWS);
+  for (int k = 0; k < NB; ++k) {
+    if ((1 << k) >= R) continue;
+    if (k < NL) w[1 << k] = __ldg(twp + k * TWS);
+    else w[1 << k] = cmul(w[1 << (k - 1)], w[1 << (k - 1)]);
+  }
 #pragma unroll
   for (int p = 3; p < R; ++p) {
     const int hi = (p >= 8) ? 8 : (p >= 4) ? 4 : 2;
@@ -234,8 +241,9 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   const int t = blockIdx.x, b = blockIdx.y;
   // running max |re|, |im| of what this thread stores: the per-row max|x| the peak search needs comes for free
   T mx_re = (T)0, mx_im = (T)0;
+  int ix_re = 0, ix_im = 0;  // output index of the thread's running maxima (argmax candidates)
   auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
-  auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v, mx_re, mx_im); };
+  auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v, mx_re, mx_im, ix_re, ix_im); };
   auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
   fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false, kPrefetch>(nullptr, gl, ss, NoPost{});
@@ -246,6 +254,8 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   if (f.tracks_max()) {
     __syncthreads();  // the tile is free: reuse it for the block reduction
     T* red = reinterpret_cast<T*>(smem_raw);
+    int* arg = reinterpret_cast<int*>(red + 2 * (NT / 32) + 2);
+    const T my_re = mx_re, my_im = mx_im;
     for (int o = 16; o; o >>= 1) {
       mx_re = fmax(mx_re, __shfl_xor_sync(0xffffffffu, mx_re, o));
       mx_im = fmax(mx_im, __shfl_xor_sync(0xffffffffu, mx_im, o));
@@ -254,13 +264,18 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
       red[2 * (threadIdx.x >> 5)] = mx_re;
       red[2 * (threadIdx.x >> 5) + 1] = mx_im;
     }
+    if (threadIdx.x == 0) { arg[0] = 0x7fffffff; arg[1] = 0x7fffffff; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < NT / 32; ++w) {
-        mx_re = fmax(mx_re, red[2 * w]);
-        mx_im = fmax(mx_im, red[2 * w + 1]);
-      }
-      f.publish_max(b, mx_re, mx_im);
+    for (int w = 0; w < NT / 32; ++w) {
+      mx_re = fmax(mx_re, red[2 * w]);
+      mx_im = fmax(mx_im, red[2 * w + 1]);
+    }
+    if (threadIdx.x == 0) f.publish_max(b, mx_re, mx_im);
+    if (f.tracks_arg()) {
+      if (my_re == mx_re) atomicMin(arg, ix_re);
+      if (my_im == mx_im) atomicMin(arg + 1, ix_im);
+      __syncthreads();
+      if (threadIdx.x == 0) f.publish_arg(b, t, mx_re, arg[0], mx_im, arg[1]);
     }
   }
 }

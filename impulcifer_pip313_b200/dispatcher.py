@@ -177,7 +177,8 @@ class BatchDispatcher:
             row_offs = (set_base * (n_tracks * n_samples) + lay['offs'][None, :]).reshape(-1)
             plan = est.plan(L, precision)
             e_max = torch.empty(B, dtype=torch.float64, device=dev)
-            E = plan.execute(recordings.reshape(-1), length=L, row_offsets=row_offs, absmax=e_max)
+            e_arg = torch.empty(B, dtype=torch.int64, device=dev)
+            E = plan.execute(recordings.reshape(-1), length=L, row_offsets=row_offs, absmax=e_max, argmax=e_arg)
             if E.dtype != torch.float64:
                 E = E.to(torch.float64)
             launches += plan.launches(B)
@@ -197,6 +198,8 @@ class BatchDispatcher:
             crop = crop.reshape(-1)
             n1 = L - crop
             off1 = rows * L + crop
+            # max |E row| and where: lets the view kernels skip their max scans (impb_view.hint_*)
+            hint_arg = e_arg - crop
             # From here on nothing is materialised: the cropped, faded and shifted responses are VIEWS over E
             # (impb_view: start offset, composite shift, surviving index range, fade-in table).
             window_in = hann(head * 2)[:head] if head > 0 else None
@@ -221,8 +224,8 @@ class BatchDispatcher:
             if 'FL' in lay['speakers'] and len(lay['groups']) > 1:
                 rg = (set_base * n + lay['gl'][None, :]).reshape(-1)
                 gp = ops.peak_index(flatE, off1[rg], n1[rg], max_len=L,
-                                    view=dict(shift=shift[rg], valid_lo=lo[rg], valid_hi=hi[rg],
-                                              fade_in=window_in)).view(S, -1)
+                                    view=dict(shift=shift[rg], valid_lo=lo[rg], valid_hi=hi[rg], fade_in=window_in,
+                                              hint_max=e_max[rg], hint_argmax=hint_arg[rg])).view(S, -1)
                 launches += 4
                 d = gp - gp[:, lay['g_ref']:lay['g_ref'] + 1]
                 shift2.index_add_(1, lay['g_rows'], -d[:, lay['g_of_row']])
@@ -233,7 +236,7 @@ class BatchDispatcher:
             total = shift + shift2
             lo = torch.clamp(lo + shift2, min=0)
             hi = torch.maximum(torch.minimum(hi + shift2, n1), lo)
-            view = dict(shift=total, valid_lo=lo, valid_hi=hi, fade_in=window_in)
+            view = dict(shift=total, valid_lo=lo, valid_hi=hi, fade_in=window_in, hint_max=e_max, hint_argmax=hint_arg)
             # 5. Lundeby knee per response (K4) -> per-set tail index (ref :614-653): the one host sync
             _, knee, _, _ = ops.lundeby(flatE, off1, n1, fs, max_len=L, view=view)
             launches += 5

@@ -63,18 +63,24 @@ def _dev_window(win, device):
     return t
 
 
-def make_view(device, shift=None, valid_lo=None, valid_hi=None, fade_in=None):
-    """(ctypes impb_view or None, keep-alive tensors).  See include/impb.h."""
-    if shift is None and valid_lo is None and valid_hi is None and fade_in is None:
+def make_view(device, shift=None, valid_lo=None, valid_hi=None, fade_in=None, hint_max=None, hint_argmax=None):
+    """(ctypes impb_view or None, keep-alive tensors).  See include/impb.h.  ``hint_max`` / ``hint_argmax``: float64 /
+    int64 CUDA tensors (max |x| of the untouched samples and where, relative to the row offset)."""
+    if shift is None and valid_lo is None and valid_hi is None and fade_in is None and hint_max is None:
         return None, ()
     sh = None if shift is None else as_index_tensor(shift, device)
     lo = None if valid_lo is None else as_index_tensor(valid_lo, device)
     hi = None if valid_hi is None else as_index_tensor(valid_hi, device)
     fi = _dev_window(fade_in, device)
+    hm = ha = None
+    if hint_max is not None and hint_argmax is not None:
+        hm = hint_max.contiguous()
+        ha = as_index_tensor(hint_argmax, device)
     v = _lib.View(None if sh is None else sh.data_ptr(), None if lo is None else lo.data_ptr(),
                   None if hi is None else hi.data_ptr(), None if fi is None else fi.data_ptr(),
-                  0 if fi is None else fi.numel())
-    return v, (sh, lo, hi, fi)
+                  0 if fi is None else fi.numel(), None if hm is None else hm.data_ptr(),
+                  None if ha is None else ha.data_ptr())
+    return v, (sh, lo, hi, fi, hm, ha)
 
 
 def peak_index(x, offsets, lengths, height=0.12589, max_len=None, view=None, known_max=None):

@@ -46,13 +46,20 @@ typedef struct impb_fft impb_fft;
 /* Optional per-row "view" for the crop/align kernels: the array the reference would hold after crop_heads'
  * fade-in and a chain of ImpulseResponse.shift calls, as index arithmetic over the untouched samples
  *   v[j] = fade_in[j - shift] * x[offset + j - shift]   for valid_lo <= j < valid_hi,   0 elsewhere
- * (fade_in applies where j - shift < fade_in_len).  Every pointer may be NULL (no shift / all valid / no fade). */
+ * (fade_in applies where j - shift < fade_in_len).  Every pointer may be NULL (no shift / all valid / no fade).
+ * hint_max / hint_argmax (both or neither): max |x| over a range of the untouched samples that contains the whole
+ * view, and one index (relative to `offset`) where it is attained, e.g. absmax_out / argmax_out of
+ * impb_deconv_execute minus the head crop.  A row whose hinted sample survives inside the view outside the faded
+ * head takes hint_max as its max |v| without a scan; every other row is scanned as usual, so results do not
+ * depend on the hint being usable. */
 typedef struct impb_view {
   const int64_t* shift;
   const int64_t* valid_lo;
   const int64_t* valid_hi;
   const double* fade_in;
   int64_t fade_in_len;
+  const double* hint_max;
+  const int64_t* hint_argmax;
 } impb_view;
 
 IMPB_API uint32_t impb_version(void);
@@ -73,7 +80,9 @@ IMPB_API const char* impb_last_error(void); /* thread-local */
  * out ([batch, ld_out] f64 for precision 64, f32 for precision 32 unless out_f64 != 0) receives
  *   convolve(rec[r, :len], inverse_filter, 'same')[out_offset : out_offset + out_len].
  * absmax_out (nullable, device double[batch]) receives max |out[r, :]|, tracked by the final column pass for
- * free; impb_peak_index accepts it as known_max and then skips its own max pass.
+ * free; impb_peak_index accepts it as known_max and then skips its own max pass.  argmax_out (nullable, device
+ * int64[batch], needs absmax_out) receives one index j with |out[r, j]| == absmax_out[r] (the smallest one found
+ * among the per-tile candidates), for impb_view.hint_argmax.
  */
 IMPB_API int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, int64_t M, int64_t L,
                                 int32_t precision, impb_plan** out);
@@ -82,8 +91,8 @@ IMPB_API int64_t impb_deconv_workspace_bytes(const impb_plan* plan, int64_t batc
 IMPB_API int32_t impb_deconv_plan_info(const impb_plan* plan, int64_t* nfft, int64_t* n1, int64_t* n2);
 IMPB_API int32_t impb_deconv_execute(impb_plan* plan, const void* rec, const int64_t* in_offsets, int64_t ld_in,
                             int32_t in_fmt, int64_t len, void* out, int64_t ld_out, int32_t out_f64,
-                            int64_t out_offset, int64_t out_len, double* absmax_out, int64_t batch,
-                            void* workspace, void* stream);
+                            int64_t out_offset, int64_t out_len, double* absmax_out, int64_t* argmax_out,
+                            int64_t batch, void* workspace, void* stream);
 /* name and launch count of the kernels one execute() issues (bench.py gpu_launches accounting) */
 IMPB_API int32_t impb_deconv_launches_per_execute(const impb_plan* plan, int64_t batch);
 

@@ -150,3 +150,32 @@ def test_full_size_properties(torch_cuda):
     got32 = est.estimate_batch(torch.from_numpy(q.astype(np.float32)[None, :]).cuda()).cpu().numpy()[0]
     gotpcm = est.estimate_batch(torch.from_numpy(np.rint(q * 2 ** 31).astype(np.int32)[None, :]).cuda()).cpu().numpy()[0]
     assert np.array_equal(got32, ref) and np.array_equal(gotpcm, ref)
+
+
+def test_absmax_and_argmax_outputs(torch_cuda):
+    T = torch_cuda
+    """absmax_out / argmax_out of impb_deconv_execute: exact max |row| and an index attaining it, for the
+    specialised 768x768 plan (tracked in the final pass) and a generic plan (extra pass), odd batch."""
+    from impulcifer_pip313_b200 import ImpulseResponseEstimator
+    for dur, fs, batch in ((5.0, 48000, 5), (0.3, 44100, 3)):
+        est = ImpulseResponseEstimator(min_duration=dur, fs=fs)
+        L = 2 * fs + len(est)
+        g = T.Generator(device='cuda').manual_seed(11)
+        x = T.randn(batch, L, dtype=T.float64, device='cuda', generator=g) * 0.05
+        x[1] = 0.0  # an all-zero row
+        plan = est.plan(L)
+        amax = T.empty(batch, dtype=T.float64, device='cuda')
+        arg = T.empty(batch, dtype=T.int64, device='cuda')
+        out = plan.execute(x, absmax=amax, argmax=arg)
+        ref = out.abs().max(dim=1).values
+        assert T.equal(amax, ref)
+        a = arg.cpu().numpy()
+        o = out.cpu().numpy()
+        for r in range(batch):
+            if ref[r] > 0:
+                assert 0 <= a[r] < L and abs(o[r, a[r]]) == float(ref[r]), r
+        # a cropped output window shifts the index origin
+        out2 = plan.execute(x, out_offset=1000, out_len=50000, absmax=amax, argmax=arg)
+        assert T.equal(amax, out2.abs().max(dim=1).values)
+        a2, o2 = arg.cpu().numpy(), out2.cpu().numpy()
+        assert abs(o2[0, a2[0]]) == float(amax[0])

@@ -100,6 +100,55 @@ def test_lundeby_fuzz(T):
         assert abs(noise[i] - rn) < 1e-9
 
 
+def test_view_max_hints_never_change_results(T):
+    """impb_view.hint_max / hint_argmax only skip scans: peak_index and lundeby of a view must be identical with
+    hints, without hints and on the materialised array (oracle), also when the hinted sample is faded or shifted
+    out of the view."""
+    from impulcifer_pip313_b200 import ops
+    rng = np.random.default_rng(17)
+    fs, L, head = 48000, 120000, 48
+    fade_in = O.hann(2 * head)[:head]
+    rows, crops, shifts = [], [], []
+    for i in range(12):
+        d = int(rng.integers(300, 3000))
+        x = 1e-4 * rng.standard_normal(L)
+        x[d:] += rng.standard_normal(L - d) * 10 ** (-3 * np.arange(L - d) / (fs * rng.uniform(0.1, 0.5)))
+        x[d] = 3.0 if i % 2 else -3.0
+        rows.append(x)
+        crops.append(d - int(rng.integers(head, 200)))
+        shifts.append(int(rng.integers(-40, 40)))
+    # rows whose maximum is NOT usable: inside the faded head, shifted out on the left, cropped away entirely
+    crops[3] = int(np.argmax(np.abs(rows[3]))) - 5
+    shifts[4] = -(int(np.argmax(np.abs(rows[4]))) - crops[4] + 7)
+    crops[5] = int(np.argmax(np.abs(rows[5]))) + 100
+    src = np.stack(rows)
+    flat = T.from_numpy(src.reshape(-1)).cuda()
+    crops, shifts = np.array(crops), np.array(shifts)
+    n1 = L - crops
+    lo = np.maximum(shifts, 0)
+    hi = np.maximum(np.minimum(n1 + shifts, n1), lo)
+    offs = np.arange(12) * L + crops
+    hint_max = T.from_numpy(np.abs(src).max(axis=1)).cuda()
+    hint_arg = T.from_numpy(np.argmax(np.abs(src), axis=1) - crops).cuda()
+    base = dict(shift=shifts, valid_lo=lo, valid_hi=hi, fade_in=fade_in)
+    hinted = dict(base, hint_max=hint_max, hint_argmax=hint_arg)
+    p0 = ops.peak_index(flat, offs, n1, max_len=L, view=base).cpu().numpy()
+    p1 = ops.peak_index(flat, offs, n1, max_len=L, view=hinted).cpu().numpy()
+    l0 = [t.cpu().numpy() for t in ops.lundeby(flat, offs, n1, fs, max_len=L, view=base)]
+    l1 = [t.cpu().numpy() for t in ops.lundeby(flat, offs, n1, fs, max_len=L, view=hinted)]
+    assert np.array_equal(p0, p1)
+    for a, b in zip(l0, l1):
+        assert np.array_equal(a, b)
+    for r in range(12):
+        d = src[r, crops[r]:].copy()
+        d[:head] *= fade_in
+        d = O.shift(d, int(shifts[r]))
+        assert p1[r] == O.peak_index(d), r
+        rp, rk, rn, rw = O.decay_params(d, fs)
+        assert (l1[0][r], l1[1][r], l1[3][r]) == (rp, rk, rw), r
+        assert abs(l1[2][r] - rn) < 1e-9
+
+
 def test_xcorr_lag(T):
     from impulcifer_pip313_b200 import ops
     rng = np.random.default_rng(2)
