@@ -411,7 +411,7 @@ static int build_spectrum(impb_plan* pl, const double* inv_host) {
       IMPB_CUDA(cudaMalloc(&pl->e64.hs, total * sizeof(double2)));
       k_spec_layout<double><<<(unsigned)((total + thr - 1) / thr), thr>>>(nat, pl->e64.hs, pl->e64.fft.perm_col,
                                                                        pl->e64.fft.perm_row, N1, N2, tl, R, scale,
-                                                                       (tl == 8 && pl->e64.fft.col_fixed && pl->e64.fft.row_fixed && !getenv("IMPB_NO_FIXED")) ? 1 : 0);
+                                                                       1);
     } else {
       const int R = target.row.radix[target.row.nst - 1];
       const int tl = target.tile;
@@ -419,7 +419,7 @@ static int build_spectrum(impb_plan* pl, const double* inv_host) {
       IMPB_CUDA(cudaMalloc(&pl->e32.hs, total * sizeof(float2)));
       k_spec_layout<float><<<(unsigned)((total + thr - 1) / thr), thr>>>(nat, pl->e32.hs, pl->e32.fft.perm_col,
                                                                       pl->e32.fft.perm_row, N1, N2, tl, R, scale,
-                                                                      (tl == 16 && pl->e32.fft.col_fixed && pl->e32.fft.row_fixed && !getenv("IMPB_NO_FIXED")) ? 1 : 0);
+                                                                      1);
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) rc = cuda_fail(e, "inverse-filter spectrum build");

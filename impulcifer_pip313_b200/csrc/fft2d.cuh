@@ -78,28 +78,28 @@ template <typename T> struct Fft2D {
 
   // launch helpers; F is a functor type, TILE must equal p.tile
   template <int TILE, class F> int col_fwd(const F& f, int batch, cudaStream_t st) const {
-    auto k = k_tile_fwd<T, TILE, F>;
+    auto k = k_tile_fwd<T, TILE, false, F>;
     IMPB_CUDA(set_smem(k, p.smem_col));
     k<<<dim3(col_tiles(), batch), p.threads, p.smem_col, st>>>(p.col, tab_col, f);
     IMPB_CUDA(cudaGetLastError());
     return IMPB_OK;
   }
   template <int TILE, class F> int col_inv(const F& f, int batch, cudaStream_t st) const {
-    auto k = k_tile_inv<T, TILE, F>;
+    auto k = k_tile_inv<T, TILE, false, F>;
     IMPB_CUDA(set_smem(k, p.smem_col));
     k<<<dim3(col_tiles(), batch), p.threads, p.smem_col, st>>>(p.col, tab_col, f);
     IMPB_CUDA(cudaGetLastError());
     return IMPB_OK;
   }
   template <int TILE, class F> int row_fwd(const F& f, int batch, cudaStream_t st) const {
-    auto k = k_tile_fwd<T, TILE, F>;
+    auto k = k_tile_fwd<T, TILE, true, F>;
     IMPB_CUDA(set_smem(k, p.smem_row));
     k<<<dim3(row_tiles(), batch), p.threads, p.smem_row, st>>>(p.row, tab_row, f);
     IMPB_CUDA(cudaGetLastError());
     return IMPB_OK;
   }
   template <int TILE, class F> int row_inv(const F& f, int batch, cudaStream_t st) const {
-    auto k = k_tile_inv<T, TILE, F>;
+    auto k = k_tile_inv<T, TILE, true, F>;
     IMPB_CUDA(set_smem(k, p.smem_row));
     k<<<dim3(row_tiles(), batch), p.threads, p.smem_row, st>>>(p.row, tab_row, f);
     IMPB_CUDA(cudaGetLastError());

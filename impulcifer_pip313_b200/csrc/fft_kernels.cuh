@@ -10,37 +10,37 @@
 
 namespace impb {
 
-template <typename T, int TILE, class F>
+template <typename T, int TILE, bool ROW, class F>
 __global__ void __launch_bounds__(512) k_tile_fwd(const SubPlan sp, const cx_t<T>* __restrict__ tab_g, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
-  cx_t<T>* tab = tile + (size_t)sp.S * (TILE + 1);
+  cx_t<T>* tab = tile + (size_t)tile_row_pitch(sp.S) * TILE;
   load_table<T>(tab, tab_g, sp.ntab);
   __syncthreads();
   const int t = blockIdx.x, b = blockIdx.y;
   auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
   auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
-  tile_fft_forward<T, TILE>(sp, tile, tab, gl, gs);
+  tile_fft_forward<T, TILE, ROW>(sp, tile, tab, gl, gs);
 }
 
-template <typename T, int TILE, class F>
+template <typename T, int TILE, bool ROW, class F>
 __global__ void __launch_bounds__(512) k_tile_inv(const SubPlan sp, const cx_t<T>* __restrict__ tab_g, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
-  cx_t<T>* tab = tile + (size_t)sp.S * (TILE + 1);
+  cx_t<T>* tab = tile + (size_t)tile_row_pitch(sp.S) * TILE;
   load_table<T>(tab, tab_g, sp.ntab);
   __syncthreads();
   const int t = blockIdx.x, b = blockIdx.y;
   auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
   auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
-  tile_fft_inverse<T, TILE>(sp, tile, tab, gl, gs);
+  tile_fft_inverse<T, TILE, ROW>(sp, tile, tab, gl, gs);
 }
 
 template <typename T, int TILE, class F>
 __global__ void __launch_bounds__(512) k_tile_conv(const SubPlan sp, const cx_t<T>* __restrict__ tab_g, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
-  cx_t<T>* tab = tile + (size_t)sp.S * (TILE + 1);
+  cx_t<T>* tab = tile + (size_t)tile_row_pitch(sp.S) * TILE;
   load_table<T>(tab, tab_g, sp.ntab);
   __syncthreads();
   const int t = blockIdx.x, b = blockIdx.y;

@@ -4,9 +4,8 @@
 // A length-N transform is factored N = N1 x N2 ("four-step").  One CTA owns a tile of TILE adjacent
 // columns (column pass, sub-FFT length N1, element stride N2 in HBM) or TILE adjacent rows (row pass,
 // sub-FFT length N2, contiguous in HBM).  TILE*sizeof(complex) = 128 B, so every HBM access of a warp is
-// made of whole 128-byte (column pass) or 64-byte (row pass) segments.  The tile lives in shared memory
-// as [S][TILE+1] complex: the +1 pad makes every stage access (a quarter-warp = one row x TILE columns)
-// hit TILE distinct 16-byte bank groups, for any radix and stride.
+// made of whole 128-byte segments.  The tile lives in shared memory XOR-swizzled ([S][TILE] for the column
+// pass, [TILE][S] for the row pass, see tile_addr) so that a quarter-warp hits 8 distinct 16-byte bank groups.
 //
 // Forward sub-FFTs are decimation-in-frequency (natural order in, digit-reversed order out), inverse
 // sub-FFTs are the exact mirror decimation-in-time (digit-reversed in, natural out).  Convolutions and the
@@ -186,29 +185,61 @@ template <typename T> __device__ __forceinline__ cx_t<T> tw_fetch(const cx_t<T>*
   }
 }
 
-// One work item of one radix-R stage: r elements of one column.  ld(e, c) / st(e, c, v) hide whether the
-// operand is HBM (first / last stage) or the shared tile.
-template <typename T, int R, bool INV, class LD, class ST>
-__device__ __forceinline__ void stage_item(const SubPlan& sp, int s, int j, int c, const cx_t<T>* tab, LD ld, ST st) {
-  const int stride = sp.stride[s];
-  const int b = j / stride;
-  const int np = j - b * stride;
-  const int base = b * sp.len[s] + np;
-  const int mult = sp.mult[s];
-  cx_t<T> x[R];
+// ------------------------------------------------------------------------------------------------
+// work-item order and shared-memory layout of a tile
+//  * column pass (ROW = false): the TILE columns are the fast index of a work item, the tile is [S][TILE] with
+//    slot = c ^ (e & (TILE-1)): a quarter-warp is one row x 8 columns = one 128-byte HBM segment and 8 bank groups.
+//  * row pass (ROW = true): the butterfly index j is the fast index, the tile is [TILE][SP] (SP = S rounded up
+//    to 8) with e' = e ^ ((e >> 3) & 7): a quarter-warp is 8 consecutive elements of ONE row, again one 128-byte
+//    segment (with the columns fast it would be 8 different lines per request).
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int tile_row_pitch(int S) { return (S + 7) & ~7; }
+
+template <bool ROW, int TILE> __device__ __forceinline__ void tile_decode(int w, int per_col, int& c, int& j) {
+  if (ROW) { c = w / per_col; j = w - c * per_col; } else { c = w % TILE; j = w / TILE; }
+}
+template <bool ROW, int TILE> __device__ __forceinline__ int tile_addr(int e, int c, int SP) {
+  return ROW ? c * SP + (e ^ ((e >> 3) & 7)) : e * TILE + (c ^ (e & (TILE - 1)));
+}
+
+// all items of one radix-R stage.  ld(e, c) / st(e, c, v) hide whether the operand is HBM (first / last stage) or
+// the shared tile.  Stage twiddles w_p = exp(-2 pi i np p / len) come from the quarter-wave table in shared memory.
+template <typename T, int TILE, int R, bool INV, bool ROW, class LD, class ST>
+__device__ __forceinline__ void stage_loop(const SubPlan& sp, int s, const cx_t<T>* tab, LD ld, ST st) {
+  const int stride = sp.stride[s], len = sp.len[s], mult = sp.mult[s];
+  const int per_col = sp.S / R;
+  const int items = per_col * TILE;
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    int c, j;
+    tile_decode<ROW, TILE>(w, per_col, c, j);
+    const int b = j / stride;
+    const int np = j - b * stride;
+    const int base = b * len + np;
+    cx_t<T> x[R];
 #pragma unroll
-  for (int q = 0; q < R; ++q) x[q] = ld(base + q * stride, c);
-  if (INV && stride > 1) {
+    for (int q = 0; q < R; ++q) x[q] = ld(base + q * stride, c);
+    if (stride > 1) {
+      // every twiddle is a correctly rounded table entry: the cepstral (minimum-phase) pipeline takes logs of
+      // spectra near their nulls and amplifies each extra ulp of transform noise (min-phase tolerance)
+      cx_t<T> wv[R];
+      const int step = np * mult;
 #pragma unroll
-    for (int p = 1; p < R; ++p) x[p] = cmul(x[p], cconj(tw_fetch<T>(tab, np * p * mult, sp)));
+      for (int p = 1; p < R; ++p) wv[p] = tw_fetch<T>(tab, step * p, sp);
+      if (INV) {
+#pragma unroll
+        for (int p = 1; p < R; ++p) x[p] = cmul(x[p], cconj(wv[p]));
+        Dft<T, R, true>::run(x);
+      } else {
+        Dft<T, R, false>::run(x);
+#pragma unroll
+        for (int p = 1; p < R; ++p) x[p] = cmul(x[p], wv[p]);
+      }
+    } else {
+      Dft<T, R, INV>::run(x);
+    }
+#pragma unroll
+    for (int p = 0; p < R; ++p) st(base + p * stride, c, x[p]);
   }
-  Dft<T, R, INV>::run(x);
-  if (!INV && stride > 1) {
-#pragma unroll
-    for (int p = 1; p < R; ++p) x[p] = cmul(x[p], tw_fetch<T>(tab, np * p * mult, sp));
-  }
-#pragma unroll
-  for (int p = 0; p < R; ++p) st(base + p * stride, c, x[p]);
 }
 
 #define IMPB_RADIX_SWITCH(r_, CALL)   \
@@ -234,115 +265,101 @@ template <typename T> __device__ __forceinline__ void load_table(cx_t<T>* tab_s,
 // ------------------------------------------------------------------------------------------------
 // forward (DIF) tile transform:  gl(e, c) -> [stages] -> gs(pos, c, v)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int TILE, class GL, class GS>
+template <typename T, int TILE, bool ROW, class GL, class GS>
 __device__ __forceinline__ void tile_fft_forward(const SubPlan& sp, cx_t<T>* tile, const cx_t<T>* tab, GL gl, GS gs) {
-  constexpr int PITCH = TILE + 1;
+  const int SP = tile_row_pitch(sp.S);
   for (int s = 0; s < sp.nst; ++s) {
     const bool first = (s == 0), last = (s == sp.nst - 1);
-    auto ld = [&](int e, int c) -> cx_t<T> { return first ? gl(e, c) : tile[e * PITCH + c]; };
+    auto ld = [&](int e, int c) -> cx_t<T> { return first ? gl(e, c) : tile[tile_addr<ROW, TILE>(e, c, SP)]; };
     auto st = [&](int e, int c, cx_t<T> v) {
-      if (last) gs(e, c, v); else tile[e * PITCH + c] = v;
+      if (last) gs(e, c, v); else tile[tile_addr<ROW, TILE>(e, c, SP)] = v;
     };
-    const int items = (sp.S / sp.radix[s]) * TILE;
-    for (int w = threadIdx.x; w < items; w += blockDim.x) {
-      const int c = w % TILE, j = w / TILE;
-#define IMPB_CALL(R_) stage_item<T, R_, false>(sp, s, j, c, tab, ld, st)
-      IMPB_RADIX_SWITCH(sp.radix[s], IMPB_CALL)
+#define IMPB_CALL(R_) stage_loop<T, TILE, R_, false, ROW>(sp, s, tab, ld, st)
+    IMPB_RADIX_SWITCH(sp.radix[s], IMPB_CALL)
 #undef IMPB_CALL
-    }
     if (!last) __syncthreads();
   }
 }
 
 // inverse (DIT) tile transform, the mirror image: stages run nst-1 .. 0
-template <typename T, int TILE, class GL, class GS>
+template <typename T, int TILE, bool ROW, class GL, class GS>
 __device__ __forceinline__ void tile_fft_inverse(const SubPlan& sp, cx_t<T>* tile, const cx_t<T>* tab, GL gl, GS gs) {
-  constexpr int PITCH = TILE + 1;
+  const int SP = tile_row_pitch(sp.S);
   for (int s = sp.nst - 1; s >= 0; --s) {
     const bool first = (s == sp.nst - 1), last = (s == 0);
-    auto ld = [&](int e, int c) -> cx_t<T> { return first ? gl(e, c) : tile[e * PITCH + c]; };
+    auto ld = [&](int e, int c) -> cx_t<T> { return first ? gl(e, c) : tile[tile_addr<ROW, TILE>(e, c, SP)]; };
     auto st = [&](int e, int c, cx_t<T> v) {
-      if (last) gs(e, c, v); else tile[e * PITCH + c] = v;
+      if (last) gs(e, c, v); else tile[tile_addr<ROW, TILE>(e, c, SP)] = v;
     };
-    const int items = (sp.S / sp.radix[s]) * TILE;
-    for (int w = threadIdx.x; w < items; w += blockDim.x) {
-      const int c = w % TILE, j = w / TILE;
-#define IMPB_CALL(R_) stage_item<T, R_, true>(sp, s, j, c, tab, ld, st)
-      IMPB_RADIX_SWITCH(sp.radix[s], IMPB_CALL)
+#define IMPB_CALL(R_) stage_loop<T, TILE, R_, true, ROW>(sp, s, tab, ld, st)
+    IMPB_RADIX_SWITCH(sp.radix[s], IMPB_CALL)
 #undef IMPB_CALL
-    }
     if (!last) __syncthreads();
   }
 }
 
 // The last DIF stage, a pointwise multiply and the first DIT stage touch the same r elements from the
-// same thread: done in registers with no shared-memory round trip in between.
-template <typename T, int R, class LD, class ST, class PW>
-__device__ __forceinline__ void mid_item(int j, int c, int w, LD ld, ST st, PW pw) {
-  cx_t<T> x[R];
-  const int base = j * R;
+// same thread: done in registers with no shared-memory round trip in between.  Row pass only.
+template <typename T, int TILE, int R, class LD, class ST, class PW>
+__device__ __forceinline__ void mid_loop(const SubPlan& sp, LD ld, ST st, PW pw) {
+  const int per_col = sp.S / R;
+  const int items = per_col * TILE;
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    int c, j;
+    tile_decode<true, TILE>(w, per_col, c, j);
+    cx_t<T> x[R];
+    const int base = j * R;
 #pragma unroll
-  for (int q = 0; q < R; ++q) x[q] = ld(base + q, c);
-  Dft<T, R, false>::run(x);
+    for (int q = 0; q < R; ++q) x[q] = ld(base + q, c);
+    Dft<T, R, false>::run(x);
 #pragma unroll
-  for (int q = 0; q < R; ++q) x[q] = cmul(x[q], pw(q, w));
-  Dft<T, R, true>::run(x);
+    for (int q = 0; q < R; ++q) x[q] = cmul(x[q], pw(q, w));
+    Dft<T, R, true>::run(x);
 #pragma unroll
-  for (int q = 0; q < R; ++q) st(base + q, c, x[q]);
+    for (int q = 0; q < R; ++q) st(base + q, c, x[q]);
+  }
 }
 
-// forward -> pointwise multiply -> inverse on one tile (circular convolution along the tile's axis)
+// forward -> pointwise multiply -> inverse on one tile (circular convolution along the tile's rows)
 template <typename T, int TILE, class GL, class GS, class PW>
 __device__ __forceinline__ void tile_fft_conv(const SubPlan& sp, cx_t<T>* tile, const cx_t<T>* tab, GL gl, GS gs, PW pw) {
-  constexpr int PITCH = TILE + 1;
+  const int SP = tile_row_pitch(sp.S);
   const int m = sp.nst - 1;
+  auto sl = [&](int e, int c) -> cx_t<T> { return tile[tile_addr<true, TILE>(e, c, SP)]; };
+  auto ss = [&](int e, int c, cx_t<T> v) { tile[tile_addr<true, TILE>(e, c, SP)] = v; };
   for (int s = 0; s < m; ++s) {
     const bool first = (s == 0);
-    auto ld = [&](int e, int c) -> cx_t<T> { return first ? gl(e, c) : tile[e * PITCH + c]; };
-    auto st = [&](int e, int c, cx_t<T> v) { tile[e * PITCH + c] = v; };
-    const int items = (sp.S / sp.radix[s]) * TILE;
-    for (int w = threadIdx.x; w < items; w += blockDim.x) {
-      const int c = w % TILE, j = w / TILE;
-#define IMPB_CALL(R_) stage_item<T, R_, false>(sp, s, j, c, tab, ld, st)
-      IMPB_RADIX_SWITCH(sp.radix[s], IMPB_CALL)
+    auto ld = [&](int e, int c) -> cx_t<T> { return first ? gl(e, c) : sl(e, c); };
+#define IMPB_CALL(R_) stage_loop<T, TILE, R_, false, true>(sp, s, tab, ld, ss)
+    IMPB_RADIX_SWITCH(sp.radix[s], IMPB_CALL)
 #undef IMPB_CALL
-    }
     __syncthreads();
   }
   {
     const bool only = (m == 0);
-    auto ld = [&](int e, int c) -> cx_t<T> { return only ? gl(e, c) : tile[e * PITCH + c]; };
+    auto ld = [&](int e, int c) -> cx_t<T> { return only ? gl(e, c) : sl(e, c); };
     auto st = [&](int e, int c, cx_t<T> v) {
-      if (only) gs(e, c, v); else tile[e * PITCH + c] = v;
+      if (only) gs(e, c, v); else ss(e, c, v);
     };
-    const int items = (sp.S / sp.radix[m]) * TILE;
-    for (int w = threadIdx.x; w < items; w += blockDim.x) {
-      const int c = w % TILE, j = w / TILE;
-#define IMPB_CALL(R_) mid_item<T, R_>(j, c, w, ld, st, pw)
-      IMPB_RADIX_SWITCH(sp.radix[m], IMPB_CALL)
+#define IMPB_CALL(R_) mid_loop<T, TILE, R_>(sp, ld, st, pw)
+    IMPB_RADIX_SWITCH(sp.radix[m], IMPB_CALL)
 #undef IMPB_CALL
-    }
     if (!only) __syncthreads();
   }
   for (int s = m - 1; s >= 0; --s) {
     const bool last = (s == 0);
-    auto ld = [&](int e, int c) -> cx_t<T> { return tile[e * PITCH + c]; };
     auto st = [&](int e, int c, cx_t<T> v) {
-      if (last) gs(e, c, v); else tile[e * PITCH + c] = v;
+      if (last) gs(e, c, v); else ss(e, c, v);
     };
-    const int items = (sp.S / sp.radix[s]) * TILE;
-    for (int w = threadIdx.x; w < items; w += blockDim.x) {
-      const int c = w % TILE, j = w / TILE;
-#define IMPB_CALL(R_) stage_item<T, R_, true>(sp, s, j, c, tab, ld, st)
-      IMPB_RADIX_SWITCH(sp.radix[s], IMPB_CALL)
+#define IMPB_CALL(R_) stage_loop<T, TILE, R_, true, true>(sp, s, tab, sl, st)
+    IMPB_RADIX_SWITCH(sp.radix[s], IMPB_CALL)
 #undef IMPB_CALL
-    }
     if (!last) __syncthreads();
   }
 }
 
 template <typename T> inline size_t tile_smem_bytes(const SubPlan& sp, int tile) {
-  return ((size_t)sp.S * (tile + 1) + (size_t)sp.ntab) * sizeof(cx_t<T>);
+  return ((size_t)tile_row_pitch(sp.S) * tile + (size_t)sp.ntab) * sizeof(cx_t<T>);
 }
 
 }  // namespace impb

@@ -206,7 +206,7 @@ static bool plan_2d_tile(const impb_ctx* ctx, int64_t n_min, bool exact, int ele
   for (int S = 2; S <= 4096; ++S) {
     if (!is_5smooth(S)) continue;
     const size_t ntab = (S % 4 == 0) ? S / 4 : S;
-    const size_t smem = ((size_t)S * (tile + 1) + ntab) * cx;
+    const size_t smem = ((size_t)((S + 7) & ~7) * tile + ntab) * cx;
     if (smem > smem_max) break;
     const int threads = smem > smem_two ? 512 : 256;
     std::vector<int> rad;
