@@ -47,6 +47,8 @@ bool make_subplan(int S, int tile, int threads, SubPlan* sp);
 bool fixed_radices(int S, int* r);
 // per-stage twiddle table of the specialised kernels (column-pass or transposed row-pass layout)
 std::vector<double> stage_table(const SubPlan& sp, int s, bool transposed);
+// the same with every power p = 1..R-1 stored (exact twiddles for the frequency-response transforms)
+std::vector<double> stage_table_full(const SubPlan& sp, int s, bool transposed);
 // digit-reversal: perm[pos] = frequency index held at tile position pos after the DIF stages
 std::vector<int> subplan_perm(const SubPlan& sp);
 

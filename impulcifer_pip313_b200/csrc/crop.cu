@@ -8,6 +8,7 @@
 // performs (x / max|x| by true division, no FMA contraction on the values that are compared).
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -155,14 +156,19 @@ __global__ void __launch_bounds__(256) k_first_peak(const double* __restrict__ x
     // (first_argmax is only consulted when no peak exists at all, so it need not be complete then)
     const unsigned long long cur = *((volatile unsigned long long*)&s[r].first_peak);
     if (cur != kNoIndex && cur < (unsigned long long)lo) return;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
-      const double v = p[i];
+    auto visit = [&](int64_t i, double v) {
       const double av = fabs(v);
       if (av == m) atomicMin(&s[r].first_argmax, (unsigned long long)i);
-      if (i < 1 || i > n - 2 || av < guard) continue;
+      if (i < 1 || i > n - 2 || av < guard) return;
       int64_t mid;
       if (peak_at(p, n, i, m, v > 0 ? 1.0 : -1.0, height, &mid)) atomicMin(&s[r].first_peak, (unsigned long long)mid);
+    };
+    int64_t i = lo + threadIdx.x;
+    for (; i + 768 < hi; i += 1024) {  // four independent loads in flight per thread
+      const double a0 = p[i], a1 = p[i + 256], a2 = p[i + 512], a3 = p[i + 768];
+      visit(i, a0); visit(i + 256, a1); visit(i + 512, a2); visit(i + 768, a3);
     }
+    for (; i < hi; i += 256) visit(i, p[i]);
   }
 }
 
@@ -195,13 +201,22 @@ int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double he
     k_peak_init<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, batch);
   // enough blocks per segment to fill the machine for small batches, few for large ones
   // ~16 samples per thread
-  int64_t chunks = std::max<int64_t>(1, (max_len_hint + thr * 16 - 1) / (thr * 16));
+  static const int spt = getenv("IMPB_PEAK_SPT") ? atoi(getenv("IMPB_PEAK_SPT")) : 16;
+  int64_t chunks = std::max<int64_t>(1, (max_len_hint + thr * spt - 1) / (thr * spt));
   chunks = std::min<int64_t>(chunks, 4096);
   for (int64_t b0 = 0; b0 < batch; b0 += (int64_t)1 << 30) {
     const int64_t nb = std::min<int64_t>((int64_t)1 << 30, batch - b0);
     dim3 grid((unsigned)nb, (unsigned)chunks);
     if (!known_max) k_absmax<<<grid, thr, 0, st>>>(x, va, b0, scratch + b0);
-    const dim3 pgrid((unsigned)nb, (unsigned)std::min<int64_t>(chunks, 8));
+    // Blocks per row.  Head-cropped views (they carry the max hint) have their onset within the first samples: the
+    // row is walked front to back by just enough blocks to fill the machine (896 rows on B200: 2 blocks per row
+    // 111 us, one block per chunk 192 us, mostly block scheduling).  Raw estimates have the onset anywhere (the
+    // 'same' slice puts it ~40 % into the row): every chunk gets its own block and the ones behind a published
+    // peak drop out (2 blocks per row: 1004 us, one per chunk: ~200 us).
+    static const int peak_g = getenv("IMPB_PEAK_G") ? atoi(getenv("IMPB_PEAK_G")) : 0;
+    const bool near_start = va.hint_max != nullptr;
+    const int64_t want = peak_g > 0 ? peak_g : near_start ? std::max<int64_t>(1, 2048 / std::max<int64_t>(nb, 1)) : chunks;
+    const dim3 pgrid((unsigned)nb, (unsigned)std::min<int64_t>(chunks, want));
     k_first_peak<<<pgrid, thr, 0, st>>>(x, va, b0, height, scratch + b0, (int)chunks);
   }
   k_peak_final<<<(unsigned)((batch + thr - 1) / thr), thr, 0, st>>>(scratch, peak_out, batch);

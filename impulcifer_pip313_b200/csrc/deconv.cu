@@ -263,7 +263,7 @@ template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
 #define IMPB_FX_CASE(KERNEL, S_, R0_, R1_, R2_)                                                 \
   case S_: {                                                                                    \
     auto k = KERNEL<T, TILE, 256, Radix3<R0_, R1_, R2_>, F>;                                     \
-    const size_t smem = (size_t)S_ * TILE * sizeof(cx_t<T>);                                     \
+    const size_t smem = fx_tile_elems<S_, TILE>() * sizeof(cx_t<T>);                             \
     int rc = fx_prepare(k, smem, device);                                                        \
     if (rc) return rc;                                                                           \
     k<<<grid, 256, smem, st>>>(tw0, tw1, f);                                                     \
@@ -291,8 +291,12 @@ template <typename T> struct DeconvEngine {
   int device = 0;
   static constexpr int FULL = TileOf<T>::value;  // 8 (f64) / 16 (f32)
 
+  // lengths with an instantiated K1 kernel triple (IMPB_FX_DISPATCH below); other specialised lengths of the menu
+  // in plan.cu:fixed_radices only serve the frequency-response transforms
+  static bool k1_length(int S) { return S == 768; }
   bool fixed_path() const {
-    return fft.p.tile == FULL && fft.col_fixed && fft.row_fixed && getenv("IMPB_NO_FIXED") == nullptr;
+    return fft.p.tile == FULL && fft.col_fixed && fft.row_fixed && k1_length(fft.p.N1) && k1_length(fft.p.N2) &&
+           getenv("IMPB_NO_FIXED") == nullptr;
   }
 
   int launch(const DeconvArgs<T>& a, int pairs, cudaStream_t st) const {
@@ -302,7 +306,7 @@ template <typename T> struct DeconvEngine {
   template <int TILE> int launch_t(const DeconvArgs<T>& a, int pairs, cudaStream_t st) const {
     int rc;
     static const bool no_fixed = getenv("IMPB_NO_FIXED") != nullptr;
-    if (TILE == FULL && fft.col_fixed && fft.row_fixed && !no_fixed) {
+    if (TILE == FULL && fixed_path() && !no_fixed) {
       const Plan2D& p = fft.p;
       static const bool no_async = getenv("IMPB_NO_ASYNC") != nullptr;
       if constexpr (TILE == FULL) {
@@ -325,9 +329,9 @@ template <typename T> struct DeconvEngine {
       return fx_inv<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
                              DeconvColOut<T, TILE>{a});
     }
-    if ((rc = fft.template col_fwd<TILE>(DeconvColIn<T, TILE>{a}, pairs, st))) return rc;
+    if ((rc = fft.template col_fwd<TILE, false>(DeconvColIn<T, TILE>{a}, pairs, st))) return rc;
     if ((rc = fft.template row_conv<TILE>(DeconvRow<T, TILE>{a}, pairs, st))) return rc;
-    if ((rc = fft.template col_inv<TILE>(DeconvColOut<T, TILE>{a}, pairs, st))) return rc;
+    if ((rc = fft.template col_inv<TILE, false>(DeconvColOut<T, TILE>{a}, pairs, st))) return rc;
     if (a.absmax) {  // the generic column pass does not track maxima: one extra read of the rows just written
       const int64_t r0 = a.row0, nr = std::min<int64_t>(2 * (int64_t)pairs, a.nrows - r0);
       const dim3 grid((unsigned)nr, (unsigned)std::max<int64_t>(1, std::min<int64_t>(a.out_len / 4096, 1024)));
@@ -394,11 +398,11 @@ static int build_spectrum(impb_plan* pl, const double* inv_host) {
   a.rec = d_h; a.ld_in = pl->M; a.len = pl->M; a.nrows = 1; a.row0 = 0; a.in_fmt = IMPB_FMT_F64;
   int rc;
   if (f64->p.tile == 8) {
-    rc = f64->col_fwd<8>(DeconvColIn<double, 8>{a}, 1, 0);
-    if (!rc) rc = f64->row_fwd<8>(RowPlain<double, 8>{ws, ws, nullptr, (int64_t)N, N1, N2, 0, 0}, 1, 0);
+    rc = f64->col_fwd<8, false>(DeconvColIn<double, 8>{a}, 1, 0);
+    if (!rc) rc = f64->row_fwd<8, false>(RowPlain<double, 8>{ws, ws, nullptr, (int64_t)N, N1, N2, 0, 0}, 1, 0);
   } else {
-    rc = f64->col_fwd<4>(DeconvColIn<double, 4>{a}, 1, 0);
-    if (!rc) rc = f64->row_fwd<4>(RowPlain<double, 4>{ws, ws, nullptr, (int64_t)N, N1, N2, 0, 0}, 1, 0);
+    rc = f64->col_fwd<4, false>(DeconvColIn<double, 4>{a}, 1, 0);
+    if (!rc) rc = f64->row_fwd<4, false>(RowPlain<double, 4>{ws, ws, nullptr, (int64_t)N, N1, N2, 0, 0}, 1, 0);
   }
   if (!rc) {
     const int thr = 256;

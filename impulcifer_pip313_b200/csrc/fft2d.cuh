@@ -1,8 +1,12 @@
 // Host-side handle for one N = N1 x N2 transform: owns the device tables of a Plan2D and launches passes.
 #pragma once
+#include <mutex>
+#include <set>
+#include <stdlib.h>
 #include <vector>
 
 #include "common.cuh"
+#include "fft_fixed.cuh"
 #include "fft_kernels.cuh"
 
 namespace impb {
@@ -14,6 +18,9 @@ template <typename T> struct Fft2D {
   cx_t<T>* tab_row = nullptr;
   cx_t<T>* fx_col[2] = {nullptr, nullptr};  // per-stage tables of the specialised kernels (if fixed)
   cx_t<T>* fx_row[2] = {nullptr, nullptr};
+  cx_t<T>* fxf_col[2] = {nullptr, nullptr};  // full (exact) stage tables of the plain specialised passes
+  cx_t<T>* fxf_row[2] = {nullptr, nullptr};
+  int device = 0;
   bool col_fixed = false, row_fixed = false;
   int* perm_col = nullptr;     // device copies of the digit-reversal maps
   int* perm_row = nullptr;
@@ -57,8 +64,15 @@ template <typename T> struct Fft2D {
         cx_t<T>** dst = which ? &fx_row[s] : &fx_col[s];
         IMPB_CUDA(cudaMalloc(dst, tt.size() * sizeof(cx_t<T>)));
         IMPB_CUDA(cudaMemcpy(*dst, tt.data(), tt.size() * sizeof(cx_t<T>), cudaMemcpyHostToDevice));
+        std::vector<double> tf = stage_table_full(sp, s, /*transposed=*/which == 1);
+        std::vector<cx_t<T>> ttf(tf.size() / 2);
+        for (size_t i = 0; i < ttf.size(); ++i) ttf[i] = mkc<T>((T)tf[2 * i], (T)tf[2 * i + 1]);
+        dst = which ? &fxf_row[s] : &fxf_col[s];
+        IMPB_CUDA(cudaMalloc(dst, ttf.size() * sizeof(cx_t<T>)));
+        IMPB_CUDA(cudaMemcpy(*dst, ttf.data(), ttf.size() * sizeof(cx_t<T>), cudaMemcpyHostToDevice));
       }
     }
+    IMPB_CUDA(cudaGetDevice(&device));
     IMPB_CUDA(cudaMalloc(&perm_col, p.N1 * sizeof(int)));
     IMPB_CUDA(cudaMalloc(&perm_row, p.N2 * sizeof(int)));
     IMPB_CUDA(cudaMemcpy(perm_col, h_perm_col.data(), p.N1 * sizeof(int), cudaMemcpyHostToDevice));
@@ -68,7 +82,10 @@ template <typename T> struct Fft2D {
 
   void release() {
     cudaFree(tw); cudaFree(tab_col); cudaFree(tab_row); cudaFree(perm_col); cudaFree(perm_row);
-    for (int s = 0; s < 2; ++s) { cudaFree(fx_col[s]); cudaFree(fx_row[s]); fx_col[s] = fx_row[s] = nullptr; }
+    for (int s = 0; s < 2; ++s) {
+      cudaFree(fx_col[s]); cudaFree(fx_row[s]); cudaFree(fxf_col[s]); cudaFree(fxf_row[s]);
+      fx_col[s] = fx_row[s] = fxf_col[s] = fxf_row[s] = nullptr;
+    }
     tw = tab_col = tab_row = nullptr;
     perm_col = perm_row = nullptr;
   }
@@ -76,29 +93,84 @@ template <typename T> struct Fft2D {
   int col_tiles() const { return (p.N2 + p.tile - 1) / p.tile; }
   int row_tiles() const { return (p.N1 + p.tile - 1) / p.tile; }
 
+  // ---- specialised plain passes (fft_fixed.cuh:k_fxg_*): lengths of plan.cu:fixed_radices, full-width tiles ----------
+  template <class K> static int fxg_prepare(K kernel, size_t smem, int device) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    const std::pair<const void*, int> key((const void*)kernel, device);
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count(key)) return IMPB_OK;
+    IMPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done.insert(key);
+    return IMPB_OK;
+  }
+#define IMPB_FXG_CASE(S_, R0_, R1_, R2_)                                                             \
+  case S_: {                                                                                         \
+    auto k = INV ? k_fxg_inv<T, TILE, 256, Radix3<R0_, R1_, R2_>, ROW, F>                             \
+                 : k_fxg_fwd<T, TILE, 256, Radix3<R0_, R1_, R2_>, ROW, F>;                            \
+    const size_t smem = fx_tile_elems<S_, TILE>() * sizeof(cx_t<T>);                                  \
+    int rc = fxg_prepare(k, smem, device);                                                            \
+    if (rc) return rc;                                                                                \
+    k<<<grid, 256, smem, st>>>(tw0, tw1, f);                                                          \
+    IMPB_CUDA(cudaGetLastError());                                                                    \
+    return IMPB_OK;                                                                                   \
+  }
+  template <int TILE, bool ROW, bool INV, class F> int fxg_launch(int S, dim3 grid, const F& f, cudaStream_t st) const {
+    const cx_t<T>* tw0 = ROW ? fxf_row[0] : fxf_col[0];
+    const cx_t<T>* tw1 = ROW ? fxf_row[1] : fxf_col[1];
+    switch (S) {
+      IMPB_FXG_CASE(768, 8, 12, 8)
+      IMPB_FXG_CASE(675, 15, 9, 5)
+      IMPB_FXG_CASE(432, 12, 9, 4)
+      IMPB_FXG_CASE(400, 10, 8, 5)
+      IMPB_FXG_CASE(300, 12, 5, 5)
+      IMPB_FXG_CASE(256, 8, 8, 4)
+      IMPB_FXG_CASE(243, 9, 9, 3)
+      IMPB_FXG_CASE(162, 9, 6, 3)
+      IMPB_FXG_CASE(160, 8, 5, 4)
+      IMPB_FXG_CASE(135, 5, 9, 3)
+      IMPB_FXG_CASE(128, 8, 4, 4)
+      IMPB_FXG_CASE(125, 5, 5, 5)
+      IMPB_FXG_CASE(120, 8, 5, 3)
+      IMPB_FXG_CASE(108, 4, 9, 3)
+      IMPB_FXG_CASE(81, 3, 9, 3)
+      IMPB_FXG_CASE(75, 5, 5, 3)
+      default: set_error("no specialised pass for S=%d", S); return IMPB_EUNSUPPORTED;
+    }
+  }
+#undef IMPB_FXG_CASE
+  template <int TILE> bool fxg_ok(bool row) const {
+    static const bool off = getenv("IMPB_NO_FIXED") != nullptr;
+    return !off && TILE == TileOf<T>::value && (row ? row_fixed : col_fixed);
+  }
+
   // launch helpers; F is a functor type, TILE must equal p.tile
-  template <int TILE, class F> int col_fwd(const F& f, int batch, cudaStream_t st) const {
+  template <int TILE, bool ALLOW_FX = true, class F> int col_fwd(const F& f, int batch, cudaStream_t st) const {
+    if constexpr (ALLOW_FX) if (fxg_ok<TILE>(false)) return fxg_launch<TILE, false, false>(p.N1, dim3(col_tiles(), batch), f, st);
     auto k = k_tile_fwd<T, TILE, false, F>;
     IMPB_CUDA(set_smem(k, p.smem_col));
     k<<<dim3(col_tiles(), batch), p.threads, p.smem_col, st>>>(p.col, tab_col, f);
     IMPB_CUDA(cudaGetLastError());
     return IMPB_OK;
   }
-  template <int TILE, class F> int col_inv(const F& f, int batch, cudaStream_t st) const {
+  template <int TILE, bool ALLOW_FX = true, class F> int col_inv(const F& f, int batch, cudaStream_t st) const {
+    if constexpr (ALLOW_FX) if (fxg_ok<TILE>(false)) return fxg_launch<TILE, false, true>(p.N1, dim3(col_tiles(), batch), f, st);
     auto k = k_tile_inv<T, TILE, false, F>;
     IMPB_CUDA(set_smem(k, p.smem_col));
     k<<<dim3(col_tiles(), batch), p.threads, p.smem_col, st>>>(p.col, tab_col, f);
     IMPB_CUDA(cudaGetLastError());
     return IMPB_OK;
   }
-  template <int TILE, class F> int row_fwd(const F& f, int batch, cudaStream_t st) const {
+  template <int TILE, bool ALLOW_FX = true, class F> int row_fwd(const F& f, int batch, cudaStream_t st) const {
+    if constexpr (ALLOW_FX) if (fxg_ok<TILE>(true)) return fxg_launch<TILE, true, false>(p.N2, dim3(row_tiles(), batch), f, st);
     auto k = k_tile_fwd<T, TILE, true, F>;
     IMPB_CUDA(set_smem(k, p.smem_row));
     k<<<dim3(row_tiles(), batch), p.threads, p.smem_row, st>>>(p.row, tab_row, f);
     IMPB_CUDA(cudaGetLastError());
     return IMPB_OK;
   }
-  template <int TILE, class F> int row_inv(const F& f, int batch, cudaStream_t st) const {
+  template <int TILE, bool ALLOW_FX = true, class F> int row_inv(const F& f, int batch, cudaStream_t st) const {
+    if constexpr (ALLOW_FX) if (fxg_ok<TILE>(true)) return fxg_launch<TILE, true, true>(p.N2, dim3(row_tiles(), batch), f, st);
     auto k = k_tile_inv<T, TILE, true, F>;
     IMPB_CUDA(set_smem(k, p.smem_row));
     k<<<dim3(row_tiles(), batch), p.threads, p.smem_row, st>>>(p.row, tab_row, f);

@@ -35,16 +35,20 @@ template <int R0_, int R1_, int R2_> struct Radix3 {
 //  * row pass (ROW = true): j fastest.  A quarter-warp is 8 consecutive elements of ONE row: again one 128-byte
 //    HBM segment (with c fastest it would be 8 different lines = 8x the LSU wavefronts, measured 18 wavefronts
 //    per request in round 1).  Tile is [c][S] with  e' = e ^ ((e >> 3) & 7), conflict-free for strides 64, 8, 1.
-// No padding: the tile is exactly S * TILE elements.
+// The row pitch is S rounded up to 16 (the XOR stays inside an aligned group of 8 / 16 elements), so sub-FFT lengths
+// that are not multiples of 16 (125, 75 ...) do not run into the next row; for 768 / 256 / 128 there is no padding.
+constexpr int fx_pitch(int S) { return (S + 15) & ~15; }
+template <int S, int TILE> constexpr size_t fx_tile_elems() { return (size_t)fx_pitch(S) * TILE; }
 template <bool ROW, int TILE, int PER_COL> __device__ __forceinline__ void fx_decode(int w, int& c, int& j) {
   if (ROW) { j = w % PER_COL; c = w / PER_COL; } else { c = w % TILE; j = w / TILE; }
 }
 template <bool ROW, int TILE, int S> __device__ __forceinline__ int fx_smem(int e, int c) {
   if (!ROW) return e * TILE + (c ^ (e & (TILE - 1)));
-  if (TILE == 8) return c * S + (e ^ ((e >> 3) & 7));  // 16-byte elements: 8 slots per 128 B, quarter-warps
+  constexpr int SP = fx_pitch(S);
+  if (TILE == 8) return c * SP + (e ^ ((e >> 3) & 7));  // 16-byte elements: 8 slots per 128 B, quarter-warps
   // 8-byte elements (FP32 tiles): a half-warp must cover 16 distinct slots for strides 96, 8 and 1
   const int v = e >> 4;
-  return c * S + (e ^ (v & 7) ^ (((v >> 1) & 1) << 3));
+  return c * SP + (e ^ (v & 7) ^ (((v >> 1) & 1) << 3));
 }
 
 // Stage twiddles w_p = exp(-2 pi i np p / LEN), p = 1..R-1, from the power-of-two entries of the table only
@@ -53,8 +57,16 @@ template <bool ROW, int TILE, int S> __device__ __forceinline__ int fx_smem(int 
 #ifndef IMPB_TW_LOADS
 #define IMPB_TW_LOADS 1  // how many of the power-of-two entries are loaded; the rest are squared from the last one
 #endif
-template <typename T, int R, bool ROW, int STRIDE>
+// FULL: every w_p is its own correctly rounded table entry (tw[np][p-1] / tw[p-1][np]).  Used by the frequency-
+// response transforms: the cepstral minimum-phase chain takes logs of spectra next to their nulls and amplifies
+// each extra ulp of transform noise (min-phase tolerance), so no composed twiddles there.
+template <typename T, int R, bool ROW, int STRIDE, bool FULL = false>
 __device__ __forceinline__ void fx_twiddles(const cx_t<T>* __restrict__ tw, int np, cx_t<T>* w) {
+  if constexpr (FULL) {
+#pragma unroll
+    for (int p = 1; p < R; ++p) w[p] = __ldg(ROW ? tw + (p - 1) * STRIDE + np : tw + np * (R - 1) + (p - 1));
+    return;
+  }
   constexpr int NB = (R > 8) ? 4 : (R > 4) ? 3 : (R > 2) ? 2 : 1;
   constexpr int NL = NB < IMPB_TW_LOADS ? NB : IMPB_TW_LOADS;
   const cx_t<T>* twp = ROW ? tw + np : tw + np * NB;
@@ -76,8 +88,8 @@ __device__ __forceinline__ void fx_twiddles(const cx_t<T>* __restrict__ tw, int 
 // multiplier per OUTPUT element (four-step twiddle); it is fetched at the top of the trip so that its latency
 // hides behind the butterfly instead of sitting in front of the store.
 struct NoPost {};
-template <typename T, int TILE, int NT, int S, int LEN, int R, bool INV, bool ROW, bool PF = false, class LD, class ST,
-          class POST>
+template <typename T, int TILE, int NT, int S, int LEN, int R, bool INV, bool ROW, bool PF = false, bool TWFULL = false,
+          class LD, class ST, class POST>
 __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, ST st, POST post) {
   constexpr int STRIDE = LEN / R;
   constexpr int PER_COL = S / R;
@@ -126,7 +138,7 @@ __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, 
     }
     if (STRIDE > 1) {
       cx_t<T> wv[R];
-      fx_twiddles<T, R, ROW, STRIDE>(tw, np, wv);
+      fx_twiddles<T, R, ROW, STRIDE, TWFULL>(tw, np, wv);
       if (INV) {
 #pragma unroll
         for (int p = 1; p < R; ++p) x[p] = cmul(x[p], cconj(wv[p]));
@@ -303,6 +315,45 @@ k_fx_conv(const cx_t<T>* __restrict__ tw0r, const cx_t<T>* __restrict__ tw1r, co
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true, true>(tw1r, sl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, true, true>(tw0r, sl, gs, post);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward-only / inverse-only passes for plain functors (F.load / F.store, the four-step twiddle applied by the
+// functor itself): the frequency-response transforms of fr.cu (K8 magnitudes, firwin2, cepstrum) run through
+// these whenever their sub-FFT length has a specialised radix sequence, with full-table (exact) stage twiddles.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int TILE, int NT, class RX, bool ROW, class F>
+__global__ void __launch_bounds__(NT, 2)
+k_fxg_fwd(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
+  const int t = blockIdx.x, b = blockIdx.y;
+  auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
+  auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
+  auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<ROW, TILE, RX::S>(e, c)]; };
+  auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<ROW, TILE, RX::S>(e, c)] = v; };
+  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, ROW, false, true>(tw0, gl, ss, NoPost{});
+  __syncthreads();
+  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false, ROW, false, true>(tw1, sl, ss, NoPost{});
+  __syncthreads();
+  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, false, ROW, false, true>(nullptr, sl, gs, NoPost{});
+}
+
+template <typename T, int TILE, int NT, class RX, bool ROW, class F>
+__global__ void __launch_bounds__(NT, 2)
+k_fxg_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
+  const int t = blockIdx.x, b = blockIdx.y;
+  auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
+  auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
+  auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<ROW, TILE, RX::S>(e, c)]; };
+  auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<ROW, TILE, RX::S>(e, c)] = v; };
+  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, ROW, false, true>(nullptr, gl, ss, NoPost{});
+  __syncthreads();
+  fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true, ROW, false, true>(tw1, sl, ss, NoPost{});
+  __syncthreads();
+  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, true, ROW, false, true>(tw0, sl, gs, NoPost{});
 }
 
 }  // namespace impb

@@ -64,12 +64,43 @@ static double subplan_cost(int S, int tile, int threads, std::vector<int>* radic
 }
 
 bool fixed_radices(int S, int* r) {
-  // sub-FFT lengths with a compile-time specialised kernel (fft_fixed.cuh); keep in sync with the
-  // dispatch switches in deconv.cu
+  // sub-FFT lengths with compile-time specialised kernels (fft_fixed.cuh); keep in sync with the dispatch switches
+  // in fft2d.cuh (every length: plain forward / inverse passes) and deconv.cu (768: the fused K1 triple)
   switch (S) {
     case 768: r[0] = 8; r[1] = 12; r[2] = 8; return true;
+    case 675: r[0] = 15; r[1] = 9; r[2] = 5; return true;
+    case 432: r[0] = 12; r[1] = 9; r[2] = 4; return true;
+    case 400: r[0] = 10; r[1] = 8; r[2] = 5; return true;
+    case 300: r[0] = 12; r[1] = 5; r[2] = 5; return true;
+    case 256: r[0] = 8; r[1] = 8; r[2] = 4; return true;
+    case 243: r[0] = 9; r[1] = 9; r[2] = 3; return true;
+    case 162: r[0] = 9; r[1] = 6; r[2] = 3; return true;
+    case 160: r[0] = 8; r[1] = 5; r[2] = 4; return true;
+    case 135: r[0] = 5; r[1] = 9; r[2] = 3; return true;
+    case 128: r[0] = 8; r[1] = 4; r[2] = 4; return true;
+    case 125: r[0] = 5; r[1] = 5; r[2] = 5; return true;
+    case 120: r[0] = 8; r[1] = 5; r[2] = 3; return true;
+    case 108: r[0] = 4; r[1] = 9; r[2] = 3; return true;
+    case 81: r[0] = 3; r[1] = 9; r[2] = 3; return true;
+    case 75: r[0] = 5; r[1] = 5; r[2] = 3; return true;
     default: return false;
   }
+}
+
+std::vector<double> stage_table_full(const SubPlan& sp, int s, bool transposed) {
+  // every stage twiddle exp(-2 pi i np p / len_s), p = 1..R-1, at [np*(R-1) + p-1] (column pass) or
+  // [(p-1)*stride + np] (row pass): the exact-twiddle tables of the plain specialised passes
+  const int R = sp.radix[s], st = sp.stride[s], len = sp.len[s];
+  std::vector<double> t(2 * (size_t)st * (R - 1));
+  for (int np = 0; np < st; ++np)
+    for (int p = 1; p < R; ++p) {
+      double re, im;
+      unit_root((int64_t)np * p, len, &re, &im);
+      const size_t i = transposed ? (size_t)(p - 1) * st + np : (size_t)np * (R - 1) + (p - 1);
+      t[2 * i] = re;
+      t[2 * i + 1] = im;
+    }
+  return t;
 }
 
 bool make_subplan(int S, int tile, int threads, SubPlan* sp) {

@@ -85,6 +85,8 @@ class BatchDispatcher:
         self.fs = estimator.fs
         self._layout = None
         self.launches = 0
+        self.phase_timing = False   # developer hook: record device time per phase of process() into phase_ms
+        self.phase_ms = []
 
     # ---- static layout of one set ---------------------------------------------------------------------
     def _prepare(self, n_tracks, n_samples, device):
@@ -171,7 +173,16 @@ class BatchDispatcher:
         B = S * n
         head = int(self.head_ms * fs / 1000)
         launches = 0
+        marks = [] if self.phase_timing else None
+
+        def mark(name):  # developer hook (tools/profile_dispatch.py): device-time stamps between the phases
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
         with torch.cuda.device(dev):
+            mark('start')
             set_base = torch.arange(S, device=dev, dtype=torch.int64)[:, None]
             # 1. deconvolution of every column of every set (K1)
             row_offs = (set_base * (n_tracks * n_samples) + lay['offs'][None, :]).reshape(-1)
@@ -182,12 +193,14 @@ class BatchDispatcher:
             if E.dtype != torch.float64:
                 E = E.to(torch.float64)
             launches += plan.launches(B)
+            mark('K1 deconvolution')
             flatE = E.reshape(-1)
             rows = torch.arange(B, device=dev, dtype=torch.int64)
             full = torch.full((B,), L, device=dev, dtype=torch.int64)
             # 2. first peaks (K2) and the pairwise head crop (ref core/hrir.py:573-606), integer ops on device
             peaks = ops.peak_index(flatE, rows * L, full, max_len=L, known_max=e_max)
             launches += 3
+            mark('first peaks')
             pk = peaks.view(S, n)
             pl, pr = pk[:, lay['left']], pk[:, lay['right']]
             first = torch.where(pl < pr, pl, pr)
@@ -217,6 +230,7 @@ class BatchDispatcher:
                 shift.index_add_(1, lay['pos_rows'], torch.clamp(lags, min=0)[:, lay['pos_k']])
                 shift.index_add_(1, lay['neg_rows'], torch.clamp(-lags, min=0)[:, lay['neg_k']])
             shift = shift.reshape(-1)
+            mark('head crop + ipsilateral lag')
             lo = torch.clamp(shift, min=0)
             hi = torch.maximum(torch.minimum(n1 + shift, n1), lo)
             # 4. group onset alignment against FL-left (ref :957-1001): K2 on the shifted views of the leaders
@@ -232,6 +246,7 @@ class BatchDispatcher:
             elif 'FL' not in lay['speakers']:
                 raise RuntimeError("Cannot find FL left channel reference for onset alignment.")
             shift2 = shift2.reshape(-1)
+            mark('group onset peaks')
             # two length-preserving shifts compose into one shift plus a surviving range
             total = shift + shift2
             lo = torch.clamp(lo + shift2, min=0)
@@ -240,6 +255,7 @@ class BatchDispatcher:
             # 5. Lundeby knee per response (K4) -> per-set tail index (ref :614-653): the one host sync
             _, knee, _, _ = ops.lundeby(flatE, off1, n1, fs, max_len=L, view=view)
             launches += 5
+            mark('Lundeby')
             host = torch.stack([knee, n1, peaks, crop]).cpu().numpy()
             knees_h, n1_h, peaks_h, crop_h = (host[i].reshape(S, n) for i in range(4))
             if head > 0 and n1_h.min() < head:
@@ -261,6 +277,10 @@ class BatchDispatcher:
                 launches += 1
                 for k, s in enumerate(sets):
                     results[s] = SetResult(lay['names'], out[k], tail, peaks_h[s], crop_h[s], knees_h[s], side_msgs[s])
+            mark('tail gather')
+        if marks is not None:
+            torch.cuda.synchronize(dev)
+            self.phase_ms = [(b[0], a[1].elapsed_time(b[1])) for a, b in zip(marks[:-1], marks[1:])]
         self.launches = launches
         return results
 

@@ -141,3 +141,41 @@ dist.destroy_process_group()
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "GATHER_OK" in r.stdout
+
+
+def test_next_row_host_constants_match_reference_formulas():
+    """Host-side pieces of the next-row chains (no device work): the correction-limit mask, the microphone band taper,
+    the virtual-bass filter constants and the golden fixtures they were pinned with."""
+    from scipy import signal
+    from impulcifer_pip313_b200 import room_correction as rc
+    from impulcifer_pip313_b200.frequency_response import FrequencyResponse
+    from impulcifer_pip313_b200.microphone_deviation import MicrophoneMatchingCorrector
+    from impulcifer_pip313_b200.virtual_bass import bass_constants, rbj_high_shelf
+    from _util import load
+    f = FrequencyResponse.generate_frequencies(f_step=1.01, f_min=10, f_max=24000)
+    for limit in (400, 1000, 63.0):
+        start, end = np.argmax(f > limit / 2), np.argmax(f > limit)
+        want = np.concatenate([np.ones(start), signal.windows.hann(end - start), np.zeros(len(f) - end)])
+        np.testing.assert_allclose(rc.correction_limit_mask(f, limit), want, rtol=0, atol=1e-15)
+    # the golden mismatch curve is zero outside the taper and clamped inside: same band weight as the reference used
+    g = load('room_chain_golden.npz')
+    c = MicrophoneMatchingCorrector(48000)
+    w = c._band_weight()
+    assert np.array_equal(c.frequency, g['mic_frequency'])
+    assert np.all(g['mic_auto_mismatch'][w == 0] == 0) and np.all(np.abs(g['mic_auto_mismatch']) <= 12.0)
+    assert w[np.searchsorted(c.frequency, 1000)] == 1.0 and w[0] == 0.0 and 0.0 <= w[-1] < 1e-3
+    assert (c.win_samples, c.pre_samples) == (240, 24)
+    # virtual-bass constants: causal impulse responses of the reference's own filter designs
+    h_hp8, mpbass, sos_ild = bass_constants(4096, 48000, 250, 15.0)
+    hp4 = signal.butter(4, 250 / 24000, btype="high", output="sos")
+    imp = np.zeros(4096)
+    imp[0] = 1.0
+    assert np.array_equal(h_hp8, signal.sosfilt(np.vstack([hp4, hp4]), imp))
+    x = np.random.default_rng(0).standard_normal(4096)
+    direct = signal.sosfilt(np.vstack([hp4, hp4]), x)
+    via_ir = np.convolve(x, h_hp8)[:4096]
+    assert np.max(np.abs(direct - via_ir)) < 1e-12 * np.max(np.abs(direct))   # what virtual_bass.py relies on
+    assert sos_ild.shape == (3, 6) and mpbass.shape == (4096,)
+    sh = rbj_high_shelf(400.0, 48000, -3.0, 0.66)
+    wz, hz = signal.sosfreqz(sh, worN=[1e-3, np.pi * 0.999])
+    assert abs(20 * np.log10(abs(hz[0]))) < 1e-3 and abs(20 * np.log10(abs(hz[1])) + 3.0) < 1e-3
