@@ -192,7 +192,7 @@ class BatchDispatcher:
             E = plan.execute(recordings.reshape(-1), length=L, row_offsets=row_offs, absmax=e_max, argmax=e_arg)
             if E.dtype != torch.float64:
                 E = E.to(torch.float64)
-            launches += plan.launches(B)
+            launches += plan.launches(B) + 1  # + argmax pick
             mark('K1 deconvolution')
             flatE = E.reshape(-1)
             rows = torch.arange(B, device=dev, dtype=torch.int64)
@@ -254,7 +254,7 @@ class BatchDispatcher:
             view = dict(shift=total, valid_lo=lo, valid_hi=hi, fade_in=window_in, hint_max=e_max, hint_argmax=hint_arg)
             # 5. Lundeby knee per response (K4) -> per-set tail index (ref :614-653): the one host sync
             _, knee, _, _ = ops.lundeby(flatE, off1, n1, fs, max_len=L, view=view)
-            launches += 5
+            launches += 7  # peak_index (init, max, first peak, final) + window max + block sums + Lundeby
             mark('Lundeby')
             host = torch.stack([knee, n1, peaks, crop]).cpu().numpy()
             knees_h, n1_h, peaks_h, crop_h = (host[i].reshape(S, n) for i in range(4))
