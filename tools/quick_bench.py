@@ -12,7 +12,8 @@ from impulcifer_pip313_b200.estimator import ImpulseResponseEstimator
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 224
 prec = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-est = ImpulseResponseEstimator(5.0, 48000)
+fs = int(sys.argv[4]) if len(sys.argv) > 4 else 48000
+est = ImpulseResponseEstimator(5.0, fs)
 L = 2 * est.fs + len(est)
 x = torch.randn(batch, L, dtype=torch.float64, device='cuda') * 0.01
 if prec == 32:
