@@ -482,8 +482,9 @@ int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, in
   }
   const size_t cx = precision == 64 ? sizeof(double2) : sizeof(float2);
   // pairs per launch triple: measured on B200, fewer/larger launches beat L2-resident chunks at the
-  // current kernel speed (tools/quick_bench.py, IMPB_CHUNK_PAIRS sweep); cap the workspace at 1 GiB
-  int64_t chunk = (int64_t)((size_t)1 << 30) / (int64_t)(p.N * cx);
+  // current kernel speed (tools/quick_bench.py, IMPB_CHUNK_PAIRS sweep: 6 pairs 3.53 ms, 37 pairs 3.00 ms, 113 pairs
+  // 2.80 ms, 224 pairs 2.75 ms per 448 IRs); cap the workspace at 4 GiB of the 180 GB
+  int64_t chunk = (int64_t)((size_t)4 << 30) / (int64_t)(p.N * cx);
   if (const char* e = getenv("IMPB_CHUNK_PAIRS")) chunk = atoll(e);
   pl->chunk_pairs = std::max<int64_t>(1, std::min<int64_t>(chunk, 32768));
   if (const char* e = getenv("IMPB_STREAMS")) pl->nstreams = std::max(1, std::min(4, atoi(e)));
