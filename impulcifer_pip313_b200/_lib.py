@@ -33,7 +33,8 @@ SIGNATURES = {
     "impb_deconv_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "impb_deconv_plan_info": (c_i32, [c_vp, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "impb_deconv_execute": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp,
-                                    c_vp, c_i64, c_vp, c_vp]),
+                                    c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "impb_deconv_blockmax_info": (c_i32, [c_vp, c_i64, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "impb_deconv_launches_per_execute": (c_i32, [c_vp, c_i64]),
     "impb_peak_index": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_i64, c_i64, c_vp]),
     "impb_lundeby": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
@@ -69,7 +70,8 @@ SIGNATURES = {
 class View(C.Structure):
     """``impb_view`` of include/impb.h (all members optional)."""
     _fields_ = [("shift", c_vp), ("valid_lo", c_vp), ("valid_hi", c_vp), ("fade_in", c_vp), ("fade_in_len", c_i64),
-                ("hint_max", c_vp), ("hint_argmax", c_vp)]
+                ("hint_max", c_vp), ("hint_argmax", c_vp), ("blk_max", c_vp), ("nblk", c_i64), ("blk_len", c_i64),
+                ("blk_first", c_i64)]
 
 
 class ImpbError(RuntimeError):

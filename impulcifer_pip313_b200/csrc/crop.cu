@@ -34,6 +34,8 @@ struct ViewArgs {
   int64_t fade_len;
   const double* hint_max;      // nullable pair: max |src| over a superset of the view and one source index
   const int64_t* hint_arg;     //                (relative to offsets[r]) where it is attained
+  const double* blk_max;       // nullable: [rows][nblk] block maxima of the untouched samples
+  int64_t nblk, blk_len, blk_first;
 };
 
 struct RowView {
@@ -149,7 +151,16 @@ __global__ void __launch_bounds__(256) k_first_peak(const double* __restrict__ x
   int64_t C = (n + nchunks - 1) / nchunks;
   C = (C + 255) & ~(int64_t)255;
   const double guard = 0.999 * height * m;
-  for (int64_t k = blockIdx.y; k < nchunks; k += gridDim.y) {
+  // a peak candidate is a sample >= guard: nothing before the first block whose maximum reaches it can qualify
+  int64_t k0 = 0;
+  if (va.blk_max) {
+    const double* bm = va.blk_max + (r0 + r) * va.nblk;
+    int64_t skip = n;
+    for (int64_t q = 0; q < va.nblk; ++q)
+      if (bm[q] >= guard) { skip = va.blk_first + q * va.blk_len; break; }
+    k0 = max((int64_t)0, min(skip, n - 1)) / C;
+  }
+  for (int64_t k = k0 + blockIdx.y; k < nchunks; k += gridDim.y) {
     const int64_t lo = k * C, hi = min(n, lo + C);
     if (lo >= hi) return;
     // nothing in this chunk (or any later one) can beat an already published earlier peak
@@ -214,7 +225,7 @@ int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double he
     // 'same' slice puts it ~40 % into the row): every chunk gets its own block and the ones behind a published
     // peak drop out (2 blocks per row: 1004 us, one per chunk: ~200 us).
     static const int peak_g = getenv("IMPB_PEAK_G") ? atoi(getenv("IMPB_PEAK_G")) : 0;
-    const bool near_start = va.hint_max != nullptr;
+    const bool near_start = va.hint_max != nullptr || va.blk_max != nullptr;
     const int64_t want = peak_g > 0 ? peak_g : near_start ? std::max<int64_t>(1, 2048 / std::max<int64_t>(nb, 1)) : chunks;
     const dim3 pgrid((unsigned)nb, (unsigned)std::min<int64_t>(chunks, want));
     k_first_peak<<<pgrid, thr, 0, st>>>(x, va, b0, height, scratch + b0, (int)chunks);
@@ -726,8 +737,12 @@ __global__ void __launch_bounds__(256) k_gather_window(const double* __restrict_
 extern "C" {
 
 static ViewArgs make_view(const int64_t* offsets, const int64_t* lengths, const impb_view* v) {
-  ViewArgs a{offsets, lengths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
+  ViewArgs a{offsets, lengths, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0};
   if (v) {
+    // block maxima describe untouched rows: ignored for shifted / faded views
+    if (v->blk_max && v->nblk > 0 && v->blk_len > 0 && !v->shift && !(v->fade_in_len > 0) && !v->valid_lo && !v->valid_hi) {
+      a.blk_max = v->blk_max; a.nblk = v->nblk; a.blk_len = v->blk_len; a.blk_first = v->blk_first;
+    }
     if (v->hint_max && v->hint_argmax) { a.hint_max = v->hint_max; a.hint_arg = v->hint_argmax; }
     a.shift = v->shift;
     a.lo = v->valid_lo;

@@ -51,6 +51,8 @@ template <typename T> struct DeconvArgs {
   unsigned long long* cand_val;
   int64_t* cand_idx;
   int cand_tiles;
+  unsigned long long* blockmax;  // optional [nrows][nblk]: bits of max |out| per time block (specialised path)
+  int nblk;
 };
 
 __device__ __forceinline__ double load_sample(const void* p, int fmt, int64_t i) {
@@ -132,16 +134,16 @@ template <typename T, int TILE> struct DeconvColOut {
     return a.ws[(size_t)b * a.N + (size_t)e * a.N2 + n2];
   }
   __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v) const {
-    T m0 = 0, m1 = 0;
-    int i0 = 0, i1 = 0;
-    store(b, t, e, c, v, m0, m1, i0, i1);
+    T ax, ay;
+    int j;
+    store_abs(b, t, e, c, v, ax, ay, j);
   }
-  // also folds |value as stored| (and where it was stored) into the caller's running maxima
-  __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v, T& mx_re, T& mx_im, int& ix_re,
-                                        int& ix_im) const {
+  // stores and reports |value as stored| of both rows and the output index; false if the sample lies outside the
+  // requested output window
+  __device__ __forceinline__ bool store_abs(int b, int t, int e, int c, cx_t<T> v, T& ax, T& ay, int& jj) const {
     const int n2 = t * TILE + c;
     const int64_t j = (int64_t)e * a.N2 + n2 - a.out_start;
-    if (n2 >= a.N2 || j < 0 || j >= a.out_len) return;
+    if (n2 >= a.N2 || j < 0 || j >= a.out_len) return false;
     const int64_t ra = a.row0 + 2 * (int64_t)b, rb = ra + 1;
     if (a.out_f64) {
       double* o = reinterpret_cast<double*>(a.out);
@@ -154,8 +156,18 @@ template <typename T, int TILE> struct DeconvColOut {
       o[ra * a.ld_out + j] = (float)v.x;
       if (rb < a.nrows) o[rb * a.ld_out + j] = (float)v.y;
     }
-    if (fabs(v.x) > mx_re) { mx_re = fabs(v.x); ix_re = (int)j; }
-    if (fabs(v.y) > mx_im) { mx_im = fabs(v.y); ix_im = (int)j; }
+    ax = fabs(v.x);
+    ay = fabs(v.y);
+    jj = (int)j;
+    return true;
+  }
+  __device__ __forceinline__ bool tracks_blocks() const { return a.blockmax != nullptr; }
+  __device__ __forceinline__ void publish_block(int b, int p, int which, T m) const {
+    const int64_t r = a.row0 + 2 * (int64_t)b + which;
+    if (r >= a.nrows || !(m > (T)0)) return;
+    unsigned long long* dst = a.blockmax + r * a.nblk + p;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong((double)m);
+    if (bits > __ldcg(dst)) atomicMax(dst, bits);
   }
   __device__ __forceinline__ bool tracks_max() const { return a.absmax != nullptr; }
   __device__ __forceinline__ bool tracks_arg() const { return a.cand_val != nullptr; }
@@ -170,8 +182,10 @@ template <typename T, int TILE> struct DeconvColOut {
   }
   __device__ __forceinline__ void publish_max(int b, T mx_re, T mx_im) const {
     const int64_t ra = a.row0 + 2 * (int64_t)b, rb = ra + 1;
-    atomicMax(a.absmax + ra, (unsigned long long)__double_as_longlong((double)mx_re));
-    if (rb < a.nrows) atomicMax(a.absmax + rb, (unsigned long long)__double_as_longlong((double)mx_im));
+    const unsigned long long br = (unsigned long long)__double_as_longlong((double)mx_re);
+    const unsigned long long bi = (unsigned long long)__double_as_longlong((double)mx_im);
+    if (br > __ldcg(a.absmax + ra)) atomicMax(a.absmax + ra, br);
+    if (rb < a.nrows && bi > __ldcg(a.absmax + rb)) atomicMax(a.absmax + rb, bi);
   }
 };
 
@@ -190,18 +204,17 @@ __global__ void __launch_bounds__(256) k_row_absmax(const O* __restrict__ out, i
 }
 
 // argmax from the per-tile candidates of the specialised final pass: smallest index whose value equals the row max
-__global__ void k_argmax_pick(const unsigned long long* __restrict__ absmax, const unsigned long long* __restrict__ cand_val,
-                              const int64_t* __restrict__ cand_idx, int tiles, int64_t* __restrict__ argmax, int64_t rows) {
-  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+k_argmax_pick(const unsigned long long* __restrict__ absmax, const unsigned long long* __restrict__ cand_val,
+              const int64_t* __restrict__ cand_idx, int tiles, int64_t* __restrict__ argmax, int64_t rows) {
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per row
   if (r >= rows) return;
   const unsigned long long m = absmax[r];
-  int64_t best = -1;
-  for (int t = 0; t < tiles; ++t)
-    if (cand_val[r * tiles + t] == m) {
-      const int64_t i = cand_idx[r * tiles + t];
-      if (best < 0 || i < best) best = i;
-    }
-  argmax[r] = best;
+  unsigned best = 0xffffffffu;
+  for (int t = threadIdx.x & 31; t < tiles; t += 32)
+    if (cand_val[r * tiles + t] == m) best = min(best, (unsigned)cand_idx[r * tiles + t]);
+  best = __reduce_min_sync(0xffffffffu, best);
+  if ((threadIdx.x & 31) == 0) argmax[r] = best == 0xffffffffu ? -1 : (int64_t)best;
 }
 
 // generic-engine plans: argmax by one more read of the rows (absmax is final when this runs)
@@ -534,9 +547,21 @@ int32_t impb_deconv_launches_per_execute(const impb_plan* pl, int64_t batch) {
   return (int32_t)(3 * ((pairs + pl->chunk_pairs - 1) / pl->chunk_pairs));
 }
 
+int32_t impb_deconv_blockmax_info(const impb_plan* pl, int64_t out_offset, int64_t* nblk, int64_t* blk_len,
+                                  int64_t* blk_first) {
+  if (!pl || !nblk || !blk_len || !blk_first) return IMPB_EINVAL;
+  const bool fixed = pl->precision == 64 ? pl->e64.fixed_path() : pl->e32.fixed_path();
+  const Plan2D& p = pl->precision == 64 ? pl->e64.fft.p : pl->e32.fft.p;
+  *nblk = fixed ? 8 : 0;
+  *blk_len = fixed ? (int64_t)(p.N1 / 8) * p.N2 : 0;
+  *blk_first = -(pl->s + out_offset);
+  return IMPB_OK;
+}
+
 int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_offsets, int64_t ld_in, int32_t in_fmt,
                             int64_t len, void* out, int64_t ld_out, int32_t out_f64, int64_t out_offset, int64_t out_len,
-                            double* absmax_out, int64_t* argmax_out, int64_t batch, void* workspace, void* stream) {
+                            double* absmax_out, int64_t* argmax_out, double* blockmax_out, int64_t batch, void* workspace,
+                            void* stream) {
   if (!pl || !rec || !out || !workspace || batch < 0 || len < 0 || len > pl->L || (!in_offsets && ld_in < len) ||
       out_offset < 0 || (argmax_out && !absmax_out) ||
       out_len < 0 || out_offset + out_len > len || ld_out < out_len || in_fmt < 0 || in_fmt > 2) {
@@ -550,12 +575,19 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
   if (absmax_out) IMPB_CUDA(cudaMemsetAsync(absmax_out, 0, sizeof(double) * batch, st));
   // argmax: per-(row, tile) candidates from the specialised final pass, or one extra read for generic plans
   const bool fixed = pl->precision == 64 ? pl->e64.fixed_path() : pl->e32.fixed_path();
-  const int cand_tiles = pl->precision == 64 ? pl->e64.fft.col_tiles() : pl->e32.fft.col_tiles();
+  // one argmax candidate per (row, column tile, warp of the 256-thread CTA)
+  const int cand_tiles = 8 * (pl->precision == 64 ? pl->e64.fft.col_tiles() : pl->e32.fft.col_tiles());
   unsigned long long* cand_val = nullptr;
   int64_t* cand_idx = nullptr;
   if (argmax_out && fixed) {
     IMPB_CUDA(cudaMallocAsync(&cand_val, sizeof(unsigned long long) * batch * cand_tiles, st));
     IMPB_CUDA(cudaMallocAsync(&cand_idx, sizeof(int64_t) * batch * cand_tiles, st));
+  }
+  int nblk = 0;
+  if (blockmax_out) {
+    if (!fixed) { set_error("impb_deconv_execute: this plan has no block maxima (impb_deconv_blockmax_info)"); return IMPB_EUNSUPPORTED; }
+    nblk = 8;  // R0 of the 768-point column pass
+    IMPB_CUDA(cudaMemsetAsync(blockmax_out, 0, sizeof(double) * batch * nblk, st));
   }
   const int64_t pairs = (batch + 1) / 2;
   const int ns = pl->nstreams;
@@ -580,6 +612,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = 1;
       a.absmax = (unsigned long long*)absmax_out;
       a.cand_val = cand_val; a.cand_idx = cand_idx; a.cand_tiles = cand_tiles;
+      a.blockmax = (unsigned long long*)blockmax_out; a.nblk = nblk;
       rc = pl->e64.launch(a, np, st);
     } else {
       DeconvArgs<float> a{};
@@ -590,6 +623,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = out_f64 ? 1 : 0;
       a.absmax = (unsigned long long*)absmax_out;
       a.cand_val = cand_val; a.cand_idx = cand_idx; a.cand_tiles = cand_tiles;
+      a.blockmax = (unsigned long long*)blockmax_out; a.nblk = nblk;
       rc = pl->e32.launch(a, np, st);
     }
     if (rc) return rc;
@@ -602,7 +636,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
   }
   if (argmax_out) {
     if (fixed) {
-      k_argmax_pick<<<(unsigned)((batch + 127) / 128), 128, 0, user>>>((const unsigned long long*)absmax_out, cand_val,
+      k_argmax_pick<<<(unsigned)((batch + 7) / 8), 256, 0, user>>>((const unsigned long long*)absmax_out, cand_val,
                                                                        cand_idx, cand_tiles, argmax_out, batch);
       IMPB_CUDA(cudaGetLastError());
       IMPB_CUDA(cudaFreeAsync(cand_val, user));

@@ -156,7 +156,11 @@ __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, 
       for (int p = 0; p < R; ++p) x[p] = cmul(x[p], m[p]);
     }
 #pragma unroll
-    for (int p = 0; p < R; ++p) st(base + p * STRIDE, c, x[p]);
+    for (int p = 0; p < R; ++p) {
+      // a store functor may ask for the (compile-time, after unrolling) butterfly output number p
+      if constexpr (std::is_invocable_v<ST, int, int, cx_t<T>, int>) st(base + p * STRIDE, c, x[p], p);
+      else st(base + p * STRIDE, c, x[p]);
+    }
   }
 }
 
@@ -254,8 +258,30 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   // running max |re|, |im| of what this thread stores: the per-row max|x| the peak search needs comes for free
   T mx_re = (T)0, mx_im = (T)0;
   int ix_re = 0, ix_im = 0;  // output index of the thread's running maxima (argmax candidates)
+  // Output number p of the last DIT stage owns the contiguous time block [p, p+1) * (S/R0) * N2 of the row: the
+  // maxima per p are the maxima of R0 consecutive blocks of the output ("block maxima", impb_view.blk_max), with
+  // which the first-peak search starts at the first block that can hold a peak instead of at sample 0.
+  // (kept as the integer bit patterns of the non-negative magnitudes: integer max is cheaper than FP64 max)
+  using bits_t = typename std::conditional<sizeof(T) == 8, long long, int>::type;
+  auto to_bits = [](T v) -> bits_t {
+    if constexpr (sizeof(T) == 8) return __double_as_longlong(v); else return __float_as_int(v);
+  };
+  auto from_bits = [](bits_t v) -> T {
+    if constexpr (sizeof(T) == 8) return __longlong_as_double(v); else return __int_as_float(v);
+  };
+  bits_t bm_re[RX::R0], bm_im[RX::R0];
+#pragma unroll
+  for (int p = 0; p < RX::R0; ++p) bm_re[p] = bm_im[p] = 0;
+  const bool blocks = f.tracks_blocks();
   auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
-  auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v, mx_re, mx_im, ix_re, ix_im); };
+  auto gs = [&](int e, int c, cx_t<T> v, int p) {
+    T ax, ay;
+    int j;
+    if (!f.store_abs(b, t, e, c, v, ax, ay, j)) return;
+    if (ax > mx_re) { mx_re = ax; ix_re = j; }
+    if (ay > mx_im) { mx_im = ay; ix_im = j; }
+    if (blocks) { bm_re[p] = max(bm_re[p], to_bits(ax)); bm_im[p] = max(bm_im[p], to_bits(ay)); }
+  };
   auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
   fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false, kPrefetch>(nullptr, gl, ss, NoPost{});
@@ -264,30 +290,39 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, true, false>(tw0, sl, gs, NoPost{});
   if (f.tracks_max()) {
-    __syncthreads();  // the tile is free: reuse it for the block reduction
-    T* red = reinterpret_cast<T*>(smem_raw);
-    int* arg = reinterpret_cast<int*>(red + 2 * (NT / 32) + 2);
-    const T my_re = mx_re, my_im = mx_im;
-    for (int o = 16; o; o >>= 1) {
-      mx_re = fmax(mx_re, __shfl_xor_sync(0xffffffffu, mx_re, o));
-      mx_im = fmax(mx_im, __shfl_xor_sync(0xffffffffu, mx_im, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-      red[2 * (threadIdx.x >> 5)] = mx_re;
-      red[2 * (threadIdx.x >> 5) + 1] = mx_im;
-    }
-    if (threadIdx.x == 0) { arg[0] = 0x7fffffff; arg[1] = 0x7fffffff; }
-    __syncthreads();
-    for (int w = 0; w < NT / 32; ++w) {
-      mx_re = fmax(mx_re, red[2 * w]);
-      mx_im = fmax(mx_im, red[2 * w + 1]);
-    }
-    if (threadIdx.x == 0) f.publish_max(b, mx_re, mx_im);
+    // Everything below is per warp (integer REDUX on the bit patterns of the non-negative magnitudes): no shared
+    // memory and no barrier at the end of the CTA.  Each warp publishes its maxima (atomicMax only if it beats the
+    // value already there) and, for argmax, one candidate per (row, tile, warp).
+    auto warp_max = [](bits_t v) -> bits_t {
+      if constexpr (sizeof(T) == 8) {
+        const unsigned hi = (unsigned)((unsigned long long)v >> 32);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? (unsigned)(unsigned long long)v : 0u);
+        return (long long)(((unsigned long long)mh << 32) | ml);
+      } else {
+        return (int)__reduce_max_sync(0xffffffffu, (unsigned)v);
+      }
+    };
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bits_t my_re = to_bits(mx_re), my_im = to_bits(mx_im);
+    const bits_t w_re = warp_max(my_re), w_im = warp_max(my_im);
+    if (lane == 0) f.publish_max(b, from_bits(w_re), from_bits(w_im));
     if (f.tracks_arg()) {
-      if (my_re == mx_re) atomicMin(arg, ix_re);
-      if (my_im == mx_im) atomicMin(arg + 1, ix_im);
-      __syncthreads();
-      if (threadIdx.x == 0) f.publish_arg(b, t, mx_re, arg[0], mx_im, arg[1]);
+      const unsigned a_re = __reduce_min_sync(0xffffffffu, my_re == w_re ? (unsigned)ix_re : 0x7fffffffu);
+      const unsigned a_im = __reduce_min_sync(0xffffffffu, my_im == w_im ? (unsigned)ix_im : 0x7fffffffu);
+      if (lane == 0) f.publish_arg(b, t * (NT / 32) + warp, from_bits(w_re), (int)a_re, from_bits(w_im), (int)a_im);
+    }
+    if (blocks) {
+      // warp-level integer reductions (REDUX) of the 2 * R0 bit patterns; lane q of every warp then publishes value
+      // q if it beats what is already there: no shared memory, no barrier, and after the first few CTAs of a row
+      // hardly any atomics
+      bits_t mine = 0;
+#pragma unroll
+      for (int q = 0; q < 2 * RX::R0; ++q) {
+        const bits_t r = warp_max((q & 1) ? bm_im[q >> 1] : bm_re[q >> 1]);
+        if (lane == q) mine = r;
+      }
+      if (lane < 2 * RX::R0 && mine > 0) f.publish_block(b, lane >> 1, lane & 1, from_bits(mine));
     }
   }
 }

@@ -189,7 +189,10 @@ class BatchDispatcher:
             plan = est.plan(L, precision)
             e_max = torch.empty(B, dtype=torch.float64, device=dev)
             e_arg = torch.empty(B, dtype=torch.int64, device=dev)
-            E = plan.execute(recordings.reshape(-1), length=L, row_offsets=row_offs, absmax=e_max, argmax=e_arg)
+            nblk, blk_len, blk_first = plan.blockmax_info()
+            e_blk = torch.empty((B, nblk), dtype=torch.float64, device=dev) if nblk else None
+            E = plan.execute(recordings.reshape(-1), length=L, row_offsets=row_offs, absmax=e_max, argmax=e_arg,
+                             blockmax=e_blk)
             if E.dtype != torch.float64:
                 E = E.to(torch.float64)
             launches += plan.launches(B) + 1  # + argmax pick
@@ -198,7 +201,8 @@ class BatchDispatcher:
             rows = torch.arange(B, device=dev, dtype=torch.int64)
             full = torch.full((B,), L, device=dev, dtype=torch.int64)
             # 2. first peaks (K2) and the pairwise head crop (ref core/hrir.py:573-606), integer ops on device
-            peaks = ops.peak_index(flatE, rows * L, full, max_len=L, known_max=e_max)
+            peaks = ops.peak_index(flatE, rows * L, full, max_len=L, known_max=e_max,
+                                   view=None if e_blk is None else dict(blocks=(e_blk, blk_len, blk_first)))
             launches += 3
             mark('first peaks')
             pk = peaks.view(S, n)

@@ -67,12 +67,21 @@ class DeconvPlan:
     def launches(self, batch: int) -> int:
         return int(_lib.lib().impb_deconv_launches_per_execute(self.handle, int(batch)))
 
+    def blockmax_info(self, out_offset=0):
+        """(nblk, blk_len, blk_first) of the block maxima ``execute`` can emit (nblk = 0: not available)."""
+        import ctypes as C
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().impb_deconv_blockmax_info(self.handle, int(out_offset), C.byref(a), C.byref(b), C.byref(c)),
+                   "impb_deconv_blockmax_info")
+        return int(a.value), int(b.value), int(c.value)
+
     def execute(self, rec, out=None, length=None, out_offset=0, out_len=None, row_offsets=None, absmax=None,
-                argmax=None):
+                argmax=None, blockmax=None):
         """rec: CUDA tensor [batch, ld] (float64 / float32 / int32 PCM), or any CUDA tensor plus
         ``row_offsets`` (int64 CUDA tensor: element offset of every row inside ``rec``) and ``length``.
         ``absmax`` (optional float64 CUDA tensor [batch]) receives max |out[r, :]| at no extra cost; ``argmax``
-        (optional int64 CUDA tensor [batch], needs ``absmax``) an index where it is attained.
+        (optional int64 CUDA tensor [batch], needs ``absmax``) an index where it is attained; ``blockmax`` (optional
+        float64 CUDA tensor [batch, nblk], see ``blockmax_info``) the maxima per time block.
         Returns CUDA tensor [batch, out_len]."""
         import torch
         if row_offsets is None and rec.dim() == 1:
@@ -99,8 +108,8 @@ class DeconvPlan:
                 self.handle, rec.data_ptr(), None if row_offsets is None else row_offsets.data_ptr(),
                 (rec.stride(0) if batch > 1 else rec.shape[-1]) if row_offsets is None else 0, fmt, length,
                 out.data_ptr(), out.stride(0) if batch > 1 else out.shape[1], out_f64, int(out_offset), out_len,
-                None if absmax is None else absmax.data_ptr(), None if argmax is None else argmax.data_ptr(), batch,
-                ws.data_ptr(),
+                None if absmax is None else absmax.data_ptr(), None if argmax is None else argmax.data_ptr(),
+                None if blockmax is None else blockmax.data_ptr(), batch, ws.data_ptr(),
                 _lib.current_stream_ptr(rec.device)), "impb_deconv_execute")
         return out
 

@@ -63,10 +63,11 @@ def _dev_window(win, device):
     return t
 
 
-def make_view(device, shift=None, valid_lo=None, valid_hi=None, fade_in=None, hint_max=None, hint_argmax=None):
+def make_view(device, shift=None, valid_lo=None, valid_hi=None, fade_in=None, hint_max=None, hint_argmax=None,
+              blocks=None):
     """(ctypes impb_view or None, keep-alive tensors).  See include/impb.h.  ``hint_max`` / ``hint_argmax``: float64 /
     int64 CUDA tensors (max |x| of the untouched samples and where, relative to the row offset)."""
-    if shift is None and valid_lo is None and valid_hi is None and fade_in is None and hint_max is None:
+    if shift is None and valid_lo is None and valid_hi is None and fade_in is None and hint_max is None and blocks is None:
         return None, ()
     sh = None if shift is None else as_index_tensor(shift, device)
     lo = None if valid_lo is None else as_index_tensor(valid_lo, device)
@@ -80,7 +81,12 @@ def make_view(device, shift=None, valid_lo=None, valid_hi=None, fade_in=None, hi
                   None if hi is None else hi.data_ptr(), None if fi is None else fi.data_ptr(),
                   0 if fi is None else fi.numel(), None if hm is None else hm.data_ptr(),
                   None if ha is None else ha.data_ptr())
-    return v, (sh, lo, hi, fi, hm, ha)
+    bm = None
+    if blocks is not None:  # (block maxima [rows, nblk] CUDA float64, blk_len, blk_first) of untouched rows
+        bm, blk_len, blk_first = blocks
+        bm = bm.contiguous()
+        v.blk_max, v.nblk, v.blk_len, v.blk_first = bm.data_ptr(), bm.shape[1], int(blk_len), int(blk_first)
+    return v, (sh, lo, hi, fi, hm, ha, bm)
 
 
 def peak_index(x, offsets, lengths, height=0.12589, max_len=None, view=None, known_max=None):

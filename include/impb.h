@@ -60,6 +60,11 @@ typedef struct impb_view {
   int64_t fade_in_len;
   const double* hint_max;
   const int64_t* hint_argmax;
+  /* block maxima of the untouched samples (rows without shift / fade only): blk_max[r * nblk + p] = max |x| over
+   * x[offset + blk_first + p * blk_len : ... + blk_len) (clipped to the row), as written by impb_deconv_execute's
+   * blockmax_out.  impb_peak_index then starts its search at the first block that can contain a peak. */
+  const double* blk_max;
+  int64_t nblk, blk_len, blk_first;
 } impb_view;
 
 IMPB_API uint32_t impb_version(void);
@@ -82,7 +87,9 @@ IMPB_API const char* impb_last_error(void); /* thread-local */
  * absmax_out (nullable, device double[batch]) receives max |out[r, :]|, tracked by the final column pass for
  * free; impb_peak_index accepts it as known_max and then skips its own max pass.  argmax_out (nullable, device
  * int64[batch], needs absmax_out) receives one index j with |out[r, j]| == absmax_out[r] (the smallest one found
- * among the per-tile candidates), for impb_view.hint_argmax.
+ * among the per-tile candidates), for impb_view.hint_argmax.  blockmax_out (nullable, device double[batch, nblk]):
+ * max |out[r, :]| per contiguous time block, geometry from impb_deconv_blockmax_info (nblk = 0: the plan cannot
+ * provide them, pass NULL), for impb_view.blk_max.
  */
 IMPB_API int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, int64_t M, int64_t L,
                                 int32_t precision, impb_plan** out);
@@ -92,7 +99,10 @@ IMPB_API int32_t impb_deconv_plan_info(const impb_plan* plan, int64_t* nfft, int
 IMPB_API int32_t impb_deconv_execute(impb_plan* plan, const void* rec, const int64_t* in_offsets, int64_t ld_in,
                             int32_t in_fmt, int64_t len, void* out, int64_t ld_out, int32_t out_f64,
                             int64_t out_offset, int64_t out_len, double* absmax_out, int64_t* argmax_out,
-                            int64_t batch, void* workspace, void* stream);
+                            double* blockmax_out, int64_t batch, void* workspace, void* stream);
+/* block p of blockmax_out covers output samples [blk_first + p * blk_len, blk_first + (p + 1) * blk_len) */
+IMPB_API int32_t impb_deconv_blockmax_info(const impb_plan* plan, int64_t out_offset, int64_t* nblk, int64_t* blk_len,
+                                  int64_t* blk_first);
 /* name and launch count of the kernels one execute() issues (bench.py gpu_launches accounting) */
 IMPB_API int32_t impb_deconv_launches_per_execute(const impb_plan* plan, int64_t batch);
 

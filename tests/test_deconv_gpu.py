@@ -174,6 +174,28 @@ def test_absmax_and_argmax_outputs(torch_cuda):
         for r in range(batch):
             if ref[r] > 0:
                 assert 0 <= a[r] < L and abs(o[r, a[r]]) == float(ref[r]), r
+        # block maxima (specialised plans only) and the peak search that starts from them
+        nblk, blk_len, blk_first = plan.blockmax_info()
+        if nblk:
+            from impulcifer_pip313_b200 import ops
+            bm = T.empty((batch, nblk), dtype=T.float64, device='cuda')
+            out_b = plan.execute(x, absmax=amax, argmax=arg, blockmax=bm)
+            assert T.equal(out_b, out)
+            ob = out.abs().cpu().numpy()
+            want = np.zeros((batch, nblk))
+            for q in range(nblk):
+                lo, hi = max(blk_first + q * blk_len, 0), min(blk_first + (q + 1) * blk_len, L)
+                if hi > lo:
+                    want[:, q] = ob[:, lo:hi].max(axis=1)
+            assert np.array_equal(bm.cpu().numpy(), want)
+            offs = T.arange(batch, device='cuda', dtype=T.int64) * L
+            lens = T.full((batch,), L, device='cuda', dtype=T.int64)
+            p0 = ops.peak_index(out.reshape(-1), offs, lens, max_len=L, known_max=amax)
+            p1 = ops.peak_index(out.reshape(-1), offs, lens, max_len=L, known_max=amax,
+                                view=dict(blocks=(bm, blk_len, blk_first)))
+            assert T.equal(p0, p1)
+        else:
+            assert blk_len == 0
         # a cropped output window shifts the index origin
         out2 = plan.execute(x, out_offset=1000, out_len=50000, absmax=amax, argmax=arg)
         assert T.equal(amax, out2.abs().max(dim=1).values)

@@ -21,13 +21,21 @@ if prec == 32:
 plan = est.plan(L, precision=prec)
 print('plan', plan.nfft, plan.n1, plan.n2, 'launches', plan.launches(batch), 'ws MB', plan.workspace(batch).numel() / 2**20)
 out = torch.empty(batch, L, dtype=torch.float64 if prec == 64 else torch.float32, device='cuda')
+track = sys.argv[5] if len(sys.argv) > 5 else ''
+kw = {}
+if 'a' in track:
+    kw['absmax'] = torch.empty(batch, dtype=torch.float64, device='cuda')
+if 'g' in track:
+    kw['argmax'] = torch.empty(batch, dtype=torch.int64, device='cuda')
+if 'b' in track and plan.blockmax_info()[0]:
+    kw['blockmax'] = torch.empty((batch, plan.blockmax_info()[0]), dtype=torch.float64, device='cuda')
 for _ in range(3):
-    plan.execute(x, out=out)
+    plan.execute(x, out=out, **kw)
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
 ev[0].record()
 for i in range(iters):
-    plan.execute(x, out=out)
+    plan.execute(x, out=out, **kw)
     ev[i + 1].record()
 torch.cuda.synchronize()
 ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]
