@@ -41,6 +41,8 @@ SIGNATURES = {
     "impb_xcorr_lag": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "impb_gather_window": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp,
                                    c_i64, c_i64, c_vp]),
+    "impb_gather_rows": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl,
+                                 c_vp, c_i64, c_vp]),
     "impb_fft_create": (c_i32, [c_vp, c_i64, c_i32, C.POINTER(c_vp)]),
     "impb_fft_destroy": (None, [c_vp]),
     "impb_fft_workspace_bytes": (c_i64, [c_vp, c_i64]),

@@ -714,8 +714,13 @@ __global__ void __launch_bounds__(256) k_gather_window(const double* __restrict_
                                                        const int64_t* __restrict__ valid_hi, int64_t out_len,
                                                        const double* __restrict__ fade_in, int64_t fade_in_len,
                                                        const double* __restrict__ fade_out, int64_t fade_out_len, double gain,
-                                                       int apply_gain, double* __restrict__ dst, int64_t ld_dst) {
+                                                       int apply_gain, double* __restrict__ dst, int64_t ld_dst,
+                                                       const int64_t* __restrict__ out_lens,
+                                                       const int64_t* __restrict__ dst_offsets) {
   const int r = blockIdx.y;
+  if (out_lens) out_len = out_lens[r];  // ragged form: per-row length and destination offset
+  if (out_len < fade_out_len) fade_out_len = 0;
+  if (dst_offsets) { dst += dst_offsets[r]; ld_dst = 0; }
   const int64_t s0 = src_start[r], sh = shift ? shift[r] : 0;
   const int64_t lo = valid_lo ? valid_lo[r] : 0, hi = valid_hi ? valid_hi[r] : out_len;
   const int64_t fo0 = out_len - fade_out_len;
@@ -847,7 +852,32 @@ int32_t impb_gather_window(impb_ctx* ctx, const double* src, const int64_t* src_
     k_gather_window<<<dim3((unsigned)bx, nb), thr, 0, (cudaStream_t)stream>>>(
         src, src_start + b0, shift ? shift + b0 : nullptr, valid_lo ? valid_lo + b0 : nullptr,
         valid_hi ? valid_hi + b0 : nullptr, out_len, fade_in, fade_in_len, fade_out, fade_out_len, gain,
-        gain != 1.0 ? 1 : 0, dst + (size_t)b0 * ld_dst, ld_dst);
+        gain != 1.0 ? 1 : 0, dst + (size_t)b0 * ld_dst, ld_dst, nullptr, nullptr);
+  }
+  IMPB_CUDA(cudaGetLastError());
+  return IMPB_OK;
+}
+
+int32_t impb_gather_rows(impb_ctx* ctx, const double* src, const int64_t* src_start, const int64_t* shift,
+                         const int64_t* valid_lo, const int64_t* valid_hi, const int64_t* out_lens,
+                         const int64_t* dst_offsets, int64_t max_out_len, const double* fade_in, int64_t fade_in_len,
+                         const double* fade_out, int64_t fade_out_len, double gain, double* dst, int64_t batch,
+                         void* stream) {
+  if (!ctx || !src || !src_start || !out_lens || !dst_offsets || !dst || batch < 0 || max_out_len < 0 || fade_in_len < 0 ||
+      fade_out_len < 0 || (fade_in_len > 0 && !fade_in) || (fade_out_len > 0 && !fade_out)) {
+    set_error("impb_gather_rows: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0 || max_out_len == 0) return IMPB_OK;
+  DeviceGuard g(ctx->device);
+  const int thr = 256;
+  int64_t bx = std::max<int64_t>(1, std::min<int64_t>((max_out_len + thr * 4 - 1) / (thr * 4), 1024));
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int nb = (int)std::min<int64_t>(65535, batch - b0);
+    k_gather_window<<<dim3((unsigned)bx, nb), thr, 0, (cudaStream_t)stream>>>(
+        src, src_start + b0, shift ? shift + b0 : nullptr, valid_lo ? valid_lo + b0 : nullptr,
+        valid_hi ? valid_hi + b0 : nullptr, 0, fade_in, fade_in_len, fade_out, fade_out_len, gain, gain != 1.0 ? 1 : 0,
+        dst, 0, out_lens + b0, dst_offsets + b0);
   }
   IMPB_CUDA(cudaGetLastError());
   return IMPB_OK;

@@ -17,6 +17,7 @@ needs ONE host synchronisation: reading the knee indices that fix each set's out
 from __future__ import annotations
 
 import threading
+import time
 import warnings
 from dataclasses import dataclass, field
 
@@ -54,16 +55,34 @@ def fft_convolve_full(x, fir, out_len=None):
     return plan.execute(padded, out_len=out_len)
 
 
-@dataclass
 class SetResult:
-    """Cropped responses of one recording set, in the reference's estimation order."""
-    names: list            # ["FL-left", "FL-right", ...]
-    data: object           # CUDA tensor [n_irs, tail_ind]
-    tail_ind: int
-    peaks: np.ndarray      # raw-estimate peak index per IR
-    crop: np.ndarray       # head crop index per IR
-    knees: np.ndarray      # Lundeby knee index per IR (after alignment)
-    warnings: list = field(default_factory=list)
+    """Cropped responses of one recording set, in the reference's estimation order.
+
+    ``data`` is the CUDA tensor ``[n_irs, tail_ind]``.  The dispatcher hands over the set's slice of one flat output
+    buffer and the 2-D view is made on first access (64 sets x a few microseconds of tensor bookkeeping stay off the
+    critical path between two steps)."""
+    __slots__ = ("names", "tail_ind", "peaks", "crop", "knees", "warnings", "_data", "_flat")
+
+    def __init__(self, names, data, tail_ind, peaks, crop, knees, warnings=None, flat=None):
+        self.names = names            # ["FL-left", "FL-right", ...]
+        self.tail_ind = tail_ind
+        self.peaks = peaks            # raw-estimate peak index per IR
+        self.crop = crop              # head crop index per IR
+        self.knees = knees            # Lundeby knee index per IR (after alignment)
+        self.warnings = [] if warnings is None else warnings
+        self._data = data
+        self._flat = flat             # 1-D slice [n_irs * tail_ind] of the dispatcher's output buffer
+
+    @property
+    def data(self):
+        if self._data is None:
+            self._data = self._flat.view(len(self.names), self.tail_ind)
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+        self._flat = None
 
     def as_dict(self):
         out = {}
@@ -179,7 +198,7 @@ class BatchDispatcher:
             if marks is not None:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
-                marks.append((name, ev))
+                marks.append((name, ev, time.perf_counter()))
 
         with torch.cuda.device(dev):
             mark('start')
@@ -260,31 +279,39 @@ class BatchDispatcher:
             _, knee, _, _ = ops.lundeby(flatE, off1, n1, fs, max_len=L, view=view)
             launches += 7  # peak_index (init, max, first peak, final) + window max + block sums + Lundeby
             mark('Lundeby')
-            host = torch.stack([knee, n1, peaks, crop]).cpu().numpy()
-            knees_h, n1_h, peaks_h, crop_h = (host[i].reshape(S, n) for i in range(4))
-            if head > 0 and n1_h.min() < head:
-                raise ValueError("an impulse response is shorter than the fade-in; use the HRIR class for such files")
+            # everything that does not depend on the results is prepared while the device is still busy
             seconds_per_octave = len(est) / est.fs / est.n_octaves
             fade_out = 2 * int(fs * seconds_per_octave * (1 / 24))
             window_out = hann(fade_out)[fade_out // 2:]
+            ops._dev_window(window_out, dev)
+            row_in_set = np.arange(n)[None, :]
+            host = torch.stack([knee, n1, peaks, crop]).cpu().numpy()
+            mark('host sync')
+            knees_h, n1_h, peaks_h, crop_h = (host[i].reshape(S, n) for i in range(4))
+            if head > 0 and n1_h.min() < head:
+                raise ValueError("an impulse response is shorter than the fade-in; use the HRIR class for such files")
             tails = np.minimum(n1_h.min(axis=1), next_fast_len(knees_h.max(axis=1))).tolist()
-            results = [None] * S
+            if min(tails) < len(window_out):
+                raise ValueError("negative dimensions are not allowed")
+            # one ragged gather for all sets: set s owns n rows of tails[s] samples in a flat buffer
+            tails_np = np.asarray(tails, dtype=np.int64)
+            set_off = np.concatenate([[0], np.cumsum(tails_np * n)])
+            geom = np.stack([np.repeat(tails_np, n),
+                             (set_off[:-1, None] + row_in_set * tails_np[:, None]).reshape(-1)])
+            geom_d = torch.from_numpy(geom).to(dev, non_blocking=True)
+            flat = ops.gather_rows(flatE, off1, geom_d[0], geom_d[1], int(set_off[-1]), int(tails_np.max()), shift=total,
+                                   valid_lo=lo, valid_hi=hi, fade_in=window_in, fade_out=window_out)
+            launches += 1
+            # host-only bookkeeping after the last launch: it overlaps the gather
             side_msgs = self._side_warnings(lay, peaks_h)
-            for tail in sorted(set(tails)):
-                if tail < len(window_out):
-                    raise ValueError("negative dimensions are not allowed")
-                sets = [s for s in range(S) if tails[s] == tail]
-                sel = (torch.as_tensor(sets, device=dev, dtype=torch.int64)[:, None] * n +
-                       torch.arange(n, device=dev, dtype=torch.int64)[None, :]).reshape(-1)
-                out = ops.gather_window(flatE, off1[sel], tail, shift=total[sel], valid_lo=lo[sel], valid_hi=hi[sel],
-                                        fade_in=window_in, fade_out=window_out).view(len(sets), n, tail)
-                launches += 1
-                for k, s in enumerate(sets):
-                    results[s] = SetResult(lay['names'], out[k], tail, peaks_h[s], crop_h[s], knees_h[s], side_msgs[s])
+            pieces = flat.split((tails_np * n).tolist())
+            results = [SetResult(lay['names'], None, tails[s], peaks_h[s], crop_h[s], knees_h[s], side_msgs[s], pieces[s])
+                       for s in range(S)]
             mark('tail gather')
         if marks is not None:
             torch.cuda.synchronize(dev)
             self.phase_ms = [(b[0], a[1].elapsed_time(b[1])) for a, b in zip(marks[:-1], marks[1:])]
+            self.phase_host_ms = [(b[0], (b[2] - a[2]) * 1e3) for a, b in zip(marks[:-1], marks[1:])]
         self.launches = launches
         return results
 

@@ -252,6 +252,32 @@ def gather_window(src, src_start, out_len, shift=None, valid_lo=None, valid_hi=N
     return out
 
 
+def gather_rows(src, src_start, out_lens, dst_offsets, total, max_out_len, shift=None, valid_lo=None, valid_hi=None,
+                fade_in=None, fade_out=None, gain=1.0):
+    """Ragged ``gather_window``: row r -> ``dst[dst_offsets[r] : dst_offsets[r] + out_lens[r]]`` of one flat CUDA
+    tensor of ``total`` samples (returned).  All index arguments are CUDA int64 tensors (or array-likes)."""
+    torch = _torch()
+    src = src.contiguous()
+    dev = src.device
+    src_start = as_index_tensor(src_start, dev)
+    out_lens, dst_offsets = as_index_tensor(out_lens, dev), as_index_tensor(dst_offsets, dev)
+    batch = src_start.numel()
+    shift_t = None if shift is None else as_index_tensor(shift, dev)
+    lo_t = None if valid_lo is None else as_index_tensor(valid_lo, dev)
+    hi_t = None if valid_hi is None else as_index_tensor(valid_hi, dev)
+    fi, fo = _dev_window(fade_in, dev), _dev_window(fade_out, dev)
+    out = torch.empty(int(total), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_gather_rows(
+            _lib.context(_dev(src)).handle, src.data_ptr(), _i64(src_start),
+            None if shift_t is None else _i64(shift_t), None if lo_t is None else _i64(lo_t),
+            None if hi_t is None else _i64(hi_t), _i64(out_lens), _i64(dst_offsets), int(max_out_len),
+            None if fi is None else fi.data_ptr(), 0 if fi is None else fi.numel(),
+            None if fo is None else fo.data_ptr(), 0 if fo is None else fo.numel(), float(gain), out.data_ptr(), batch,
+            _stream(src)), "impb_gather_rows")
+    return out
+
+
 # ---- K8 -------------------------------------------------------------------------------------------
 class FftPlan:
     """Exact-length transform plan used by ``magnitude_db``."""

@@ -178,6 +178,16 @@ IMPB_API int32_t impb_gather_window(impb_ctx* ctx, const double* src, const int6
                            int64_t fade_out_len, double gain, double* dst, int64_t ld_dst, int64_t batch,
                            void* stream);
 
+/* Ragged form of impb_gather_window: row r has its own length out_lens[r] (fade_out laid over ITS last fade_out_len
+ * samples; a row shorter than the fade gets none, the caller rejects such rows as the reference does) and is written
+ * at dst + dst_offsets[r]; max_out_len sizes the grid.  One launch for recording sets with different tail lengths
+ * (HRIR.crop_tails per set, core/hrir.py:614-653). */
+IMPB_API int32_t impb_gather_rows(impb_ctx* ctx, const double* src, const int64_t* src_start, const int64_t* shift,
+                         const int64_t* valid_lo, const int64_t* valid_hi, const int64_t* out_lens,
+                         const int64_t* dst_offsets, int64_t max_out_len, const double* fade_in, int64_t fade_in_len,
+                         const double* fade_out, int64_t fade_out_len, double gain, double* dst, int64_t batch,
+                         void* stream);
+
 /* ---- generic batched complex FFT plan (used by K8 / K12 / K13 and the host-side shim) -------------- */
 IMPB_API int32_t impb_fft_create(impb_ctx* ctx, int64_t n, int32_t precision, impb_fft** out);
 IMPB_API void impb_fft_destroy(impb_fft* fft);

@@ -25,13 +25,16 @@ for _ in range(5):
 torch.cuda.synchronize()
 print('wall per step ms', (time.perf_counter() - t0) / 5 * 1e3)
 disp.phase_timing = True
-acc = {}
+acc, hacc = {}, {}
 for _ in range(5):
     disp.process(batch)
     for name, ms in disp.phase_ms:
         acc[name] = acc.get(name, 0.0) + ms / 5
+    for name, ms in disp.phase_host_ms:
+        hacc[name] = hacc.get(name, 0.0) + ms / 5
 disp.phase_timing = False
 print('device time per phase (ms):', {k: round(v, 3) for k, v in acc.items()}, 'sum', round(sum(acc.values()), 3))
+print('host time per phase (ms):', {k: round(v, 3) for k, v in hacc.items()}, 'sum', round(sum(hacc.values()), 3))
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(5):
