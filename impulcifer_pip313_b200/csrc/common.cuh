@@ -45,6 +45,8 @@ struct DeviceGuard {
 bool make_subplan(int S, int tile, int threads, SubPlan* sp);
 // radices of the compile-time specialised kernel for length S, if one exists
 bool fixed_radices(int S, int* r);
+// ... and whether those kernels exist for full-width (true) or half-width (false) tiles
+bool fixed_tile_ok(int S, bool full_tile);
 // per-stage twiddle table of the specialised kernels (column-pass or transposed row-pass layout)
 std::vector<double> stage_table(const SubPlan& sp, int s, bool transposed);
 // the same with every power p = 1..R-1 stored (exact twiddles for the frequency-response transforms)

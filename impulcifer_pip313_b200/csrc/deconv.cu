@@ -273,15 +273,22 @@ template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
   return IMPB_OK;
 }
 
-#define IMPB_FX_CASE(KERNEL, S_, R0_, R1_, R2_)                                                 \
+// HALF_: the length is served with half-width tiles (TileOf<T>/2 columns: 192 kHz plans, whose sub-FFTs do not fit
+// shared memory at full width); a kernel is only instantiated for the tile width its length is planned with
+#define IMPB_FX_CASE(KERNEL, S_, R0_, R1_, R2_, HALF_)                                          \
   case S_: {                                                                                    \
-    auto k = KERNEL<T, TILE, 256, Radix3<R0_, R1_, R2_>, F>;                                     \
-    const size_t smem = fx_tile_elems<S_, TILE>() * sizeof(cx_t<T>);                             \
-    int rc = fx_prepare(k, smem, device);                                                        \
-    if (rc) return rc;                                                                           \
-    k<<<grid, 256, smem, st>>>(tw0, tw1, f);                                                     \
-    IMPB_CUDA(cudaGetLastError());                                                               \
-    return IMPB_OK;                                                                              \
+    if constexpr (TILE == (HALF_ ? TileOf<T>::value / 2 : TileOf<T>::value)) {                   \
+      auto k = KERNEL<T, TILE, 256, Radix3<R0_, R1_, R2_>, F>;                                   \
+      const size_t smem = fx_tile_elems<S_, TILE>() * sizeof(cx_t<T>);                           \
+      int rc = fx_prepare(k, smem, device);                                                      \
+      if (rc) return rc;                                                                         \
+      k<<<grid, 256, smem, st>>>(tw0, tw1, f);                                                   \
+      IMPB_CUDA(cudaGetLastError());                                                             \
+      return IMPB_OK;                                                                            \
+    } else {                                                                                     \
+      set_error("specialised kernel for S=%d is built for another tile width", S);              \
+      return IMPB_EUNSUPPORTED;                                                                  \
+    }                                                                                            \
   }
 
 #define IMPB_FX_DISPATCH(NAME, KERNEL)                                                                        \
@@ -289,7 +296,9 @@ template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
   static int NAME(int S, dim3 grid, cudaStream_t st, int device, const cx_t<T>* tw0, const cx_t<T>* tw1,     \
                   const F& f) {                                                                              \
     switch (S) {                                                                                             \
-      IMPB_FX_CASE(KERNEL, 768, 8, 12, 8)                                                                    \
+      IMPB_FX_CASE(KERNEL, 768, 8, 12, 8, false)                                                             \
+      IMPB_FX_CASE(KERNEL, 1536, 12, 8, 16, true)                                                            \
+      IMPB_FX_CASE(KERNEL, 1600, 16, 10, 10, true)                                                           \
       default: set_error("no specialised kernel for S=%d", S); return IMPB_EUNSUPPORTED;                    \
     }                                                                                                        \
   }
@@ -306,10 +315,11 @@ template <typename T> struct DeconvEngine {
 
   // lengths with an instantiated K1 kernel triple (IMPB_FX_DISPATCH below); other specialised lengths of the menu
   // in plan.cu:fixed_radices only serve the frequency-response transforms
-  static bool k1_length(int S) { return S == 768; }
   bool fixed_path() const {
-    return fft.p.tile == FULL && fft.col_fixed && fft.row_fixed && k1_length(fft.p.N1) && k1_length(fft.p.N2) &&
-           getenv("IMPB_NO_FIXED") == nullptr;
+    const Plan2D& p = fft.p;
+    const bool full = p.tile == FULL && p.N1 == 768 && p.N2 == 768;          // 44.1 / 48 kHz sweeps
+    const bool half = p.tile == FULL / 2 && p.N1 == 1536 && p.N2 == 1600;    // 192 kHz sweeps
+    return fft.col_fixed && fft.row_fixed && (full || half) && getenv("IMPB_NO_FIXED") == nullptr;
   }
 
   int launch(const DeconvArgs<T>& a, int pairs, cudaStream_t st) const {
@@ -319,18 +329,13 @@ template <typename T> struct DeconvEngine {
   template <int TILE> int launch_t(const DeconvArgs<T>& a, int pairs, cudaStream_t st) const {
     int rc;
     static const bool no_fixed = getenv("IMPB_NO_FIXED") != nullptr;
-    if (TILE == FULL && fixed_path() && !no_fixed) {
+    if (TILE == fft.p.tile && fixed_path() && !no_fixed) {
       const Plan2D& p = fft.p;
       static const bool no_async = getenv("IMPB_NO_ASYNC") != nullptr;
-      if constexpr (TILE == FULL) {
-        // the staged copy moves raw samples: the input must already be in the tile's arithmetic type
-        if (a.in_fmt == (sizeof(T) == 8 ? IMPB_FMT_F64 : IMPB_FMT_F32) && !no_async) {
-          rc = fx_fwd_async<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
-                                     DeconvColIn<T, TILE, true>{a});
-        } else {
-          rc = fx_fwd<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
-                               DeconvColIn<T, TILE, true>{a});
-        }
+      // the staged copy moves raw samples: the input must already be in the tile's arithmetic type
+      if (a.in_fmt == (sizeof(T) == 8 ? IMPB_FMT_F64 : IMPB_FMT_F32) && !no_async) {
+        rc = fx_fwd_async<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
+                                   DeconvColIn<T, TILE, true>{a});
       } else {
         rc = fx_fwd<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
                              DeconvColIn<T, TILE, true>{a});
@@ -552,8 +557,9 @@ int32_t impb_deconv_blockmax_info(const impb_plan* pl, int64_t out_offset, int64
   if (!pl || !nblk || !blk_len || !blk_first) return IMPB_EINVAL;
   const bool fixed = pl->precision == 64 ? pl->e64.fixed_path() : pl->e32.fixed_path();
   const Plan2D& p = pl->precision == 64 ? pl->e64.fft.p : pl->e32.fft.p;
-  *nblk = fixed ? 8 : 0;
-  *blk_len = fixed ? (int64_t)(p.N1 / 8) * p.N2 : 0;
+  const int r0 = p.col.radix[0];  // outputs of the last DIT stage of the column pass = time blocks of the row
+  *nblk = fixed ? r0 : 0;
+  *blk_len = fixed ? (int64_t)(p.N1 / r0) * p.N2 : 0;
   *blk_first = -(pl->s + out_offset);
   return IMPB_OK;
 }
@@ -586,7 +592,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
   int nblk = 0;
   if (blockmax_out) {
     if (!fixed) { set_error("impb_deconv_execute: this plan has no block maxima (impb_deconv_blockmax_info)"); return IMPB_EUNSUPPORTED; }
-    nblk = 8;  // R0 of the 768-point column pass
+    nblk = (pl->precision == 64 ? pl->e64.fft.p : pl->e32.fft.p).col.radix[0];  // R0 of the column pass
     IMPB_CUDA(cudaMemsetAsync(blockmax_out, 0, sizeof(double) * batch * nblk, st));
   }
   const int64_t pairs = (batch + 1) / 2;

@@ -54,7 +54,7 @@ template <typename T> struct Fft2D {
     for (int which = 0; which < 2; ++which) {
       const SubPlan& sp = which ? p.row : p.col;
       int fr[3];
-      const bool fixed = fixed_radices(sp.S, fr) && sp.nst == 3;
+      const bool fixed = fixed_radices(sp.S, fr) && sp.nst == 3 && fixed_tile_ok(sp.S, p.tile == TileOf<T>::value);
       (which ? row_fixed : col_fixed) = fixed;
       if (!fixed) continue;
       for (int s = 0; s < 2; ++s) {

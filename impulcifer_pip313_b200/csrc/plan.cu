@@ -67,6 +67,8 @@ bool fixed_radices(int S, int* r) {
   // sub-FFT lengths with compile-time specialised kernels (fft_fixed.cuh); keep in sync with the dispatch switches
   // in fft2d.cuh (every length: plain forward / inverse passes) and deconv.cu (768: the fused K1 triple)
   switch (S) {
+    case 1600: r[0] = 16; r[1] = 10; r[2] = 10; return true;  // 192 kHz K1 plan (1536 x 1600), half-width tiles only
+    case 1536: r[0] = 12; r[1] = 8; r[2] = 16; return true;
     case 768: r[0] = 8; r[1] = 12; r[2] = 8; return true;
     case 675: r[0] = 15; r[1] = 9; r[2] = 5; return true;
     case 432: r[0] = 12; r[1] = 9; r[2] = 4; return true;
@@ -85,6 +87,12 @@ bool fixed_radices(int S, int* r) {
     case 75: r[0] = 5; r[1] = 5; r[2] = 3; return true;
     default: return false;
   }
+}
+
+bool fixed_tile_ok(int S, bool full_tile) {
+  // which tile width the specialised kernels of a length are built for: 1536 / 1600 (192 kHz K1 plans) only exist for
+  // half-width tiles, everything else only for full-width tiles
+  return S > 1024 ? !full_tile : full_tile;
 }
 
 std::vector<double> stage_table_full(const SubPlan& sp, int s, bool transposed) {
@@ -215,7 +223,18 @@ bool plan_2d(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, Pla
   // full tile = 128-byte HBM segments; transforms whose sub-FFTs do not fit shared memory at that width
   // (192 kHz sweeps) fall back to half-width tiles (64-byte segments)
   const int tile = 64 / elem_bytes;
-  if (plan_2d_tile(ctx, n_min, exact, elem_bytes, tile, out)) return true;
+  if (plan_2d_tile(ctx, n_min, exact, elem_bytes, tile, out)) {
+    // a full-width plan that leaves room for ONE CTA per SM loses to half-width tiles when both sub-FFT lengths
+    // have specialised kernels at that width (192 kHz: 1536 x 1600, two 256-thread CTAs of 98 KB per SM)
+    const size_t smem_two = ((ctx && ctx->smem_per_sm) ? ctx->smem_per_sm : (size_t)228 * 1024) / 2 - 1024;
+    Plan2D h;
+    int fr[3];
+    if (allow_half_tile && std::max(out->smem_col, out->smem_row) > smem_two &&
+        plan_2d_tile(ctx, n_min, exact, elem_bytes, tile / 2, &h) && h.N1 > 768 && h.N2 > 768 &&
+        fixed_radices(h.N1, fr) && fixed_radices(h.N2, fr))
+      *out = h;
+    return true;
+  }
   return allow_half_tile && plan_2d_tile(ctx, n_min, exact, elem_bytes, tile / 2, out);
 }
 
@@ -245,7 +264,7 @@ static bool plan_2d_tile(const impb_ctx* ctx, int64_t n_min, bool exact, int ele
     if (c >= 1e299) continue;
     if (smem > smem_two) c *= 1.3;  // one CTA per SM: less latency hiding
     int fr[3];
-    if (fixed_radices(S, fr)) c *= 0.4;  // compile-time specialised kernel
+    if (fixed_radices(S, fr) && fixed_tile_ok(S, tile == 64 / elem_bytes)) c *= 0.4;  // compile-time specialised kernel
     cands.push_back({S, smem, threads, c});
   }
   double best = 1e300;
