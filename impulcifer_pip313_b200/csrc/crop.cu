@@ -675,16 +675,44 @@ __global__ void __launch_bounds__(256) k_xcorr(const double* __restrict__ x, con
     b[i] = (fade && i < fade_len) ? __dmul_rn(v, fade[i]) : v;
   }
   __syncthreads();
-  // z[k] = sum_l a[l] * b[l - k + nb - 1],  k in [0, na + nb - 1)
+  // z[k] = sum_l a[l] * b[l - k + nb - 1],  k in [0, na + nb - 1).  Every thread owns XR consecutive lags and slides a
+  // register window of b along l: one broadcast load of a[l] and one load of b feed XR FMAs (evaluated lag by lag the
+  // kernel was bound by shared-memory bandwidth: 3 wavefronts per warp-FMA).  Each lag is still ONE chain summed in
+  // increasing l (out-of-range taps contribute exact zeros), so the values are those of the plain loop.
+  constexpr int XR = 8;
   double best = -DBL_MAX;
   int best_k = 0x7fffffff;
   const int nk = na + nb - 1;
-  for (int k = threadIdx.x; k < nk; k += blockDim.x) {
-    const int shift = k - (nb - 1);       // l - shift indexes b
-    const int lo = max(0, shift), hi = min(na, nb + shift);
-    double acc = 0.0;
-    for (int l = lo; l < hi; ++l) acc = fma(a[l], b[l - shift], acc);
-    if (acc > best) { best = acc; best_k = k; }
+  auto b_at = [&](int i) -> double { return (i >= 0 && i < nb) ? b[i] : 0.0; };
+  for (int k0 = threadIdx.x * XR; k0 < nk; k0 += blockDim.x * XR) {
+    const int shift0 = k0 - (nb - 1);  // lag k0 + r pairs a[l] with b[l - shift0 - r]
+    const int lo = max(0, shift0), hi = min(na, nb + shift0 + XR - 1);
+    double acc[XR], w[XR];
+#pragma unroll
+    for (int r = 0; r < XR; ++r) { acc[r] = 0.0; w[r] = b_at(lo - shift0 - r); }
+    int l = lo;
+    for (; l + XR <= hi; l += XR) {
+#pragma unroll
+      for (int u = 0; u < XR; ++u) {
+        // at step l + u the window slot of lag r is w[(r - u) mod XR]
+        const double av = a[l + u];
+#pragma unroll
+        for (int r = 0; r < XR; ++r) acc[r] = fma(av, w[(r - u + XR) % XR], acc[r]);
+        // slot (XR - 1 - u + XR) % XR ... the oldest value (lag XR-1) is replaced by the next b for lag 0
+        w[(XR - 1 - u + XR) % XR] = b_at(l + u + 1 - shift0);
+      }
+    }
+    for (; l < hi; ++l) {  // tail: plain rotation
+      const double av = a[l];
+#pragma unroll
+      for (int r = 0; r < XR; ++r) acc[r] = fma(av, w[r], acc[r]);
+#pragma unroll
+      for (int r = XR - 1; r > 0; --r) w[r] = w[r - 1];
+      w[0] = b_at(l + 1 - shift0);
+    }
+#pragma unroll
+    for (int r = 0; r < XR; ++r)
+      if (k0 + r < nk && acc[r] > best) { best = acc[r]; best_k = k0 + r; }
   }
   // block arg-max, first index on ties
   __shared__ double sv[256];

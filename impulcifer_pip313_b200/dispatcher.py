@@ -19,7 +19,6 @@ from __future__ import annotations
 import threading
 import time
 import warnings
-from dataclasses import dataclass, field
 
 import numpy as np
 
