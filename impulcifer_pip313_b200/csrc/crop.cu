@@ -100,16 +100,19 @@ __global__ void __launch_bounds__(256) k_absmax(const double* __restrict__ x, co
       s[r].max_bits = (unsigned long long)__double_as_longlong(va.hint_max[r0 + r]);
     return;
   }
-  int64_t lo, hi;
-  chunk_bounds(p.n, &lo, &hi);
-  if (lo >= hi) return;
+  // grid = (rows, G): block g streams the 256-aligned slices g, g + G, ... of the row (few, fat blocks: the rows that
+  // take their maximum from the hint cost one block launch each instead of one per 4096 samples)
   double m = 0.0;
-  int64_t i = lo + threadIdx.x;
-  for (; i + 768 < hi; i += 1024) {  // four independent loads in flight per thread
-    const double a0 = p[i], a1 = p[i + 256], a2 = p[i + 512], a3 = p[i + 768];
-    m = fmax(fmax(m, fmax(fabs(a0), fabs(a1))), fmax(fabs(a2), fabs(a3)));
+  const int64_t slice = 4096;
+  for (int64_t lo = (int64_t)blockIdx.y * slice; lo < p.n; lo += (int64_t)gridDim.y * slice) {
+    const int64_t hi = min(p.n, lo + slice);
+    int64_t i = lo + threadIdx.x;
+    for (; i + 768 < hi; i += 1024) {  // four independent loads in flight per thread
+      const double a0 = p[i], a1 = p[i + 256], a2 = p[i + 512], a3 = p[i + 768];
+      m = fmax(fmax(m, fmax(fabs(a0), fabs(a1))), fmax(fabs(a2), fabs(a3)));
+    }
+    for (; i < hi; i += 256) m = fmax(m, fabs(p[i]));
   }
-  for (; i < hi; i += 256) m = fmax(m, fabs(p[i]));
   for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   __shared__ double sm[8];
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
@@ -218,7 +221,12 @@ int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double he
   for (int64_t b0 = 0; b0 < batch; b0 += (int64_t)1 << 30) {
     const int64_t nb = std::min<int64_t>((int64_t)1 << 30, batch - b0);
     dim3 grid((unsigned)nb, (unsigned)chunks);
-    if (!known_max) k_absmax<<<grid, thr, 0, st>>>(x, va, b0, scratch + b0);
+    if (!known_max) {
+      // with hints most rows return at once: few blocks per row; without, one block per slice streams best
+      const int64_t mg = va.hint_max ? std::max<int64_t>(8, 4096 / std::max<int64_t>(nb, 1)) : chunks;
+      const dim3 mgrid((unsigned)nb, (unsigned)std::min<int64_t>(chunks, mg));
+      k_absmax<<<mgrid, thr, 0, st>>>(x, va, b0, scratch + b0);
+    }
     // Blocks per row.  Head-cropped views (they carry the max hint) have their onset within the first samples: the
     // row is walked front to back by just enough blocks to fill the machine (896 rows on B200: 2 blocks per row
     // 111 us, one block per chunk 192 us, mostly block scheduling).  Raw estimates have the onset anywhere (the
