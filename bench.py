@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sets", type=int, default=int(os.environ.get("BENCH_SETS", "64")),
+    ap.add_argument("--sets", type=int, default=int(os.environ.get("BENCH_SETS", "128")),
                     help="recording sets per GPU per step")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--no-cpu-baseline", action="store_true")
