@@ -60,9 +60,9 @@ class SetResult:
     ``data`` is the CUDA tensor ``[n_irs, tail_ind]``.  The dispatcher hands over the set's slice of one flat output
     buffer and the 2-D view is made on first access (64 sets x a few microseconds of tensor bookkeeping stay off the
     critical path between two steps)."""
-    __slots__ = ("names", "tail_ind", "peaks", "crop", "knees", "warnings", "_data", "_flat")
+    __slots__ = ("names", "tail_ind", "peaks", "crop", "knees", "warnings", "_data", "_flat", "_off")
 
-    def __init__(self, names, data, tail_ind, peaks, crop, knees, warnings=None, flat=None):
+    def __init__(self, names, data, tail_ind, peaks, crop, knees, warnings=None, flat=None, offset=0):
         self.names = names            # ["FL-left", "FL-right", ...]
         self.tail_ind = tail_ind
         self.peaks = peaks            # raw-estimate peak index per IR
@@ -70,12 +70,14 @@ class SetResult:
         self.knees = knees            # Lundeby knee index per IR (after alignment)
         self.warnings = [] if warnings is None else warnings
         self._data = data
-        self._flat = flat             # 1-D slice [n_irs * tail_ind] of the dispatcher's output buffer
+        self._flat = flat             # the dispatcher's flat output buffer; this set starts at element `offset`
+        self._off = offset
 
     @property
     def data(self):
         if self._data is None:
-            self._data = self._flat.view(len(self.names), self.tail_ind)
+            n = len(self.names)
+            self._data = self._flat.narrow(0, self._off, n * self.tail_ind).view(n, self.tail_ind)
         return self._data
 
     @data.setter
@@ -134,6 +136,7 @@ class BatchDispatcher:
             right = np.array([row_of[f"{s}-right"] for s in spk_list])
             lay['left'] = torch.as_tensor(left, device=device)
             lay['right'] = torch.as_tensor(right, device=device)
+            lay['left_h'], lay['right_h'] = left.tolist(), right.tolist()  # host copies: no device round trip later
             head = int(self.head_ms * fs / 1000)
             lay['delay'] = torch.as_tensor([int(np.round(SPEAKER_DELAYS[s] * fs)) + head for s in spk_list],
                                            device=device)
@@ -301,10 +304,12 @@ class BatchDispatcher:
             flat = ops.gather_rows(flatE, off1, geom_d[0], geom_d[1], int(set_off[-1]), int(tails_np.max()), shift=total,
                                    valid_lo=lo, valid_hi=hi, fade_in=window_in, fade_out=window_out)
             launches += 1
+            mark('tail gather launch')
             # host-only bookkeeping after the last launch: it overlaps the gather
             side_msgs = self._side_warnings(lay, peaks_h)
-            pieces = flat.split((tails_np * n).tolist())
-            results = [SetResult(lay['names'], None, tails[s], peaks_h[s], crop_h[s], knees_h[s], side_msgs[s], pieces[s])
+            offs_l = set_off.tolist()
+            names = lay['names']
+            results = [SetResult(names, None, tails[s], peaks_h[s], crop_h[s], knees_h[s], side_msgs[s], flat, offs_l[s])
                        for s in range(S)]
             mark('tail gather')
         if marks is not None:
@@ -372,7 +377,7 @@ class BatchDispatcher:
 
     def _side_warnings(self, lay, peaks):
         """Wrong-side ITD warnings of crop_heads (ref core/hrir.py:578-606) for all sets: [S][...] messages."""
-        li, ri = lay['left'].tolist(), lay['right'].tolist()
+        li, ri = lay['left_h'], lay['right_h']
         pl, pr = peaks[:, li], peaks[:, ri]
         is_right = np.array([c == 'right' for c in lay['side_code']])
         is_left = np.array([c == 'left' for c in lay['side_code']])
