@@ -273,11 +273,12 @@ template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
   return IMPB_OK;
 }
 
-// HALF_: the length is served with half-width tiles (TileOf<T>/2 columns: 192 kHz plans, whose sub-FFTs do not fit
-// shared memory at full width); a kernel is only instantiated for the tile width its length is planned with
-#define IMPB_FX_CASE(KERNEL, S_, R0_, R1_, R2_, HALF_)                                          \
+// WIDTHS_: 1 = full-width tiles only, 2 = half-width only (TileOf<T>/2 columns: 88.2 ... 192 kHz plans, whose
+// sub-FFTs do not fit shared memory twice per SM at full width), 3 = both; a kernel is only instantiated for the tile
+// widths its length is planned with
+#define IMPB_FX_CASE(KERNEL, S_, R0_, R1_, R2_, WIDTHS_)                                        \
   case S_: {                                                                                    \
-    if constexpr (TILE == (HALF_ ? TileOf<T>::value / 2 : TileOf<T>::value)) {                   \
+    if constexpr ((TILE == TileOf<T>::value && ((WIDTHS_) & 1)) || (TILE == TileOf<T>::value / 2 && ((WIDTHS_) & 2))) { \
       auto k = KERNEL<T, TILE, 256, Radix3<R0_, R1_, R2_>, F>;                                   \
       const size_t smem = fx_tile_elems<S_, TILE>() * sizeof(cx_t<T>);                           \
       int rc = fx_prepare(k, smem, device);                                                      \
@@ -296,9 +297,9 @@ template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
   static int NAME(int S, dim3 grid, cudaStream_t st, int device, const cx_t<T>* tw0, const cx_t<T>* tw1,     \
                   const F& f) {                                                                              \
     switch (S) {                                                                                             \
-      IMPB_FX_CASE(KERNEL, 768, 8, 12, 8, false)                                                             \
-      IMPB_FX_CASE(KERNEL, 1536, 12, 8, 16, true)                                                            \
-      IMPB_FX_CASE(KERNEL, 1600, 16, 10, 10, true)                                                           \
+      IMPB_FX_CASE(KERNEL, 768, 8, 12, 8, 3)                                                                 \
+      IMPB_FX_CASE(KERNEL, 1536, 12, 8, 16, 2)                                                               \
+      IMPB_FX_CASE(KERNEL, 1600, 16, 10, 10, 2)                                                              \
       default: set_error("no specialised kernel for S=%d", S); return IMPB_EUNSUPPORTED;                    \
     }                                                                                                        \
   }
@@ -317,8 +318,9 @@ template <typename T> struct DeconvEngine {
   // in plan.cu:fixed_radices only serve the frequency-response transforms
   bool fixed_path() const {
     const Plan2D& p = fft.p;
+    auto k1_half = [](int S) { return S == 768 || S == 1536 || S == 1600; };
     const bool full = p.tile == FULL && p.N1 == 768 && p.N2 == 768;          // 44.1 / 48 kHz sweeps
-    const bool half = p.tile == FULL / 2 && p.N1 == 1536 && p.N2 == 1600;    // 192 kHz sweeps
+    const bool half = p.tile == FULL / 2 && k1_half(p.N1) && k1_half(p.N2);  // 88.2 ... 192 kHz sweeps
     return fft.col_fixed && fft.row_fixed && (full || half) && getenv("IMPB_NO_FIXED") == nullptr;
   }
 

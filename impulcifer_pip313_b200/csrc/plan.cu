@@ -90,9 +90,9 @@ bool fixed_radices(int S, int* r) {
 }
 
 bool fixed_tile_ok(int S, bool full_tile) {
-  // which tile width the specialised kernels of a length are built for: 1536 / 1600 (192 kHz K1 plans) only exist for
-  // half-width tiles, everything else only for full-width tiles
-  return S > 1024 ? !full_tile : full_tile;
+  // which tile width the specialised kernels of a length are built for: 1536 / 1600 (88.2 ... 192 kHz K1 plans) only
+  // exist for half-width tiles, 768 for both (it pairs with 1536 at 88.2 / 96 kHz), everything else for full width
+  return S > 1024 ? !full_tile : (full_tile || S == 768);
 }
 
 std::vector<double> stage_table_full(const SubPlan& sp, int s, bool transposed) {
@@ -230,8 +230,8 @@ bool plan_2d(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, Pla
     Plan2D h;
     int fr[3];
     if (allow_half_tile && std::max(out->smem_col, out->smem_row) > smem_two &&
-        plan_2d_tile(ctx, n_min, exact, elem_bytes, tile / 2, &h) && h.N1 > 768 && h.N2 > 768 &&
-        fixed_radices(h.N1, fr) && fixed_radices(h.N2, fr))
+        plan_2d_tile(ctx, n_min, exact, elem_bytes, tile / 2, &h) && h.N1 >= 768 && h.N2 >= 768 &&
+        fixed_radices(h.N1, fr) && fixed_radices(h.N2, fr) && fixed_tile_ok(h.N1, false) && fixed_tile_ok(h.N2, false))
       *out = h;
     return true;
   }

@@ -201,3 +201,44 @@ def test_absmax_and_argmax_outputs(torch_cuda):
         assert T.equal(amax, out2.abs().max(dim=1).values)
         a2, o2 = arg.cpu().numpy(), out2.cpu().numpy()
         assert abs(o2[0, a2[0]]) == float(amax[0])
+
+
+@pytest.mark.parametrize("fs,plan", [(96000, (768, 1536)), (192000, (1536, 1600))])
+def test_high_rate_plans_use_half_width_tiles_and_match_oracle(torch_cuda, fs, plan):
+    """88.2 ... 192 kHz sweeps: specialised kernels at half tile width (768 x 1536, 1536 x 1600), FP64 and FP32."""
+    T = torch_cuda
+    est = _est(5.0, fs)
+    L = 2 * fs + len(est)
+    p64 = est.plan(L)
+    assert (p64.n1, p64.n2) == plan
+    rng = np.random.default_rng(fs)
+    rec = np.zeros((3, L))
+    for r in range(3):
+        d = int(rng.integers(1000, 50000))
+        h = np.zeros(4000)
+        h[0] = 1.0
+        h[1:] = 0.1 * rng.standard_normal(3999) * np.exp(-np.arange(3999) / 600.0)
+        seg = np.convolve(est.test_signal, h)[:L - d]
+        rec[r, d:d + len(seg)] = seg
+    want = np.stack([O.estimate(rec[r], est.inverse_filter) for r in range(3)])
+    amax = T.empty(3, dtype=T.float64, device='cuda')
+    arg = T.empty(3, dtype=T.int64, device='cuda')
+    nblk, blk_len, blk_first = p64.blockmax_info()
+    assert nblk == p64_radix0(plan)
+    bm = T.empty((3, nblk), dtype=T.float64, device='cuda')
+    got = p64.execute(T.from_numpy(rec).cuda(), absmax=amax, argmax=arg, blockmax=bm).cpu().numpy()
+    for r in range(3):
+        assert rel_peak_err(got[r], want[r]) < 1e-9
+        assert float(amax[r]) == np.abs(got[r]).max() and abs(got[r, int(arg[r])]) == float(amax[r])
+    ob = np.abs(got)
+    for q in range(nblk):
+        lo, hi = max(blk_first + q * blk_len, 0), min(blk_first + (q + 1) * blk_len, L)
+        if hi > lo:
+            assert np.array_equal(bm[:, q].cpu().numpy(), ob[:, lo:hi].max(axis=1))
+    g32 = est.plan(L, precision=32).execute(T.from_numpy(rec).cuda().float()).cpu().numpy().astype(np.float64)
+    for r in range(3):
+        assert 20 * np.log10(np.max(np.abs(g32[r] - want[r])) / np.max(np.abs(want[r]))) < -90.0
+
+
+def p64_radix0(plan):
+    return {768: 8, 1536: 12}[plan[0]]
