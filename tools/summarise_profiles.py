@@ -85,7 +85,7 @@ for _, n, v in step:
     a = agg.setdefault(short(n), [0, 0.0])
     a[0] += 1
     a[1] += v
-out = ["# Round 1 — launch list of one bench step (64 recording sets = 896 IRs), B200, final build of the round", "",
+out = ["# Round 1 — launch list of one bench step (128 recording sets = 1792 IRs), B200, final build of the round", "",
        "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 1 --warmup 3 "
        "--no-cpu-baseline --no-fp32`",
        "(taken right after the same command exited 0 without ncu; per-launch times under ncu are cold-cache and serialised: "
