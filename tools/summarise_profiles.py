@@ -76,8 +76,9 @@ recs = [(k, d['name'], d['gpu__time_duration.sum']) for k, d in sorted(per.items
 starts = [i for i, (_, n, _) in enumerate(recs) if 'k_fx_fwd' in n]
 # a bench step = the launches between two consecutive K1 column passes of full-batch process() calls (the warm-up /
 # timed steps have ~90 launches in between; the chunked e2e calls that follow are shorter): take the last full one
-wins = [(a, b) for a, b in zip(starts[:-1], starts[1:]) if b - a >= 60]
-lo, hi = wins[-1]
+# (a step may hold several K1 chunks: its first column pass is the one that follows a long gap)
+begins = [b for a, b in zip(starts[:-1], starts[1:]) if b - a >= 60]
+lo, hi = begins[-2], begins[-1]
 step = recs[lo:hi]
 tot = sum(v for _, _, v in step)
 agg = collections.OrderedDict()
@@ -86,7 +87,7 @@ for _, n, v in step:
     a[0] += 1
     a[1] += v
 out = ["# Round 1 — launch list of one bench step (128 recording sets = 1792 IRs), B200, final build of the round", "",
-       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 1 --warmup 3 "
+       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 700 --csv python bench.py --steps 1 --warmup 3 "
        "--no-cpu-baseline --no-fp32`",
        "(taken right after the same command exited 0 without ncu; per-launch times under ncu are cold-cache and serialised: "
        "compare shares).",
