@@ -85,6 +85,19 @@ class SetResult:
         self._data = value
         self._flat = None
 
+    # pickling (DeviceShard.gather): ship this set's own samples as a host tensor, never the shared flat buffer
+    def __getstate__(self):
+        data = self.data
+        if hasattr(data, "detach"):
+            data = data.detach().cpu().contiguous().clone()
+        return {"names": self.names, "tail_ind": self.tail_ind, "peaks": self.peaks, "crop": self.crop,
+                "knees": self.knees, "warnings": self.warnings, "data": data}
+
+    def __setstate__(self, state):
+        self.names, self.tail_ind, self.peaks = state["names"], state["tail_ind"], state["peaks"]
+        self.crop, self.knees, self.warnings = state["crop"], state["knees"], state["warnings"]
+        self._data, self._flat, self._off = state["data"], None, 0
+
     def as_dict(self):
         out = {}
         host = self.data.cpu().numpy()
