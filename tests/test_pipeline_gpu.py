@@ -245,6 +245,33 @@ def test_batch_dispatcher_matches_oracle(T, est48, synth_rec):
     assert np.max(np.abs(sm[0].cpu().numpy() - O.smoothen_fractional_octave(f, raw[0].cpu().numpy(), 1 / 3))) < 1e-9
 
 
+def test_batch_dispatcher_seed_fuzz_integers_and_values(T, est48):
+    """Eight more seeded recording sets in one batch (different onset latencies, decay times, noise floors): every
+    integer the path decides (first peaks, knees, tail length) equals the oracle chain, samples within 1e-9 of peak."""
+    from impulcifer_pip313_b200 import BatchDispatcher, synth
+    fs = 48000
+    seeds = (5, 11, 23, 42, 97, 101, 314, 2718)
+    recs = [synth.recording_set(est48.test_signal, fs, synth.LAYOUT_71, seed=s) for s in seeds]
+    disp = BatchDispatcher(est48, synth.LAYOUT_71)
+    results = disp.process(T.from_numpy(np.stack(recs)).cuda())
+    P, _, _ = O.sweep_parameters(fs)
+    for k, seed in enumerate(seeds):
+        irs = O.open_recording(recs[k], fs, synth.LAYOUT_71, est48.inverse_filter, fs)
+        peaks = [O.peak_index(irs[s][e]) for s in irs for e in ('left', 'right')]
+        assert list(results[k].peaks) == peaks, seed
+        O.crop_heads(irs, fs)
+        O.align_ipsilateral_all(irs, fs)
+        O.align_onset_groups_peak_leftref(irs)
+        knees = [O.decay_params(irs[s][e], fs)[1] for s in irs for e in ('left', 'right')]
+        assert list(results[k].knees) == knees, seed
+        tail = O.crop_tails(irs, fs, len(est48), P, fs)
+        assert results[k].tail_ind == tail, seed
+        got = results[k].as_dict()
+        for s in irs:
+            for e in irs[s]:
+                assert rel_peak_err(got[s][e], irs[s][e]) < 1e-9, (seed, s, e)
+
+
 def test_repeat_runs_bitwise_deterministic(T, est48, synth_rec):
     """tests/test_brir_thread_determinism.py analogue: repeated runs give byte-identical results."""
     from impulcifer_pip313_b200 import BatchDispatcher, synth
