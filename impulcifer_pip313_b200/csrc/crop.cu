@@ -463,12 +463,17 @@ __global__ void __launch_bounds__(256) k_lb_blocksums(const double* __restrict__
         for (int64_t i = a + lane; i < b; i += 32) acc[u] += sq(i);
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      for (int o = 16; o; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-      const int k = k0 + u * 8;
-      if (lane == 0 && k < k_end) blk[(size_t)r * LB_MAXBLK + k] = acc[u];
-    }
+    // four xor-butterfly reductions packed into one: after the offset-16 step a lane only carries two of the four
+    // sums, after the offset-8 step one (6 double shuffles instead of 20).  Every partial sum has the same two
+    // operands as in the plain butterfly, so the results are bit-identical; lane 8u ends up with block u.
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    double x0 = hi16 ? acc[2] : acc[0], x1 = hi16 ? acc[3] : acc[1];
+    x0 += __shfl_xor_sync(0xffffffffu, hi16 ? acc[0] : acc[2], 16);
+    x1 += __shfl_xor_sync(0xffffffffu, hi16 ? acc[1] : acc[3], 16);
+    double y = (hi8 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, hi8 ? x0 : x1, 8);
+    for (int o = 4; o; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+    const int k = k0 + (lane >> 3) * 8;
+    if ((lane & 7) == 0 && k < k_end) blk[(size_t)r * LB_MAXBLK + k] = y;
   }
 }
 

@@ -225,10 +225,10 @@ class BatchDispatcher:
             e_arg = torch.empty(B, dtype=torch.int64, device=dev)
             nblk, blk_len, blk_first = plan.blockmax_info()
             e_blk = torch.empty((B, nblk), dtype=torch.float64, device=dev) if nblk else None
-            E = plan.execute(recordings.reshape(-1), length=L, row_offsets=row_offs, absmax=e_max, argmax=e_arg,
-                             blockmax=e_blk)
-            if E.dtype != torch.float64:
-                E = E.to(torch.float64)
+            # the FP32 fast path widens on store (exact), so the crop kernels always see float64 rows
+            E = torch.empty((B, L), dtype=torch.float64, device=dev)
+            plan.execute(recordings.reshape(-1), out=E, length=L, row_offsets=row_offs, absmax=e_max, argmax=e_arg,
+                         blockmax=e_blk)
             launches += plan.launches(B) + 1  # + argmax pick
             mark('K1 deconvolution')
             flatE = E.reshape(-1)
