@@ -53,6 +53,7 @@ template <typename T> struct DeconvArgs {
   int cand_tiles;
   unsigned long long* blockmax;  // optional [nrows][nblk]: bits of max |out| per time block (specialised path)
   int nblk;
+  bool ws_rows_ok(int pairs) const { return (int64_t)pairs * N1 < ((int64_t)1 << 31); }  // TMA coordinates are int32
 };
 
 __device__ __forceinline__ double load_sample(const void* p, int fmt, int64_t i) {
@@ -260,6 +261,32 @@ __global__ void k_spec_layout(const double2* __restrict__ nat, cx_t<T>* __restri
   hs[i] = mkc<T>((T)(v.x * scale), (T)(v.y * scale));
 }
 
+// ---- TMA descriptor of the K1 workspace: [pairs * N1 rows][2 * N2 doubles], box = 256 rows x 128 bytes, 128-byte swizzle ----
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = []() -> tmap_encode_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (tmap_encode_fn)p;
+  }();
+  return fn;
+}
+static bool ws_column_map(CUtensorMap* map, const double2* ws, int64_t rows, int N2) {
+  tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)2 * N2, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)2 * N2 * sizeof(double)};
+  const cuuint32_t box[2] = {16, 256};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)ws, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ---- compile-time specialised launches (fft_fixed.cuh); sizes must match plan.cu:fixed_radices ----
 template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
   // the opt-in shared-memory size is a per-kernel, per-device attribute: set it once
@@ -346,6 +373,19 @@ template <typename T> struct DeconvEngine {
       if ((rc = fx_conv<T, TILE>(p.N2, dim3(fft.row_tiles(), pairs), st, device, fft.fx_row[0], fft.fx_row[1],
                                  DeconvRow<T, TILE, true>{a})))
         return rc;
+      if constexpr (sizeof(T) == 8 && TILE == 8) {
+        // TMA-fed column DIT (768-row tiles): the workspace tile arrives through a tensor map, swizzled in flight
+        static const bool no_tma = getenv("IMPB_NO_TMA") != nullptr;
+        CUtensorMap map;
+        if (!no_tma && p.N1 == 768 && a.ws_rows_ok(pairs) && ws_column_map(&map, a.ws, (int64_t)pairs * p.N1, p.N2)) {
+          auto k = k_fx_inv_tma<TILE, 256, Radix3<8, 12, 8>, DeconvColOut<T, TILE>>;
+          const size_t smem = fx_tile_elems<768, TILE>() * sizeof(cx_t<T>) + 1024;  // + room for the 1024-byte alignment
+          if ((rc = fx_prepare(k, smem, device))) return rc;
+          k<<<dim3(fft.col_tiles(), pairs), 256, smem, st>>>(fft.fx_col[0], fft.fx_col[1], DeconvColOut<T, TILE>{a}, map);
+          IMPB_CUDA(cudaGetLastError());
+          return IMPB_OK;
+        }
+      }
       return fx_inv<T, TILE>(p.N1, dim3(fft.col_tiles(), pairs), st, device, fft.fx_col[0], fft.fx_col[1],
                              DeconvColOut<T, TILE>{a});
     }

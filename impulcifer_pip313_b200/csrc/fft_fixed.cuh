@@ -4,6 +4,8 @@
 // read-only path; the 8 columns of a tile share each entry, so a warp touches one or two sectors).
 // Used for the sub-FFT lengths the headline workloads need; every other length takes the generic path.
 #pragma once
+#include <cuda.h>
+
 #include <type_traits>
 
 #include "fft_tile.cuh"
@@ -249,12 +251,12 @@ k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1,
   fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, false, false>(nullptr, sl, gs, post);
 }
 
-template <typename T, int TILE, int NT, class RX, class F>
-__global__ void __launch_bounds__(NT, 2)
-k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// The column DIT pass.  FROM_SMEM: the tile has already been filled (TMA, see k_fx_inv_tma) and the first stage runs
+// in place on it instead of loading from HBM.
+template <typename T, int TILE, int NT, class RX, class F, bool FROM_SMEM>
+__device__ __forceinline__ void fx_inv_core(unsigned char* smem_raw, const cx_t<T>* __restrict__ tw0,
+                                            const cx_t<T>* __restrict__ tw1, const F& f, const int t, const int b) {
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
-  const int t = blockIdx.x, b = blockIdx.y;
   // running max |re|, |im| of what this thread stores: the per-row max|x| the peak search needs comes for free
   T mx_re = (T)0, mx_im = (T)0;
   int ix_re = 0, ix_im = 0;  // output index of the thread's running maxima (argmax candidates)
@@ -284,7 +286,8 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   };
   auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
-  fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false, kPrefetch>(nullptr, gl, ss, NoPost{});
+  if constexpr (FROM_SMEM) fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false>(nullptr, sl, ss, NoPost{});
+  else fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false, kPrefetch>(nullptr, gl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true, false>(tw1, sl, ss, NoPost{});
   __syncthreads();
@@ -327,13 +330,80 @@ k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   }
 }
 
-// row pass: forward, x spectrum, inverse.  tw0r / tw1r are the [p-1][np] (transposed) stage tables.
 template <typename T, int TILE, int NT, class RX, class F>
 __global__ void __launch_bounds__(NT, 2)
-k_fx_conv(const cx_t<T>* __restrict__ tw0r, const cx_t<T>* __restrict__ tw1r, const F f) {
+k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
+  fx_inv_core<T, TILE, NT, RX, F, false>(smem_raw, tw0, tw1, f, blockIdx.x, blockIdx.y);
+}
+
+// ---- TMA-fed variant (FP64, full-width tiles) ---------------------------------------------------------------
+// The workspace tile of a column pass is S rows x 128 bytes (8 complex doubles).  One elected thread issues S/256
+// cp.async.bulk.tensor.2d copies (a tensor-map box holds at most 256 rows) that land in shared memory in exactly the
+// layout the butterflies use: the hardware 128-byte swizzle XORs the 16-byte chunk index with (row % 8), which IS
+// slot = c ^ (e & 7).  No thread spends registers, LSU wavefronts or scoreboard waits on the HBM read.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok = 0;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(phase)
+        : "memory");
+    if (!ok && ++spins > (1 << 22)) __trap();  // a copy that never lands must abort the launch, not hang the device
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+          (unsigned)__cvta_generic_to_shared(smem_dst)),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
+      : "memory");
+}
+
+template <int TILE, int NT, class RX, class F>
+__global__ void __launch_bounds__(NT, 2)
+k_fx_inv_tma(const double2* __restrict__ tw0, const double2* __restrict__ tw1, const F f,
+             const __grid_constant__ CUtensorMap ws_map) {
+  extern __shared__ __align__(1024) unsigned char smem_tma[];
+  __shared__ __align__(8) unsigned long long bar;
+  static_assert(TILE == 8 && RX::S % 256 == 0, "128-byte rows, whole 256-row boxes");
   const int t = blockIdx.x, b = blockIdx.y;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, RX::S * TILE * (unsigned)sizeof(double2));
+#pragma unroll
+    for (int k = 0; k < RX::S / 256; ++k)  // coordinates in doubles (inner) and matrix rows (outer)
+      tma_load_2d(smem_tma + (size_t)k * 256 * TILE * sizeof(double2), &ws_map, t * TILE * 2, b * RX::S + k * 256, &bar);
+  }
+  mbar_wait(&bar, 0);
+  fx_inv_core<double, TILE, NT, RX, F, true>(smem_tma, tw0, tw1, f, t, b);
+}
+
+// row pass: forward, x spectrum, inverse.  tw0r / tw1r are the [p-1][np] (transposed) stage tables.
+// FROM_SMEM: the tile has been staged in shared memory and the first stage runs in place.  (A TMA-fed variant of this
+// pass -- one 3-D box per tile, and one copy + mbarrier per matrix row -- was measured 7-8 % SLOWER than loading the
+// first stage straight into registers: the pass is bound by shared-memory wavefronts and the staged tile adds a read.)
+template <typename T, int TILE, int NT, class RX, class F, bool FROM_SMEM>
+__device__ __forceinline__ void fx_conv_core(unsigned char* smem_raw, const cx_t<T>* __restrict__ tw0r,
+                                             const cx_t<T>* __restrict__ tw1r, const F& f, const int t, const int b) {
+  cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
   constexpr int ITEMS_MID = (RX::S / RX::R2) * TILE;
   auto gl = [&](int e, int c) -> cx_t<T> { return f.load(b, t, e, c); };
   auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
@@ -341,7 +411,8 @@ k_fx_conv(const cx_t<T>* __restrict__ tw0r, const cx_t<T>* __restrict__ tw1r, co
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<true, TILE, RX::S>(e, c)] = v; };
   auto pw = [&](int q, int w) -> cx_t<T> { return f.pw(t, RX::R2, ITEMS_MID, q, w); };
   auto post = [&](int e, int c) -> cx_t<T> { return f.post(t, e, c); };
-  fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, true, kPrefetch>(tw0r, gl, ss, NoPost{});
+  if constexpr (FROM_SMEM) fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, true>(tw0r, sl, ss, NoPost{});
+  else fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, true, kPrefetch>(tw0r, gl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false, true>(tw1r, sl, ss, NoPost{});
   __syncthreads();
@@ -350,6 +421,13 @@ k_fx_conv(const cx_t<T>* __restrict__ tw0r, const cx_t<T>* __restrict__ tw1r, co
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true, true>(tw1r, sl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, true, true>(tw0r, sl, gs, post);
+}
+
+template <typename T, int TILE, int NT, class RX, class F>
+__global__ void __launch_bounds__(NT, 2)
+k_fx_conv(const cx_t<T>* __restrict__ tw0r, const cx_t<T>* __restrict__ tw1r, const F f) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  fx_conv_core<T, TILE, NT, RX, F, false>(smem_raw, tw0r, tw1r, f, blockIdx.x, blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------------
