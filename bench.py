@@ -315,6 +315,17 @@ def main():
         fp32 = {"k1_ms_per_launch": ms32, "k1_ir_per_s": B / (ms32 / 1e3), "algorithmic_bytes_per_ir": 8 * L,
                 "achieved_gbs": B * 8 * L / (ms32 / 1e3) / 1e9}
         del x32, o32, plan32
+        # the whole hot path (same float64 recordings, FP32 deconvolution, float64 crop chain), 3 steps
+        for _ in range(2):
+            disp.process(batch, precision=32)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            disp.process(batch, precision=32)
+        b.record()
+        torch.cuda.synchronize()
+        fp32["whole_path_ir_per_s"] = 3 * B / (a.elapsed_time(b) / 1e3)
     # secondary: per-IR frequency-response post-processing on the cropped responses of one step
     for _ in range(2):
         post = disp.postprocess(res)
