@@ -229,13 +229,14 @@ k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
   const int t = blockIdx.x, b = blockIdx.y;
-  for (int i = threadIdx.x; i < RX::S * TILE; i += NT) {
+  // adjacent lanes copy the re and the im part of one element: a warp instruction then fills 16 whole complex slots
+  // (contiguous shared-memory bytes) instead of the halves of 32 (which cost twice the shared-memory wavefronts)
+  for (int k = threadIdx.x; k < 2 * RX::S * TILE; k += NT) {
+    const int i = k >> 1, which = k & 1;
     const int e = i / TILE, c = i % TILE;
-    T* dst = reinterpret_cast<T*>(&tile[fx_smem<false, TILE, RX::S>(e, c)]);
-    const T* re = f.src(b, t, e, c, 0);
-    const T* im = f.src(b, t, e, c, 1);
-    if (re) cp_async_n<sizeof(T)>(dst, re); else dst[0] = (T)0;
-    if (im) cp_async_n<sizeof(T)>(dst + 1, im); else dst[1] = (T)0;
+    T* dst = reinterpret_cast<T*>(&tile[fx_smem<false, TILE, RX::S>(e, c)]) + which;
+    const T* src = f.src(b, t, e, c, which);
+    if (src) cp_async_n<sizeof(T)>(dst, src); else *dst = (T)0;
   }
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
