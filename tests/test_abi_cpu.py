@@ -60,10 +60,18 @@ def test_planner_headline_and_exact_sizes():
     # a length with a prime factor > 5 has no exact plan: the call reports it instead of approximating
     rc, *_ = _probe(2 * 3 * 7 * 11 * 13, 1)
     assert rc != 0
-    # 96 kHz and 192 kHz sweeps still plan (longer transforms)
-    for n_min in (1145947, 2428174):
-        rc, n1, n2, _, _ = _probe(n_min, 0)
-        assert rc == 0 and n1 * n2 >= n_min
+    # 88.2 / 96 kHz and 192 kHz sweeps plan the lengths that have specialised half-width-tile kernels
+    for n_min, want in ((1077811, (768, 1536)), (990000, (768, 1536)), (2428174, (1536, 1600))):
+        rc, n1, n2, rcol, rrow = _probe(n_min, 0)
+        assert rc == 0 and n1 * n2 >= n_min and (n1, n2) == want, (n_min, n1, n2)
+    assert _probe(2428174, 0)[3:] == ([12, 8, 16], [16, 10, 10])
+    # 44.1 kHz shares the 48 kHz plan
+    assert _probe(495118, 0)[1:3] == (768, 768)
+    # exact-length transforms of the frequency-response chain factor into menu lengths (plan.cu:fixed_radices)
+    menu = {768, 675, 432, 400, 300, 256, 243, 162, 160, 135, 128, 125, 120, 108, 81, 75}
+    for n, both in ((65536, True), (19200, True), (96000, True), (84375, True), (57600, True), (21600, True)):
+        _, n1, n2, _, _ = _probe(n, 1)
+        assert (n1 in menu and n2 in menu) == both, (n, n1, n2)
 
 
 def test_resample_out_len():
