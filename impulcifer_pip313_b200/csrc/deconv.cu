@@ -31,24 +31,6 @@ using namespace impb;
 
 namespace {
 
-#ifndef IMPB_WS_HINT
-#define IMPB_WS_HINT 0  // 1: streaming (evict-first) loads / stores for the workspace, which is never re-read from cache
-#endif
-template <typename C> __device__ __forceinline__ C ws_ld(const C* p) {
-#if IMPB_WS_HINT
-  return __ldcs(p);
-#else
-  return *p;
-#endif
-}
-template <typename C> __device__ __forceinline__ void ws_st(C* p, C v) {
-#if IMPB_WS_HINT
-  __stcs(p, v);
-#else
-  *p = v;
-#endif
-}
-
 template <typename T> struct DeconvArgs {
   cx_t<T>* ws;
   const cx_t<T>* tw;
@@ -103,7 +85,7 @@ template <typename T, int TILE, bool PRE = false> struct DeconvColIn {
     const int n2 = t * TILE + c;
     if (n2 >= a.N2) return;
     const size_t idx = (size_t)e * a.N2 + n2;
-    ws_st(a.ws + (size_t)b * a.N + idx, PRE ? v : cmul(v, __ldg(a.tw + idx)));
+    a.ws[(size_t)b * a.N + idx] = PRE ? v : cmul(v, __ldg(a.tw + idx));
   }
   // four-step twiddle of output (e, c), fetched ahead of the butterfly by the specialised kernels
   __device__ __forceinline__ cx_t<T> post(int t, int e, int c) const {
@@ -127,7 +109,7 @@ template <typename T, int TILE, bool PRE = false> struct DeconvRow {
   __device__ __forceinline__ cx_t<T> load(int b, int t, int e, int c) const {
     const int row = t * TILE + c;
     if (row >= a.N1) return mkc<T>(0, 0);
-    return ws_ld(a.ws + (size_t)b * a.N + (size_t)row * a.N2 + e);
+    return a.ws[(size_t)b * a.N + (size_t)row * a.N2 + e];
   }
   __device__ __forceinline__ cx_t<T> pw(int t, int R, int items, int q, int w) const {
     return __ldg(a.hs + ((size_t)t * R + q) * items + w);
@@ -136,7 +118,7 @@ template <typename T, int TILE, bool PRE = false> struct DeconvRow {
     const int row = t * TILE + c;
     if (row >= a.N1) return;
     const size_t idx = (size_t)row * a.N2 + e;
-    ws_st(a.ws + (size_t)b * a.N + idx, PRE ? v : cmul(v, cconj(__ldg(a.tw + idx))));
+    a.ws[(size_t)b * a.N + idx] = PRE ? v : cmul(v, cconj(__ldg(a.tw + idx)));
   }
   __device__ __forceinline__ cx_t<T> post(int t, int e, int c) const {
     const int row = t * TILE + c;
