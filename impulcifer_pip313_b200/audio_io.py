@@ -70,7 +70,8 @@ def write_wav(file_path, fs, data, bit_depth=32):
 
 def magnitude_response(x, fs):
     """Reference ``core/audio_io.py:100-113``: ``(f, 20*log10|rfft(x)|)`` for the first ``ceil(n/2)`` bins,
-    computed on the device (K8).  No CPU path: lengths that are not 5-smooth are rejected by the plan."""
+    computed on the device (K8).  No CPU path: 5-smooth lengths use the two-pass FFT, every other length the chirp-z
+    (Bluestein) plan built on the same passes."""
     import torch
     from . import ops
     x = np.ascontiguousarray(x, dtype=np.float64)

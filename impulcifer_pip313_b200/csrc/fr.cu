@@ -20,6 +20,14 @@ struct impb_fft {
   impb_ctx* ctx = nullptr;
   int64_t n = 0;
   Fft2D<double> f;
+  // lengths with a prime factor > 5 (e.g. the 391 270 samples of an uncropped 48 kHz response, which the reference
+  // hands to frequency_response() in its headphone-compensation stage): Bluestein.  X[k] = conj(w_k) sum_n x[n] conj(w_n)
+  // w_(k-n) with w_m = exp(i pi m^2 / n): a circular convolution of length M >= 2n - 1 (5-smooth, plan `f`), and
+  // |X[k]| needs no final chirp multiply.
+  bool chirp = false;
+  int64_t M = 0;
+  double2* w = nullptr;   // [n]  exp(+i pi m^2 / n)
+  double2* Hs = nullptr;  // [M]  spectrum of the circularly extended chirp, in position order
 };
 
 namespace {
@@ -75,6 +83,55 @@ struct MagDbOp {
     if (k < half) out[(size_t)b * ld + k] = 20.0 * log10(hypot(v.x, v.y));
   }
 };
+
+// Bluestein: modulated real row in, |y[k]| in dB out
+struct ChirpColIn {
+  const double* x;
+  int64_t ld, n;
+  const double2* w;
+  double2* ws;
+  const double2* tw;
+  int64_t N;
+  int N2;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    const int64_t i = (int64_t)e * N2 + n2;
+    if (n2 >= N2 || i >= n) return make_double2(0.0, 0.0);
+    const double v = x[(size_t)b * ld + i];
+    const double2 ww = w[i];
+    return make_double2(v * ww.x, -v * ww.y);  // x[n] * conj(w_n)
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return;
+    const size_t idx = (size_t)e * N2 + n2;
+    ws[(size_t)b * N + idx] = cmul(v, tw[idx]);
+  }
+};
+struct ChirpColOut {
+  const double2* ws;
+  int64_t N;
+  int N2;
+  double* out;
+  int64_t ld, half;
+  double scale;  // 1 / M of the unnormalised inverse transform
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return make_double2(0.0, 0.0);
+    return ws[(size_t)b * N + (size_t)e * N2 + n2];
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int n2 = t * TILE + c;
+    const int64_t k = (int64_t)e * N2 + n2;
+    if (n2 >= N2 || k >= half) return;
+    out[(size_t)b * ld + k] = 20.0 * log10(hypot(v.x, v.y) * scale);
+  }
+};
+__global__ void __launch_bounds__(256) k_cmul_rows(double2* __restrict__ ws, const double2* __restrict__ h, int64_t N) {
+  double2* row = ws + (size_t)blockIdx.y * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+    row[i] = cmul(row[i], h[i]);
+}
 
 struct MagLinOp {  // |X[k]| for k < nbins (natural order)
   double* out;
@@ -355,15 +412,50 @@ int32_t impb_fft_create(impb_ctx* ctx, int64_t n, int32_t precision, impb_fft** 
   }
   DeviceGuard g(ctx->device);
   Plan2D p;
-  if (!plan_2d(ctx, n, true, 8, &p)) {
-    set_error("impb_fft_create: length %lld is not a product of two 5-smooth factors that fit shared memory", (long long)n);
+  if (plan_2d(ctx, n, true, 8, &p)) {
+    impb_fft* f = new impb_fft();
+    f->ctx = ctx;
+    f->n = n;
+    int rc = f->f.init(p);
+    if (rc) { delete f; return rc; }
+    *out = f;
+    return IMPB_OK;
+  }
+  // Bluestein over a 5-smooth circular length M >= 2n - 1
+  if (!plan_2d(ctx, 2 * n - 1, false, 8, &p)) {
+    set_error("impb_fft_create: no plan for length %lld (direct or chirp-z)", (long long)n);
     return IMPB_EUNSUPPORTED;
   }
   impb_fft* f = new impb_fft();
   f->ctx = ctx;
   f->n = n;
+  f->chirp = true;
+  f->M = p.N;
   int rc = f->f.init(p);
   if (rc) { delete f; return rc; }
+  const int64_t M = p.N;
+  std::vector<double2> w((size_t)n), h((size_t)M, make_double2(0.0, 0.0));
+  for (int64_t m = 0; m < n; ++m) {  // phase pi m^2 / n with m^2 reduced modulo 2n in integers
+    const unsigned __int128 sq = (unsigned __int128)(uint64_t)m * (uint64_t)m;
+    const int64_t r = (int64_t)(sq % (unsigned __int128)(2 * n));
+    const long double ang = 3.141592653589793238462643383279502884L * (long double)r / (long double)n;
+    w[(size_t)m] = make_double2((double)cosl(ang), (double)sinl(ang));
+    h[(size_t)m] = w[(size_t)m];
+    if (m) h[(size_t)(M - m)] = w[(size_t)m];
+  }
+  double2* d_h = nullptr;
+  cudaError_t e = cudaMalloc(&f->w, sizeof(double2) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&f->Hs, sizeof(double2) * M);
+  if (e == cudaSuccess) e = cudaMalloc(&d_h, sizeof(double2) * M);
+  if (e == cudaSuccess) e = cudaMemcpy(f->w, w.data(), sizeof(double2) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_h, h.data(), sizeof(double2) * M, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d_h); impb_fft_destroy(f); return cuda_fail(e, "chirp tables"); }
+  ColPlain<double, TILE> ci{d_h, f->Hs, f->f.tw, M, p.N2, 0};
+  rc = f->f.col_fwd<TILE>(ci, 1, 0);
+  if (!rc) rc = f->f.row_fwd<TILE>(RowPlain<double, TILE>{f->Hs, f->Hs, nullptr, M, p.N1, p.N2, 0, 0}, 1, 0);
+  e = cudaDeviceSynchronize();
+  cudaFree(d_h);
+  if (rc || e != cudaSuccess) { impb_fft_destroy(f); return rc ? rc : cuda_fail(e, "chirp spectrum"); }
   *out = f;
   return IMPB_OK;
 }
@@ -372,12 +464,14 @@ void impb_fft_destroy(impb_fft* f) {
   if (!f) return;
   DeviceGuard g(f->ctx->device);
   f->f.release();
+  cudaFree(f->w);
+  cudaFree(f->Hs);
   delete f;
 }
 
 int64_t impb_fft_workspace_bytes(const impb_fft* f, int64_t batch) {
   if (!f || batch < 1) return 0;
-  return batch * f->n * (int64_t)sizeof(double2);
+  return batch * (f->chirp ? f->M : f->n) * (int64_t)sizeof(double2);
 }
 
 int32_t impb_magnitude_db(impb_fft* f, const double* x, int64_t ld_x, double* mag_out, int64_t ld_out, int64_t batch,
@@ -393,6 +487,22 @@ int32_t impb_magnitude_db(impb_fft* f, const double* x, int64_t ld_x, double* ma
   const int64_t half = (f->n + 1) / 2;
   if (ld_out < half) { set_error("impb_magnitude_db: ld_out < ceil(n/2)"); return IMPB_EINVAL; }
   double2* ws = (double2*)workspace;
+  if (f->chirp) {
+    for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+      const int nb = (int)std::min<int64_t>(32768, batch - b0);
+      double2* w = ws + (size_t)b0 * p.N;
+      int rc = f->f.col_fwd<TILE>(ChirpColIn{x + (size_t)b0 * ld_x, ld_x, f->n, f->w, w, f->f.tw, p.N, p.N2}, nb, st);
+      if (!rc) rc = f->f.row_fwd<TILE>(RowPlain<double, TILE>{w, w, nullptr, p.N, p.N1, p.N2, 0, 0}, nb, st);
+      if (rc) return rc;
+      k_cmul_rows<<<dim3((unsigned)std::min<int64_t>((p.N + 255) / 256, 2048), nb), 256, 0, st>>>(w, f->Hs, p.N);
+      rc = f->f.row_inv<TILE>(RowPlain<double, TILE>{w, w, f->f.tw, p.N, p.N1, p.N2, 1, 0}, nb, st);
+      if (!rc) rc = f->f.col_inv<TILE>(ChirpColOut{w, p.N, p.N2, mag_out + (size_t)b0 * ld_out, ld_out, half,
+                                                   1.0 / (double)p.N}, nb, st);
+      if (rc) return rc;
+    }
+    IMPB_CUDA(cudaGetLastError());
+    return IMPB_OK;
+  }
   for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
     const int nb = (int)std::min<int64_t>(32768, batch - b0);
     RealColIn ci{x + (size_t)b0 * ld_x, ld_x, f->n, ws + (size_t)b0 * p.N, f->f.tw, p.N, p.N2};
@@ -412,6 +522,7 @@ int32_t impb_magnitude_lin(impb_fft* f, const double* x, int64_t ld_x, int64_t n
     set_error("impb_magnitude_lin: bad argument");
     return IMPB_EINVAL;
   }
+  if (f->chirp) { set_error("impb_magnitude_lin: chirp-z plans only serve impb_magnitude_db"); return IMPB_EUNSUPPORTED; }
   if (batch == 0 || n_bins == 0) return IMPB_OK;
   DeviceGuard g(f->ctx->device);
   cudaStream_t st = (cudaStream_t)stream;

@@ -219,6 +219,27 @@ def test_magnitude_db(T, n):
         assert np.max(np.abs(got[r] - m)) < 1e-8
 
 
+@pytest.mark.parametrize("n", [391270, 487270, 1009, 2 * 3 * 7 * 11 * 13, 30011])
+def test_magnitude_db_lengths_with_large_prime_factors(T, n):
+    """Lengths that are not 5-smooth go through the chirp-z (Bluestein) plan: 391 270 is the uncropped 48 kHz response
+    the reference hands to frequency_response() in its headphone-compensation stage, 487 270 is data/demo/FC.wav."""
+    from impulcifer_pip313_b200 import ImpulseResponse, ops
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, n)) * np.exp(-np.arange(n) / (n / 8.0))
+    x[1, n // 3] = 25.0
+    got = ops.magnitude_db(T.from_numpy(x).cuda()).cpu().numpy()
+    for r in range(2):
+        f, m = O.magnitude_response(x[r], 48000)
+        assert got[r].shape == m.shape
+        # same absolute-error regime as any FFT: compare linear magnitudes against the spectrum's peak
+        lin_g, lin_m = 10 ** (got[r] / 20), 10 ** (m / 20)
+        assert np.max(np.abs(lin_g - lin_m)) < 1e-11 * np.max(lin_m)
+    if n == 391270:
+        fr = ImpulseResponse(x[1].copy(), 48000).frequency_response()
+        f_o, raw_o = O.frequency_response(x[1], 48000)
+        assert np.array_equal(fr.frequency, f_o) and np.max(np.abs(fr.raw - raw_o)) < 1e-7
+
+
 def test_frequency_response_chain_golden(T):
     """magnitude -> decimate -> log-f lerp onto the 783-point grid == reference frequency_response()."""
     from impulcifer_pip313_b200 import ops
