@@ -43,6 +43,17 @@ def install(verbose: bool = False):
     class FrequencyResponse(frequency_response.FrequencyResponse, RefFR):
         __doc__ = RefFR.__doc__
 
+        # argument variants outside the hot path (bass-shelf target synthesis, cubic interpolation) stay the reference's
+        def compensate(self, compensation, bass_boost_gain=0.0, *args, **kwargs):
+            if bass_boost_gain:
+                return RefFR.compensate(self, compensation, bass_boost_gain, *args, **kwargs)
+            return frequency_response.FrequencyResponse.compensate(self, compensation, bass_boost_gain, *args, **kwargs)
+
+        def interpolate(self, f=None, f_step=frequency_response.DEFAULT_STEP, pol_order=1, **kwargs):
+            if pol_order != 1:
+                return RefFR.interpolate(self, f=f, f_step=f_step, pol_order=pol_order, **kwargs)
+            return frequency_response.FrequencyResponse.interpolate(self, f=f, f_step=f_step, pol_order=1, **kwargs)
+
     class ImpulseResponse(impulse_response.ImpulseResponse, RefIR):
         __doc__ = RefIR.__doc__
 
