@@ -8,6 +8,7 @@
 //   out[j] = sum_k taps[(j + n_pre_remove) * down - n_pre_pad - k * up] * x[k]
 // Each thread owns one output sample; the taps of one polyphase branch are read with stride `up`.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -58,6 +59,50 @@ __global__ void __launch_bounds__(256) k_resample(const double* __restrict__ src
       acc += xv * taps[t - k * up];
     }
     dst[(size_t)r * ld_dst + j] = acc;
+  }
+}
+
+// Register-tiled variant for up > 1: outputs j, j + up, j + 2 up ... share one polyphase branch (the same taps), and their
+// input windows are `down` samples apart, so a thread that owns RT such outputs loads every tap once for RT multiply-adds
+// (1 + RT loads per RT FMAs instead of 2 RT).  Each output is still one chain summed in ascending tap order, i.e. the
+// values are those of k_resample.
+template <int RT>
+__global__ void __launch_bounds__(256) k_resample_tiled(const double* __restrict__ src, int64_t ld_src, int64_t n,
+                                                        const double* __restrict__ decay, const double* __restrict__ taps,
+                                                        int64_t ntaps, int up, int down, int64_t n_pre_pad,
+                                                        int64_t n_pre_remove, int64_t n_out, double* __restrict__ dst,
+                                                        int64_t ld_dst) {
+  const int r = blockIdx.y;
+  const double* x = src + (size_t)r * ld_src;
+  const double* dp = decay ? decay + (size_t)r * 4 : nullptr;
+  const bool use_decay = dp && !isnan(dp[0]);
+  const int64_t groups = (n_out + (int64_t)RT * up - 1) / ((int64_t)RT * up);  // groups of RT * up consecutive outputs
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups * up; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j0 = (g / up) * ((int64_t)RT * up) + (g % up);
+    if (j0 >= n_out) continue;
+    const int64_t t0 = (j0 + n_pre_remove) * down - n_pre_pad;  // >= 0 for every output (n_pre_remove * down >= n_pre_pad)
+    const int64_t phi = t0 % up, k0 = t0 / up;                   // taps phi + i * up pair with x[k0 + q * down - i]
+    double acc[RT];
+#pragma unroll
+    for (int q = 0; q < RT; ++q) acc[q] = 0.0;
+    const int64_t n_i = phi < ntaps ? (ntaps - 1 - phi) / up + 1 : 0;
+    for (int64_t i = 0; i < n_i; ++i) {
+      const double h = taps[phi + i * up];
+#pragma unroll
+      for (int q = 0; q < RT; ++q) {
+        const int64_t k = k0 + (int64_t)q * down - i;
+        if (k >= 0 && k < n) {
+          double xv = x[k];
+          if (use_decay) xv *= decay_gain(dp, k);
+          acc[q] += xv * h;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RT; ++q) {
+      const int64_t j = j0 + (int64_t)q * up;
+      if (j < n_out) dst[(size_t)r * ld_dst + j] = acc[q];
+    }
   }
 }
 
@@ -122,8 +167,16 @@ int32_t impb_window_resample(impb_ctx* ctx, const double* src, int64_t ld_src, i
   const unsigned bx = (unsigned)std::min<int64_t>((n_out + thr - 1) / thr, 4096);
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = (int)std::min<int64_t>(65535, batch - b0);
-    k_resample<<<dim3(bx, nb), thr, 0, st>>>(src + (size_t)b0 * ld_src, ld_src, n, decay ? decay + b0 * 4 : nullptr, taps,
-                                            ntaps, u, d, n_pre_pad, n_pre_remove, n_out, dst + (size_t)b0 * ld_dst, ld_dst);
+    static const bool no_tile = getenv("IMPB_RESAMPLE_PLAIN") != nullptr;
+    if (u > 1 && n_out >= 8 * (int64_t)u && !no_tile) {
+      const unsigned bt = (unsigned)std::min<int64_t>(((n_out + 3) / 4 + thr - 1) / thr + 1, 4096);
+      k_resample_tiled<4><<<dim3(bt, nb), thr, 0, st>>>(src + (size_t)b0 * ld_src, ld_src, n, decay ? decay + b0 * 4 : nullptr,
+                                                        taps, ntaps, u, d, n_pre_pad, n_pre_remove, n_out,
+                                                        dst + (size_t)b0 * ld_dst, ld_dst);
+    } else {
+      k_resample<<<dim3(bx, nb), thr, 0, st>>>(src + (size_t)b0 * ld_src, ld_src, n, decay ? decay + b0 * 4 : nullptr, taps,
+                                              ntaps, u, d, n_pre_pad, n_pre_remove, n_out, dst + (size_t)b0 * ld_dst, ld_dst);
+    }
   }
   IMPB_CUDA(cudaGetLastError());
   return IMPB_OK;
