@@ -13,18 +13,27 @@ using namespace impb;
 
 namespace {
 
-__global__ void __launch_bounds__(256)
+constexpr int kDftThreads = 1024;
+
+__global__ void __launch_bounds__(kDftThreads)
 k_dft_bin_abs(const double* __restrict__ x, int64_t ld, int64_t n, int64_t k, double* __restrict__ out) {
-  __shared__ double red[16];
+  __shared__ double red[2 * (kDftThreads / 32)];
   const double* p = x + (size_t)blockIdx.x * ld;
   double re = 0.0, im = 0.0;
-  for (int64_t j = threadIdx.x; j < n; j += 256) {
-    // phase = 2 pi (k j mod n) / n, reduced in integers so that sincospi sees an argument in [0, 2)
-    const int64_t m = (int64_t)(((unsigned __int128)(uint64_t)k * (uint64_t)j) % (uint64_t)n);
+  // phase = 2 pi (k j mod n) / n, reduced in integers so that sincospi sees an argument in [0, 2).  The residue is
+  // carried along the thread's stride (one 128-bit modulo per thread, then add-and-wrap).
+  const uint64_t un = (uint64_t)n;
+  uint64_t m = (uint64_t)(((unsigned __int128)(uint64_t)k * (uint64_t)threadIdx.x) % un);
+  const uint64_t step = (uint64_t)(((unsigned __int128)(uint64_t)k * (uint64_t)kDftThreads) % un);
+  const double inv_n = 2.0 / (double)n;
+  for (int64_t j = threadIdx.x; j < n; j += kDftThreads) {
     double s, c;
-    sincospi(2.0 * (double)m / (double)n, &s, &c);
-    re += p[j] * c;
-    im -= p[j] * s;
+    sincospi((double)m * inv_n, &s, &c);
+    const double v = p[j];
+    re += v * c;
+    im -= v * s;
+    m += step;
+    if (m >= un) m -= un;
   }
   for (int o = 16; o; o >>= 1) {
     re += __shfl_xor_sync(0xffffffffu, re, o);
@@ -34,7 +43,7 @@ k_dft_bin_abs(const double* __restrict__ x, int64_t ld, int64_t n, int64_t k, do
   __syncthreads();
   if (threadIdx.x == 0) {
     re = im = 0.0;
-    for (int w = 0; w < 8; ++w) { re += red[2 * w]; im += red[2 * w + 1]; }
+    for (int w = 0; w < kDftThreads / 32; ++w) { re += red[2 * w]; im += red[2 * w + 1]; }
     out[blockIdx.x] = hypot(re, im);
   }
 }
@@ -66,7 +75,7 @@ int32_t impb_dft_bin_abs(impb_ctx* ctx, const double* x, int64_t ld, int64_t n, 
   cudaStream_t st = (cudaStream_t)stream;
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const int64_t nb = std::min<int64_t>(65535, batch - b0);
-    k_dft_bin_abs<<<(unsigned)nb, 256, 0, st>>>(x + (size_t)b0 * ld, ld, n, k, out + b0);
+    k_dft_bin_abs<<<(unsigned)nb, kDftThreads, 0, st>>>(x + (size_t)b0 * ld, ld, n, k, out + b0);
   }
   IMPB_CUDA(cudaGetLastError());
   return IMPB_OK;

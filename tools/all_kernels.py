@@ -22,6 +22,24 @@ batch = torch.from_numpy(base).cuda()[None].repeat(S, 1, 1).contiguous()
 disp = BatchDispatcher(est, synth.LAYOUT_71)
 
 
+def next_rows(h):
+    """room correction, headphone compensation on an uncropped (non-5-smooth) length,
+    channel balance, virtual bass."""
+    from impulcifer_pip313_b200 import FrequencyResponse
+    from impulcifer_pip313_b200 import room_correction as rc
+    from impulcifer_pip313_b200.virtual_bass import apply_virtual_bass_to_hrir
+    grid = FrequencyResponse.generate_frequencies(f_step=1.01, f_min=10, f_max=24000)
+    lf = np.log10(grid)
+    target = FrequencyResponse(name='t', frequency=grid.copy(), raw=-1.2 * (lf - 3.0))
+    rc.calculate_specific_room_corrections(h.copy(), target, mic_calibration=None, limit=400)
+    raw = HRIR(est)
+    raw.ingest(base, 48000, synth.LAYOUT_71)
+    rc.headphone_compensation(raw)
+    hb = h.copy()
+    hb.correct_channel_balance('avg')
+    apply_virtual_bass_to_hrir(h.copy())
+
+
 def one_pass():
     res = disp.process(batch)
     post = disp.postprocess(res)
@@ -33,6 +51,7 @@ def one_pass():
     h.crop_tails()
     h.decay_times()
     h.calculate_reflection_levels()
+    next_rows(h)
     h.normalize()
     h.resample(44100)
     h.pcm_frames()
