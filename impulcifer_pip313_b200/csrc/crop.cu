@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "exact_div.cuh"
 
 using namespace impb;
 
@@ -289,9 +290,10 @@ struct SqView {  // squared, peak-normalised analysis segment  sq[i] = (v[pk+i] 
   bool norm;
   const double* blk;  // shared-memory sums of aligned blocks of `bs` samples (nullptr: not built)
   int bs;
+  ExactDivisor div;   // division by mx with the reciprocal rounded once per row
   __device__ __forceinline__ double operator()(int64_t i) const {
     const double s = (*p)[pk + i];
-    const double v = norm ? __ddiv_rn(s, mx) : s;
+    const double v = norm ? div(s) : s;  // == __ddiv_rn(s, mx), see exact_div.cuh
     return __dmul_rn(v, v);
   }
 };
@@ -449,31 +451,36 @@ __global__ void __launch_bounds__(256) k_lb_blocksums(const double* __restrict__
   const int bs = lb_block_size(ns);
   const int nblk = (int)((ns + bs - 1) / bs);
   const double mx = __longlong_as_double((long long)segmax[r]);
-  const SqView sq{&ir, pk, mx, mx >= kEps, nullptr, bs};
+  const SqView sq{&ir, pk, mx, mx >= kEps, nullptr, bs, ExactDivisor(mx)};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (nblk + gridDim.y - 1) / gridDim.y;
   const int k_end = min(nblk, (int)(blockIdx.y + 1) * per);
-  for (int k0 = blockIdx.y * per + warp; k0 < k_end; k0 += 32) {  // 8 warps x 4 blocks in flight
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k0 = blockIdx.y * per + warp; k0 < k_end; k0 += 64) {  // 8 warps x 8 blocks in flight
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int k = k0 + u * 8;
       if (k < k_end) {
         const int64_t a = (int64_t)k * bs, b = min(ns, a + bs);
         for (int64_t i = a + lane; i < b; i += 32) acc[u] += sq(i);
       }
     }
-    // four xor-butterfly reductions packed into one: after the offset-16 step a lane only carries two of the four
-    // sums, after the offset-8 step one (6 double shuffles instead of 20).  Every partial sum has the same two
-    // operands as in the plain butterfly, so the results are bit-identical; lane 8u ends up with block u.
-    const bool hi16 = lane & 16, hi8 = lane & 8;
-    double x0 = hi16 ? acc[2] : acc[0], x1 = hi16 ? acc[3] : acc[1];
-    x0 += __shfl_xor_sync(0xffffffffu, hi16 ? acc[0] : acc[2], 16);
-    x1 += __shfl_xor_sync(0xffffffffu, hi16 ? acc[1] : acc[3], 16);
-    double y = (hi8 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, hi8 ? x0 : x1, 8);
-    for (int o = 4; o; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
-    const int k = k0 + (lane >> 3) * 8;
-    if ((lane & 7) == 0 && k < k_end) blk[(size_t)r * LB_MAXBLK + k] = y;
+    // eight xor-butterfly reductions packed into one: after the offset-16 step a lane only carries four of the eight
+    // sums, after offset 8 two, after offset 4 one (9 double shuffles instead of 40).  Every partial sum has the
+    // same two operands as in the plain butterfly, so the results are bit-identical; lane 4u ends up with block u.
+    const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+    double x4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      x4[i] = (hi16 ? acc[4 + i] : acc[i]) + __shfl_xor_sync(0xffffffffu, hi16 ? acc[i] : acc[4 + i], 16);
+    double y2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      y2[i] = (hi8 ? x4[2 + i] : x4[i]) + __shfl_xor_sync(0xffffffffu, hi8 ? x4[i] : x4[2 + i], 8);
+    double y = (hi4 ? y2[1] : y2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? y2[0] : y2[1], 4);
+    for (int o = 2; o; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+    const int k = k0 + (lane >> 2) * 8;
+    if ((lane & 3) == 0 && k < k_end) blk[(size_t)r * LB_MAXBLK + k] = y;
   }
 }
 
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict
   const int64_t ns = stop - pk;  // >= 1 because pk <= n_ir - 1
   // the two full reads of the window (max, block sums of sq) were done by grid-wide kernels
   const double mx = __longlong_as_double((long long)segmax[r]);
-  SqView sq{&ir, pk, mx, mx >= kEps, sh.blk, lb_block_size(ns)};
+  SqView sq{&ir, pk, mx, mx >= kEps, sh.blk, lb_block_size(ns), ExactDivisor(mx)};
   {
     const int nblk = (int)((ns + sq.bs - 1) / sq.bs);
     const double* mine = blk_g + (size_t)r * LB_MAXBLK;

@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "exact_div.cuh"
 
 using namespace impb;
 
@@ -90,16 +91,18 @@ k_decay_times(const double* __restrict__ x, const int64_t* __restrict__ offsets,
   double m = 0.0;
   for (int64_t j = tid; j < nd; j += DT_THREADS) m = fmax(m, fabs(d[j]));
   m = block_max(m, sh);
+  const ExactDivisor by_m(m);  // bit-identical to d[j] / m (exact_div.cuh): one reciprocal per row
   double acc = 0.0;
-  for (int64_t j = tid; j < min(knee, nd); j += DT_THREADS) { const double v = fabs(d[j] / m); acc += v * v; }
+  for (int64_t j = tid; j < min(knee, nd); j += DT_THREADS) { const double v = fabs(by_m(d[j])); acc += v * v; }
   const double denom = block_sum(acc, sh);
+  const ExactDivisor by_denom(denom);
 
   // backward integral S[i] = sum_{j=i..kk} sq[j] / denom  (i < kk), chunked suffix scan
   const int64_t cnt = kk + 1;
   const int64_t C = (cnt + DT_THREADS - 1) / DT_THREADS;
   const int64_t lo = min((int64_t)tid * C, cnt), hi = min(lo + C, cnt);
   acc = 0.0;
-  for (int64_t j = hi - 1; j >= lo; --j) { const double v = fabs(d[j] / m); acc += (v * v) / denom; }
+  for (int64_t j = hi - 1; j >= lo; --j) { const double v = fabs(by_m(d[j])); acc += by_denom(v * v); }
   sh.run[tid] = acc;
   if (tid < 6) sh.first[tid] = (long long)kk;  // "not found"
   __syncthreads();
@@ -113,8 +116,8 @@ k_decay_times(const double* __restrict__ x, const int64_t* __restrict__ offsets,
     long long fi[6] = {kk, kk, kk, kk, kk, kk};
     double s = sh.run[tid];
     for (int64_t j = hi - 1; j >= lo; --j) {
-      const double v = fabs(d[j] / m);
-      s += (v * v) / denom;
+      const double v = fabs(by_m(d[j]));
+      s += by_denom(v * v);
       if (j < kk) {
         const double db = 10.0 * log10(s);
         sdb[j] = db;
@@ -141,10 +144,11 @@ k_decay_times(const double* __restrict__ x, const int64_t* __restrict__ offsets,
     double m2 = 0.0;
     for (int64_t j = tid; j < La; j += DT_THREADS) m2 = fmax(m2, fabs(a[j]));
     m2 = block_max(m2, sh);
+    const ExactDivisor by_m2(m2);
     const int64_t C2 = (La + DT_THREADS - 1) / DT_THREADS;
     const int64_t l2 = min((int64_t)tid * C2, La), h2 = min(l2 + C2, La);
     acc = 0.0;
-    for (int64_t j = l2; j < h2; ++j) { const double v = a[j] / m2; acc += v * v; }
+    for (int64_t j = l2; j < h2; ++j) { const double v = by_m2(a[j]); acc += v * v; }
     __syncthreads();
     sh.run[tid] = acc;
     __syncthreads();
@@ -155,7 +159,7 @@ k_decay_times(const double* __restrict__ x, const int64_t* __restrict__ offsets,
     __syncthreads();
     double s = sh.run[tid];
     if (tid == 0) pre[0] = 0.0;
-    for (int64_t j = l2; j < h2; ++j) { const double v = a[j] / m2; s += v * v; pre[j + 1] = s; }
+    for (int64_t j = l2; j < h2; ++j) { const double v = by_m2(a[j]); s += v * v; pre[j + 1] = s; }
     __syncthreads();
     const int64_t len_avg = La - W + 1;
     const int64_t fit_s = max((int64_t)((double)kk * 0.1), avg_off);
