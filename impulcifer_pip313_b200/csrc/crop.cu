@@ -291,11 +291,11 @@ struct SqView {  // squared, peak-normalised analysis segment  sq[i] = (v[pk+i] 
   const double* blk;  // shared-memory sums of aligned blocks of `bs` samples (nullptr: not built)
   int bs;
   ExactDivisor div;   // division by mx with the reciprocal rounded once per row
-  __device__ __forceinline__ double operator()(int64_t i) const {
-    const double s = (*p)[pk + i];
+  __device__ __forceinline__ double of(double s) const {
     const double v = norm ? div(s) : s;  // == __ddiv_rn(s, mx), see exact_div.cuh
     return __dmul_rn(v, v);
   }
+  __device__ __forceinline__ double operator()(int64_t i) const { return of((*p)[pk + i]); }
 };
 
 // Every statistic of decay_params is a mean of sq over a contiguous range.  The samples are read (and divided)
@@ -455,14 +455,33 @@ __global__ void __launch_bounds__(256) k_lb_blocksums(const double* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (nblk + gridDim.y - 1) / gridDim.y;
   const int k_end = min(nblk, (int)(blockIdx.y + 1) * per);
+  // segment sample i is ir[pk + i] = ir.p[pk + i - sh] with weight 1 when lo <= pk + i < hi and pk + i - sh >= fade_len
+  const int ns32 = (int)ns;  // ns <= 2 fs
+  const int in_lo = (int)min(max(max(ir.lo - pk, ir.fade_len + ir.sh - pk), (int64_t)0), ns);
+  const int in_hi = (int)max(min(ir.hi - pk, ns), (int64_t)0);
+  const double* direct = ir.p + (pk - ir.sh);
   for (int k0 = blockIdx.y * per + warp; k0 < k_end; k0 += 64) {  // 8 warps x 8 blocks in flight
     double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (bs == 32 && k0 * 32 >= in_lo && min(ns32, (k0 + 57) * 32) <= in_hi) {
+      // one sample per lane and block, all of them inside the unfaded valid part of the view: eight predicated
+      // loads issued back to back (no control flow between them), then the arithmetic.  A lane without a sample
+      // contributes +0.0, which is what its untouched accumulator held before.
+      double v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int k = k0 + u * 8;
-      if (k < k_end) {
-        const int64_t a = (int64_t)k * bs, b = min(ns, a + bs);
-        for (int64_t i = a + lane; i < b; i += 32) acc[u] += sq(i);
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * 8, i = k * 32 + lane;
+        v[u] = (k < k_end && i < ns32) ? __ldg(direct + i) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = sq.of(v[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * 8;
+        if (k < k_end) {
+          const int64_t a = (int64_t)k * bs, b = min(ns, a + bs);
+          for (int64_t i = a + lane; i < b; i += 32) acc[u] += sq(i);
+        }
       }
     }
     // eight xor-butterfly reductions packed into one: after the offset-16 step a lane only carries four of the eight
