@@ -791,16 +791,27 @@ __global__ void __launch_bounds__(256) k_gather_window(const double* __restrict_
   const int64_t s0 = src_start[r], sh = shift ? shift[r] : 0;
   const int64_t lo = valid_lo ? valid_lo[r] : 0, hi = valid_hi ? valid_hi[r] : out_len;
   const int64_t fo0 = out_len - fade_out_len;
-  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < out_len; j += (int64_t)gridDim.x * blockDim.x) {
-    double v = 0.0;
-    if (j >= lo && j < hi) {
-      const int64_t m = j - sh;  // index into the head-cropped array
-      v = src[s0 + m];
-      if (m < fade_in_len) v = __dmul_rn(v, fade_in[m]);
+  // a block walks spans of 4 x 256 samples; the four source loads of a thread are issued before any of the
+  // dependent fade / gain arithmetic and stores (no control flow between them)
+  const double* from = src + (s0 - sh);
+  for (int64_t base = blockIdx.x * (int64_t)1024; base < out_len; base += (int64_t)gridDim.x * 1024) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = base + u * 256 + threadIdx.x;
+      v[u] = (j < out_len && j >= lo && j < hi) ? from[j] : 0.0;
     }
-    if (j >= fo0 && fade_out_len > 0) v = __dmul_rn(v, fade_out[j - fo0]);
-    if (apply_gain) v = __dmul_rn(v, gain);
-    dst[(size_t)r * ld_dst + j] = v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = base + u * 256 + threadIdx.x;
+      if (j >= out_len) break;
+      double w = v[u];
+      const int64_t m = j - sh;  // index into the head-cropped array
+      if (j >= lo && j < hi && m < fade_in_len) w = __dmul_rn(w, fade_in[m]);
+      if (j >= fo0 && fade_out_len > 0) w = __dmul_rn(w, fade_out[j - fo0]);
+      if (apply_gain) w = __dmul_rn(w, gain);
+      dst[(size_t)r * ld_dst + j] = w;
+    }
   }
 }
 
