@@ -61,7 +61,7 @@ out = ["# Round 1 — every kernel of the hot path: device time and achieved HBM
        "(after the same command exited 0 without ncu).  One pass = `BatchDispatcher.process` + `postprocess` on 32 synthetic 7.1 "
        "sets (448 IRs) followed by the", "`HRIR` chain on one set (ingest, crop, align, decay times, reflection levels, "
        "room correction, headphone compensation on the uncropped length (chirp-z), channel balance, virtual bass, "
-       "normalize, resample, PCM packing; `k_dft_bin_abs` was captured before its residue-stride rewrite, 370 -> ~60 us).  Times under ncu are",
+       "normalize, resample, PCM packing).  Times under ncu are",
        f"serialised and cold-cache.  HBM % is against the measured copy peak {hbm:.1f} GB/s (`MEASURED_PEAKS.json`).", "",
        "| kernel | launches | time us | share | DRAM read MB | DRAM write MB | achieved GB/s | % of HBM peak |",
        "|---|---|---|---|---|---|---|---|"]
