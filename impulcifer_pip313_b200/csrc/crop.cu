@@ -179,6 +179,17 @@ __global__ void __launch_bounds__(256) k_first_peak(const double* __restrict__ x
       if (peak_at(p, n, i, m, v > 0 ? 1.0 : -1.0, height, &mid)) atomicMin(&s[r].first_peak, (unsigned long long)mid);
     };
     int64_t i = lo + threadIdx.x;
+    if (lo >= max(p.lo, p.fade_len + p.sh) && hi <= p.hi) {
+      // the chunk lies in the unfaded valid part of the view: eight plain loads per thread, nothing between them
+      const double* q = p.p - p.sh;
+      for (; i + 1792 < hi; i += 2048) {
+        double a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = q[i + u * 256];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) visit(i + u * 256, a[u]);
+      }
+    }
     for (; i + 768 < hi; i += 1024) {  // four independent loads in flight per thread
       const double a0 = p[i], a1 = p[i + 256], a2 = p[i + 512], a3 = p[i + 768];
       visit(i, a0); visit(i + 256, a1); visit(i + 512, a2); visit(i + 768, a3);
