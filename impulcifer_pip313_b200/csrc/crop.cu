@@ -283,17 +283,6 @@ __device__ __forceinline__ double block_sum(double v, LundebyShared& sh) {
   return t;
 }
 
-__device__ __forceinline__ double block_max(double v, LundebyShared& sh) {
-  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = 0.0;
-#pragma unroll
-  for (int w = 0; w < LB_THREADS / 32; ++w) t = fmax(t, sh.red[w]);
-  return t;
-}
-
 struct SqView {  // squared, peak-normalised analysis segment  sq[i] = (v[pk+i] / mx)^2
   const RowView* p;
   int64_t pk;
@@ -310,36 +299,9 @@ struct SqView {  // squared, peak-normalised analysis segment  sq[i] = (v[pk+i] 
 };
 
 // Every statistic of decay_params is a mean of sq over a contiguous range.  The samples are read (and divided)
-// ONCE into per-block partial sums kept in shared memory; a range sum is then whole blocks from shared memory
-// plus at most 2*bs edge samples from HBM.  No prefix-sum differences are taken, so there is no cancellation.
-__device__ void build_block_sums(SqView& sq, int64_t ns, LundebyShared& sh) {
-  int bs = 32;
-  while ((ns + bs - 1) / bs > LB_MAXBLK) bs <<= 1;
-  const int nblk = (int)((ns + bs - 1) / bs);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NW = LB_THREADS / 32;
-  for (int k0 = warp; k0 < nblk; k0 += 4 * NW) {  // four blocks per warp iteration: independent loads in flight
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k = k0 + u * NW;
-      if (k < nblk) {
-        const int64_t a = (int64_t)k * bs, b = min(ns, a + bs);
-        for (int64_t i = a + lane; i < b; i += 32) acc[u] += sq(i);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      for (int o = 16; o; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-      const int k = k0 + u * NW;
-      if (lane == 0 && k < nblk) sh.blk[k] = acc[u];
-    }
-  }
-  __syncthreads();
-  sq.blk = sh.blk;
-  sq.bs = bs;
-}
-
+// ONCE into per-block partial sums (k_lb_blocksums, copied to shared memory by k_lundeby); a range sum is then whole
+// blocks from shared memory plus at most 2*bs edge samples from HBM.  No prefix-sum differences are taken, so there
+// is no cancellation.
 // partial (per-thread) sum of sq over [a, b) for threads `tid` of `nthr` cooperating threads
 __device__ __forceinline__ double range_partial(const SqView& sq, int64_t a, int64_t b, int tid, int nthr) {
   double acc = 0.0;
