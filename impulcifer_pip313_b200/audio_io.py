@@ -36,11 +36,13 @@ def read_wav(file_path, expand=False):
 
 
 def quantize_pcm(data: np.ndarray, bit_depth: int) -> np.ndarray:
-    """libsndfile float -> PCM conversion (``lrint(x * 2**(bits-1))`` with clipping)."""
+    """libsndfile double -> PCM conversion with clipping on (what python-soundfile selects): every depth is
+    ``lrint(x * 2**31)`` clipped to int32, PCM_16 / PCM_24 keep the top 16 / 24 bits of it (``>> 16`` / ``>> 8``,
+    libsndfile pcm.c ``d2les_clip_array`` / ``d2let_clip_array``) — a floor, not a round at the target depth."""
     if bit_depth not in (16, 24, 32):
         raise ValueError('Invalid bit depth. Accepted values are 16, 24 and 32.')
-    full = 2.0 ** (bit_depth - 1)
-    q = np.clip(np.rint(np.asarray(data, dtype=np.float64) * full), -full, full - 1)
+    q = np.clip(np.rint(np.asarray(data, dtype=np.float64) * 2.0 ** 31), -2.0 ** 31, 2.0 ** 31 - 1).astype(np.int64)
+    q >>= 32 - bit_depth
     return q.astype(np.int16 if bit_depth == 16 else np.int32)
 
 

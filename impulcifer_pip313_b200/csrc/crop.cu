@@ -260,7 +260,7 @@ int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double he
 // Lundeby: one CTA per impulse response
 // ------------------------------------------------------------------------------------------------
 constexpr int LB_THREADS = 512;
-constexpr int LB_MAXWIN = 4096;
+constexpr int LB_MAXWIN = 4096;  // >= the 4000-window upper bound of the refined pass (proof at its use)
 
 constexpr int LB_MAXBLK = 3072;  // partial sums of the squared window: blocks of bs = 32, 64, ... samples
 
@@ -559,11 +559,12 @@ __global__ void __launch_bounds__(LB_THREADS) k_lundeby(const double* __restrict
   w = max((int64_t)((double)ns / (double)n2), (int64_t)1);
   const int64_t n_t = n2;              // length of t_windows (kept even if the windows array is shortened)
   if (n2 * w > ns) n2 = ns / w;
-  if (n2 > LB_MAXWIN) {
-    // Pathological (decay faster than ~60 dB in 10 ms): the reference would build > 4096 windows.
-    // Report the first-pass result rather than silently diverging; documented in DESIGN.md.
-    LB_RETURN(pk, pk + nearest_t(knee_t, step, ns), noise, w);
-  }
+  // n2 <= 4000 < LB_MAXWIN always: the first-pass regression runs over window levels clamped to [-200 dB, 0 dB]
+  // (EPSILON = 1e-20 floor, peak normalised to 1) at 30 ms spacing, and an OLS slope over >= 2 such points is at most
+  // 200 dB / 30 ms, so wd >= 10 / (3 * 6667 dB/s) = 0.5 ms and n2 = (ns / fs) / wd <= 2 s / 0.5 ms
+  // (tests: test_lundeby_steepest_possible_decay drives the reference to 3840 windows).  Not a tolerance: an
+  // assertion — a violated bound stops the launch with a device error instead of returning a different integer.
+  if (n2 > LB_MAXWIN) __trap();
   fill_windows(sq, (int)n2, w, sh);
   const int nw = (int)n2;
   const double t_win_last = (double)(n_t - 1) * wd + wd / 2;

@@ -8,6 +8,7 @@
 // The transforms reuse the tile-FFT engine (fft2d.cuh) with exact-length plans; spectra stay in position
 // ("scrambled") order between a forward and an inverse transform, so no reordering pass exists.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -231,6 +232,8 @@ struct impb_minphase {
   Fft2D<double> big;     // length nf
   Fft2D<double> small;   // length numtaps
   double* hamming = nullptr;  // [numtaps]
+  double* nyq_S = nullptr;    // [nf/2 + 1] kernel of the Nyquist-bin imprint (see NyquistImprint below)
+  double win_sum = 0.0;       // sum(hamming)
   int64_t chunk = 256;
 };
 
@@ -253,38 +256,105 @@ struct FirwinSpec {
   double step_f;   // (fs // 2) / (n - 1)         : np.linspace(0, fs // 2, n)
   double f_stop;
   __device__ __forceinline__ double fgrid(int64_t i) const { return i == n - 1 ? f_stop : __dmul_rn((double)i, step_f); }
-  __device__ __forceinline__ double2 at(int bidx, int64_t k) const {
+  // np.interp(x_kk, freq, gain) at firwin2 grid point kk in [0, nf/2]; *x_out = the grid frequency
+  __device__ __forceinline__ double fx_at(int bidx, int64_t kk, double* x_out) const {
     const int64_t half = nf / 2;
-    const bool mirror = k > half;
-    const int64_t kk = mirror ? nf - k : k;
     const double x = kk == half ? nyq : __dmul_rn((double)kk, step_x);
-    // np.interp(x, freq, gain)
+    *x_out = x;
     const double* g = gain + (size_t)bidx * ld;
     int64_t j = (int64_t)floor(x / step_f);
     j = max((int64_t)0, min(j, n - 1));
     while (j > 0 && fgrid(j) > x) --j;
     while (j < n - 1 && fgrid(j + 1) <= x) ++j;
-    double fx;
-    if (j == n - 1) {
-      fx = g[j];
-    } else {
-      const double fj = fgrid(j);
-      if (fj == x) {
-        fx = g[j];
-      } else {
-        const double slope = __ddiv_rn(g[j + 1] - g[j], fgrid(j + 1) - fj);
-        fx = __dadd_rn(__dmul_rn(slope, x - fj), g[j]);
-      }
-    }
-    const double ang = __dmul_rn(__dmul_rn(b, x), rnyq);
+    if (j == n - 1) return g[j];
+    const double fj = fgrid(j);
+    if (fj == x) return g[j];
+    const double slope = __ddiv_rn(g[j + 1] - g[j], fgrid(j + 1) - fj);
+    return __dadd_rn(__dmul_rn(slope, x - fj), g[j]);
+  }
+  // the reference's phase-ramp angle at x, with its exact rounding sequence
+  __device__ __forceinline__ double angle(double x) const { return __dmul_rn(__dmul_rn(b, x), rnyq); }
+  __device__ __forceinline__ double2 at(int bidx, int64_t k) const {
+    const int64_t half = nf / 2;
+    const bool mirror = k > half;
+    const int64_t kk = mirror ? nf - k : k;
+    double x;
+    const double fx = fx_at(bidx, kk, &x);
     double sn, cs;
-    sincos(ang, &sn, &cs);
+    sincos(angle(x), &sn, &cs);
     double2 v = make_double2(fx * cs, fx * sn);
     if (kk == 0 || kk == half) v.y = 0.0;  // c2r transforms ignore these imaginary parts
     if (mirror) v.y = -v.y;
     return v;
   }
 };
+
+// ---- Nyquist-bin imprint --------------------------------------------------------------------------------
+// H[n_fft/2] = sum_n (-1)^n h[n] of the type-II filter is analytically zero; the ~1e-12 the reference's log sees
+// there is the imprint of the ROUNDED phase-ramp angles a_k = fl(fl(b x_k) / nyq) of firwin2
+// (scipy/signal/_fir_filter_design.py: fx2 = fx * exp(-(numtaps-1)/2 * 1j*pi*x/nyq)): with a_k = phi_k + d_k,
+// phi_k = -pi (numtaps-1) k / nf the exact linear phase, bin k contributes (2/nf) fx_k cos(psi_kn + d_k) to h[n],
+// psi_kn = pi k (2n - numtaps + 1) / nf.  The cos(psi) part is symmetric about the filter centre and cancels in
+// the alternating sum; what is left is, to first order in d_k ~ 1e-12,
+//     H[nyq] = -(2/nf) sum_k fx_k d_k S_k  +  (1/nf) fx_{nf/2} cos(a_{nf/2}) sum(w),
+//     S_k = sum_n (-1)^n w[n] sin(psi_kn)                      (depends on the window only: plan constant).
+// d_k is known to ~1e-28 (double-double pi, (numtaps-1) k / nf is exact because nf is a power of two), so this
+// sum of 32 768 terms of size 1e-12 is good to ~1e-6 relative, whereas ANY double FFT — the reference's pocketfft
+// included — only knows the bin to ~1e-16 absolute = 1e-4 relative.  The homomorphic transform turns a relative
+// error e of this one bin into ~7e-5 e of the FIR peak (tools/minphase_localise.py), so a transform-computed value
+// (1e-14 absolute with a different FFT algorithm) costs 5e-6 of peak while the analytic one lands within the
+// reference's own noise (~1e-8 of peak).
+__global__ void __launch_bounds__(256) k_mp_nyq_table(const double* __restrict__ win, int64_t numtaps, int64_t nf,
+                                                      double* __restrict__ S) {
+  const int64_t k = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t n = threadIdx.x; n < numtaps; n += blockDim.x) {
+    const int64_t m = (k * (2 * n - numtaps + 1)) % (2 * nf);  // psi = pi m / nf, reduced exactly in integers
+    const double sn = sinpi((double)m / (double)nf);
+    acc += (n & 1) ? -win[n] * sn : win[n] * sn;
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    S[k] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mp_nyq_imprint(const FirwinSpec spec, int64_t numtaps,
+                                                        const double* __restrict__ S, double win_sum,
+                                                        double* __restrict__ out) {
+  const int bidx = blockIdx.x;
+  const int64_t half = spec.nf / 2;
+  const double PI_HI = 3.141592653589793116, PI_LO = 1.2246467991473532e-16;
+  double acc = 0.0;
+  for (int64_t k = 1 + threadIdx.x; k < half; k += blockDim.x) {
+    double x;
+    const double fx = spec.fx_at(bidx, k, &x);
+    const double a = spec.angle(x);
+    const double t = (double)((numtaps - 1) * k) / (double)spec.nf;  // exact: nf is a power of two
+    const double p_hi = PI_HI * t;
+    const double p_lo = fma(PI_HI, t, -p_hi) + PI_LO * t;
+    const double d = (a + p_hi) + p_lo;  // a_k - phi_k
+    acc += fx * d * S[k];
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    double x;
+    const double fxh = spec.fx_at(bidx, half, &x);
+    double sn, cs;
+    sincos(spec.angle(x), &sn, &cs);
+    out[bidx] = -(2.0 / (double)spec.nf) * t + (fxh * cs) * win_sum / (double)spec.nf;
+  }
+}
 
 struct RowInvFirwin {  // row DIT whose input is synthesised from the gain curve
   FirwinSpec spec;
@@ -331,11 +401,12 @@ struct ColInvReal {
   }
 };
 
-struct AbsOp {  // |X| in position order
+struct AbsOp {  // |X| in position order; the Nyquist bin takes the analytic imprint (k_mp_nyq_imprint) when given
   double* mag;
   int64_t N;
-  __device__ __forceinline__ void operator()(int b, size_t pos, int64_t, double2 v) const {
-    mag[(size_t)b * N + pos] = hypot(v.x, v.y);
+  const double* nyq_val;
+  __device__ __forceinline__ void operator()(int b, size_t pos, int64_t k, double2 v) const {
+    mag[(size_t)b * N + pos] = (nyq_val && 2 * k == N) ? fabs(nyq_val[b]) : hypot(v.x, v.y);
   }
 };
 
@@ -614,7 +685,13 @@ int32_t impb_minphase_create(impb_ctx* ctx, int64_t n, const double* hamming_hos
   if (!rc) {
     cudaError_t e = cudaMalloc(&mp->hamming, mp->numtaps * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(mp->hamming, hamming_host, mp->numtaps * sizeof(double), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) rc = cuda_fail(e, "hamming upload");
+    if (e == cudaSuccess) e = cudaMalloc(&mp->nyq_S, (mp->nf / 2 + 1) * sizeof(double));
+    if (e == cudaSuccess) {
+      k_mp_nyq_table<<<(unsigned)(mp->nf / 2 + 1), 256>>>(mp->hamming, mp->numtaps, mp->nf, mp->nyq_S);
+      e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) rc = cuda_fail(e, "hamming upload / Nyquist imprint table");
+    for (int64_t i = 0; i < mp->numtaps; ++i) mp->win_sum += hamming_host[i];
   }
   if (rc) { impb_minphase_destroy(mp); return rc; }
   *out = mp;
@@ -627,12 +704,13 @@ void impb_minphase_destroy(impb_minphase* mp) {
   mp->big.release();
   mp->small.release();
   cudaFree(mp->hamming);
+  cudaFree(mp->nyq_S);
   delete mp;
 }
 
 static int64_t minphase_per_filter_bytes(const impb_minphase* mp) {
-  // complex nf | complex numtaps | real numtaps (h / cepstrum) | real numtaps (|H|) | window | minpos
-  return mp->nf * 16 + mp->numtaps * 16 + mp->numtaps * 8 + mp->numtaps * 8 + 8;
+  // complex nf | complex numtaps | real numtaps (h / cepstrum) | real numtaps (|H|) | window | minpos | nyq imprint
+  return mp->nf * 16 + mp->numtaps * 16 + mp->numtaps * 8 + mp->numtaps * 8 + 16;
 }
 
 int64_t impb_minphase_workspace_bytes(const impb_minphase* mp, int64_t batch) {
@@ -656,6 +734,8 @@ int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_t ld_gain
   double* real_buf = (double*)w;            w += cb * mp->numtaps * 8;
   double* mag = (double*)w;                 w += cb * mp->numtaps * 8;
   double* minpos = (double*)w;              w += cb * 8;
+  double* nyq_val = (double*)w;             w += cb * 8;
+  static const bool fft_nyquist = getenv("IMPB_MINPHASE_FFT_NYQUIST") != nullptr;  // diagnostic: transform-computed bin
   w = (char*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
   double* hwin = (double*)w;
   const Plan2D& pb = mp->big.p;
@@ -678,7 +758,9 @@ int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_t ld_gain
     // 2. |fft(h, n_fft)|
     RealColIn ci{real_buf, nt, nt, ws_small, mp->small.tw, ps.N, ps.N2};
     if ((rc = mp->small.col_fwd<TILE>(ci, nb, st))) return rc;
-    RowFwdOp<AbsOp> ra{ws_small, ps.N, ps.N1, ps.N2, mp->small.perm_col, mp->small.perm_row, AbsOp{mag, ps.N}};
+    k_mp_nyq_imprint<<<nb, 256, 0, st>>>(spec, nt, mp->nyq_S, mp->win_sum, nyq_val);
+    RowFwdOp<AbsOp> ra{ws_small, ps.N, ps.N1, ps.N2, mp->small.perm_col, mp->small.perm_row,
+                       AbsOp{mag, ps.N, fft_nyquist ? nullptr : nyq_val}};
     if ((rc = mp->small.row_fwd<TILE>(ra, nb, st))) return rc;
     k_min_positive<<<nb, 256, 0, st>>>(mag, ps.N, minpos);
     // 3. cepstrum = ifft(0.5 log(|H| + 1e-7 min+)).real * homomorphic window

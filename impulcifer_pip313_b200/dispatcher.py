@@ -477,6 +477,62 @@ def equalization_firs(items, room_frs, hp_left, hp_right, eq_left, eq_right, tar
     return [(spk, side, firs[i]) for i, (spk, side) in enumerate(items)]
 
 
+def decay_adjust(tasks):
+    """Batched ``process_decay_worker`` (reference ``core/parallel_workers.py:24-39``) — the work the reference
+    maps over a process pool at ``core/pipeline.py:694-716``.
+
+    ``tasks``: ``[(speaker, side, data, fs, target_seconds), ...]``.  Returns ``[(speaker, side, adjusted), ...]`` in
+    input order; ``adjusted`` is a new float64 array (the worker copies before it multiplies).  One K4 launch
+    (Lundeby parameters) and one K17 launch (Schroeder decay times) cover every response of a sampling rate, the
+    four-number window parameters are host scalars exactly as ``decay_adjustment_params`` derives them
+    (core/decay.py:355-380), and K15 applies the windows of all equal-length rows in one launch."""
+    import torch
+    from . import ops
+    from .impulse_response import _device_index
+    tasks = list(tasks)
+    if not tasks:
+        return []
+    dev = torch.device("cuda", _device_index())
+    out = [None] * len(tasks)
+    by_fs = {}
+    for i, t in enumerate(tasks):
+        by_fs.setdefault(int(t[3]), []).append(i)
+    for fs, idxs in by_fs.items():
+        rows = [np.ascontiguousarray(tasks[i][2], dtype=np.float64) for i in idxs]
+        lens = [len(r) for r in rows]
+        for i, n in zip(idxs, lens):
+            if n < 10:  # decay_params' degenerate branch has no decay time -> the reference raises TypeError
+                raise TypeError("'>' not supported between instances of 'float' and 'NoneType'")
+        flat = torch.from_numpy(np.concatenate(rows)).to(dev)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        pk, kn, nf, wn = (t.cpu().numpy() for t in ops.lundeby(flat, offs, lens, fs, max_len=max(lens)))
+        rts = ops.decay_times(flat, offs, lens, pk, kn, nf, wn, fs, max_len=max(lens))
+        params = np.full((len(idxs), 4), np.nan)
+        for r, i in enumerate(idxs):
+            target = tasks[i][4]
+            slope = None
+            for rt, level in zip(rts[r], (-10, -20, -30, -60)):
+                if np.isnan(rt) or not rt:
+                    break
+                slope = level / float(rt)
+            target_slope = -60 / target
+            if target_slope > slope:  # TypeError when nothing could be measured, as in the reference
+                continue
+            knee_time = int(kn[r]) / fs
+            start = int(pk[r]) + 2 * (fs // 1000)
+            params[r] = (start, int(kn[r]) - start, int(kn[r]), target_slope * knee_time - slope * knee_time)
+        by_len = {}
+        for r, n in enumerate(lens):
+            by_len.setdefault(n, []).append(r)
+        for n, rs in by_len.items():
+            x = torch.stack([flat[int(offs[r]):int(offs[r]) + n] for r in rs])
+            y = ops.window_resample(x, None, 1, 1, decay=params[rs]).cpu().numpy()
+            for k, r in enumerate(rs):
+                i = idxs[r]
+                out[i] = (tasks[i][0], tasks[i][1], y[k])
+    return out
+
+
 class DeviceShard:
     """Partition of recording sets over ranks (one process per GPU).  Sets are independent and never split
     (crop_heads / align / crop_tails / normalize couple all responses of a set), so the

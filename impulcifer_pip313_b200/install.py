@@ -15,7 +15,8 @@ keeps running the reference's code on top of them:
 
 and rebinds every already-imported module attribute that still points at the reference classes.  The EQ stage's
 ``parallel_map(process_equalization_worker, ...)`` call (core/pipeline.py:674-688) is routed to
-``dispatcher.equalization_firs``; every other ``parallel_map`` use keeps the reference's pools.  The module-level
+``dispatcher.equalization_firs`` and the decay stage's ``parallel_map(process_decay_worker, ...)``
+(core/pipeline.py:694-716) to ``dispatcher.decay_adjust``; every other ``parallel_map`` use keeps the reference's pools.  The module-level
 room-correction, microphone-mismatch, decay-time and virtual-bass functions are replaced by their batched twins
 (``room_correction.py``, ``microphone_deviation.py``, ``impulse_response.decay_times_batch``, ``virtual_bass.py``).
 Nothing in the reference tree is edited.  See INTEGRATION.md.
@@ -133,14 +134,18 @@ def install(verbose: bool = False):
             if new is not None:
                 d[k] = new
                 rebound += 1
-    # the process pool of the EQ stage (core/pipeline.py:674-688) -> one batched launch per stage
+    # the process pools of the EQ and decay stages (core/pipeline.py:674-688, 694-716) -> batched launches
     from core import parallel_utils as ref_pu
     pool_map = ref_pu.parallel_map
 
     def parallel_map(func, items, max_workers=None, initializer=None, initargs=(), **kw):
-        if getattr(func, '__name__', '') == 'process_equalization_worker' and len(initargs) == 8:
+        name = getattr(func, '__name__', '')
+        if name == 'process_equalization_worker' and len(initargs) == 8:
             from .dispatcher import equalization_firs
             return equalization_firs(list(items), *initargs)
+        if name == 'process_decay_worker':  # core/pipeline.py:694-716 -> K4 + K17 + K15, one launch each
+            from .dispatcher import decay_adjust
+            return decay_adjust(list(items))
         return pool_map(func, items, max_workers, initializer, initargs, **kw)
 
     parallel_map.__doc__ = pool_map.__doc__

@@ -1,17 +1,19 @@
 """TEST INFRASTRUCTURE ONLY — loader for the *unmodified* reference (115dkk/Impulcifer-pip313).
 
-Imports the reference's own hot-path modules from ``/root/reference`` so that golden vectors can be
-generated from the real implementation (``tests/golden/make_golden.py``) and so that the oracle
-restatement in ``oracle/impulcifer_oracle.py`` can be pinned against it.
+Imports the reference's own hot-path modules from the staged copy ``oracle/_ref`` (``oracle/make_ref.py``;
+git-ignored, travels to the GPU box) or, failing that, from ``/root/reference`` (build container only), so
+that golden vectors can be generated from the real implementation (``tests/golden/make_golden.py``), the
+oracle restatement in ``oracle/impulcifer_oracle.py`` can be pinned against it, the pipeline-level drop-in
+test can run the reference's own ``BRIRPipeline`` and ``bench.py --impl reference`` can time it.
 
-``/root/reference`` exists only in the build container, never on the GPU box, so nothing under
-``tests/ -m gpu``, ``bench.py`` or ``__graft_entry__.smoke()`` may import this module.
+The product package never imports this module (``tests/test_abi_cpu.py`` greps for it).
 
 Only plotting / audio-device / WAV-container modules are stubbed.  No arithmetic is restated here:
   * ``matplotlib*``, ``seaborn``, ``bokeh*``, ``sounddevice``  -> MagicMock (imported at module top by
     core/impulse_response_estimator.py:10, core/plotting/*.py)
   * ``soundfile`` -> 20-line shim over ``scipy.io.wavfile`` (PCM_32 -> float64 via /2**31, exactly what
-    libsndfile does for ``dtype='float64'``); write() quantises with ``np.round(x * 2**31)`` + clip.
+    libsndfile does for ``dtype='float64'``); write() quantises with ``np.round(x * 2**31)`` + clip
+    (PCM_16: the top 16 bits of that value, as libsndfile's clipping converters do).
   * ``nnresample`` -> the restatement in ``oracle/nnresample_port.py`` (package absent from the image;
     parity for that one step is therefore UNPINNED).
 """
@@ -22,7 +24,20 @@ from unittest.mock import MagicMock
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("IMPULCIFER_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref")          # oracle/make_ref.py: unmodified copy that travels to the GPU box
+
+
+def _default_root():
+    env = os.environ.get("IMPULCIFER_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join(_STAGED, "core", "pipeline.py")):
+        return _STAGED
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _default_root()
 
 _STUBS = [
     'matplotlib', 'matplotlib.pyplot', 'matplotlib.ticker', 'matplotlib.font_manager', 'matplotlib.figure',
@@ -55,11 +70,25 @@ def _soundfile_shim():
 
     def _write(path, data, samplerate=48000, subtype="PCM_32", **kw):
         from scipy.io import wavfile
-        data = np.asarray(data, dtype=np.float64)
+        data = np.asarray(data)
+        if data.dtype.kind == 'i':
+            # integer frames are already PCM (libsndfile i2lei / s2les / i2les: int32 -> PCM_16 keeps the top 16 bits)
+            if subtype == "PCM_32":
+                q = data.astype(np.int32) if data.dtype == np.int32 else (data.astype(np.int32) << 16)
+            elif subtype == "PCM_16":
+                q = data.astype(np.int16) if data.dtype == np.int16 else (data.astype(np.int64) >> 16).astype(np.int16)
+            else:
+                raise ValueError("shim supports PCM_16/PCM_32 only")
+            wavfile.write(path, int(samplerate), q)
+            return
+        data = data.astype(np.float64)
         if subtype == "PCM_32":
             q = np.clip(np.round(data * 2 ** 31), -2 ** 31, 2 ** 31 - 1).astype(np.int32)
         elif subtype == "PCM_16":
-            q = np.clip(np.round(data * 2 ** 15), -2 ** 15, 2 ** 15 - 1).astype(np.int16)
+            # libsndfile d2les_clip_array (python-soundfile turns SFC_SET_CLIPPING on): scale to 2^31, clip,
+            # lrint, then keep the top 16 bits (arithmetic shift = floor), NOT a round at 16-bit depth
+            q32 = np.clip(np.round(data * 2 ** 31), -2 ** 31, 2 ** 31 - 1).astype(np.int64)
+            q = (q32 >> 16).astype(np.int16)
         else:
             raise ValueError("shim supports PCM_16/PCM_32 only")
         wavfile.write(path, int(samplerate), q)
@@ -77,6 +106,38 @@ def _soundfile_shim():
     return sf
 
 
+def _tiny_png(path, *a, **k):
+    from PIL import Image
+    Image.new('RGB', (2, 2), (255, 255, 255)).save(path)
+
+
+def _plot_stubs():
+    """Plotting only: enough of pyplot for the unconditional ``_stage_plot_results`` (core/pipeline.py:783-790,
+    core/plotting/hrir_plotter.py:324-398: ``fig, ax = plt.subplots()``, ``fig.savefig`` then PIL re-opens the PNG)."""
+    plt = sys.modules['matplotlib.pyplot']
+    if not isinstance(plt, MagicMock) or plt.__dict__.get('_impb_stub'):
+        return
+
+    def subplots(*a, **k):
+        fig, ax = MagicMock(), MagicMock()
+        fig.savefig = _tiny_png
+        return fig, ax
+
+    plt.subplots = subplots
+    plt._impb_stub = True
+    sys.modules['matplotlib'].pyplot = plt
+
+
+def _patch_plotting_utils():
+    """``sync_axes`` reduces axis limits read back from real Axes; ``save_fig_as_png`` rasterises. No arithmetic
+    of the path is in either (core/plotting_utils.py:19-46, 122-128)."""
+    if not isinstance(sys.modules.get('matplotlib'), MagicMock):
+        return
+    import core.plotting_utils as pu
+    pu.sync_axes = lambda *a, **k: None
+    pu.save_fig_as_png = lambda file_path, fig, *a, **k: _tiny_png(file_path)
+
+
 _loaded = False
 
 
@@ -89,6 +150,7 @@ def load():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     for m in _STUBS:
         sys.modules.setdefault(m, MagicMock())
+    _plot_stubs()
     sys.modules.setdefault('soundfile', _soundfile_shim())
     if 'nnresample' not in sys.modules:
         here = os.path.dirname(os.path.abspath(__file__))
@@ -98,6 +160,7 @@ def load():
         sys.modules['nnresample'] = nnresample_port
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+    _patch_plotting_utils()
     _loaded = True
 
 

@@ -32,3 +32,15 @@ def rel_peak_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+# Minimum-phase FIR gates (relative to the FIR's peak).  The homomorphic transform takes log|H| at the Nyquist bin,
+# where the type-II firwin2 filter is analytically zero and the reference sees only the imprint of its own rounding
+# (1.2e-12 .. 3.5e-12 at 9 600 taps, 2e-14 .. 8e-14 at 4 800 taps); a relative error e of that ONE bin moves the FIR by
+# ~1e-4 e of its peak.  pocketfft itself only knows the bin to ~1e-16 absolute, so the reference is reproducible to
+# ~1e-8 (9 600 taps) / ~2e-7 (4 800 taps) of peak between two machines: measured, scipy's formula on the B200 box's
+# CPU against the golden recorded in the build container (profiles/r02_minphase_localise.md).  K12 evaluates the bin
+# analytically (fr.cu: k_mp_nyq_imprint) and sits at <= 1.5e-8 / <= 2.0e-7 on the same cases; the gates below are
+# that floor with headroom, not a tolerance on the transform (residual after removing the one-bin component: 1e-11).
+MINPHASE_TOL_F5 = 1e-7    # f_res = 5  -> 9 600 taps @ 48 kHz (EQ worker)
+MINPHASE_TOL_F10 = 5e-7   # f_res = 10 -> 4 800 taps @ 48 kHz (channel balance, microphone deviation)

@@ -13,6 +13,7 @@ stubs only, no arithmetic restated) and records what the reference itself comput
                          all integers, checksums of every IR, slices, FR / smoothing / min-phase vectors
   room_chain_golden.npz  room / headphone FR chains, channel-balance FIRs, microphone-mismatch estimator on the same set
   decay_chain_golden.npz decay times, reflection levels, decay-adjustment parameters, virtual bass on the same set
+  decay_window_golden.npz  ``apply_decay_window`` on fixed parameters + ``process_decay_worker`` on the same set (a11 pin)
   small_cases.npz        tiny estimators from the reference's own tests (fs=2000/0.05 s, fs=48000/1 s)
 """
 import os
@@ -370,6 +371,38 @@ def decay_chain():
           'reflection', gold['reflection'][0], 'adj', gold['decay_adjustment'][:, 1])
 
 
+def decay_window():
+    """a11 pin: the reference's own ``apply_decay_window`` (core/decay.py:383-403) on fixed parameters, and its
+    ``process_decay_worker`` (core/parallel_workers.py:24-39 = decay_adjustment_params + apply_decay_window) on
+    responses of the seeded synthetic 7.1 set."""
+    decay = ref.decay
+    pw = ref.parallel_workers
+    gold = {}
+    x = np.random.default_rng(0).standard_normal(20000)
+    gold['fixed_params'] = np.array([[100, 3000, 3100, -12.0], [0, 500, 500, -3.5], [48, 9000, 9048, -40.0],
+                                     [7, 1, 8, -6.0]])
+    for i, prm in enumerate(gold['fixed_params']):
+        y = decay.apply_decay_window(x.copy(), (int(prm[0]), int(prm[1]), int(prm[2]), float(prm[3])))
+        gold[f'fixed_out_{i}'] = y
+    est, h = _cropped_set('final')
+    keys = [(s, e) for s in h.irs for e in ('left', 'right')]
+    gold['names'] = np.array([f'{s}-{e}' for s, e in keys])
+    rows = []
+    for target in (0.05, 0.15, 2.0):
+        for k, (s, e) in enumerate(keys[:6]):
+            data = h.irs[s][e].data
+            prm = decay.decay_adjustment_params(data, est.fs, target)
+            _, _, out = pw.process_decay_worker((s, e, data, est.fs, target))
+            rows.append([target, k, -1 if prm is None else 1])
+            tag = f't{int(target * 1000)}_{s}_{e}'
+            gold[f'worker_ck_{tag}'] = checksums(out)
+            gold[f'worker_dec_{tag}'] = out[::29].copy()
+            gold[f'worker_changed_{tag}'] = np.array(not np.array_equal(out, data))
+    gold['worker_rows'] = np.array(rows)
+    np.savez_compressed(os.path.join(HERE, 'decay_window_golden.npz'), **gold)
+    print('decay_window: changed', [bool(gold[k]) for k in gold if k.startswith('worker_changed_')])
+
+
 def small_cases():
     gold = {}
     rng = np.random.default_rng(7)
@@ -430,7 +463,7 @@ def small_cases():
 
 if __name__ == '__main__':
     only = sys.argv[1:]
-    for fn in (demo_room, synth71, room_chain, decay_chain, small_cases):
+    for fn in (demo_room, synth71, room_chain, decay_chain, decay_window, small_cases):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):

@@ -125,3 +125,39 @@ def test_virtual_bass_rejects_crossover_above_nyquist(final_set):
     before = hv.irs['FL']['left'].data.copy()
     synthesize_virtual_bass(hv.irs, 48000, crossover_freq=24000)
     np.testing.assert_array_equal(hv.irs['FL']['left'].data, before)
+
+
+def test_decay_window_kernel_matches_reference():
+    """K15 against the reference's own ``apply_decay_window`` output (core/decay.py:383-403), fixed parameters."""
+    import torch
+    from impulcifer_pip313_b200 import ops
+    g = load('decay_window_golden.npz')
+    x = np.random.default_rng(0).standard_normal(20000)
+    prm = g['fixed_params']
+    xs = torch.from_numpy(np.tile(x, (len(prm), 1))).cuda()
+    got = ops.window_resample(xs, None, 1, 1, decay=prm).cpu().numpy()
+    for i in range(len(prm)):
+        assert np.max(np.abs(got[i] - g[f'fixed_out_{i}'])) <= 1e-13 * np.max(np.abs(x)), i
+
+
+def test_batched_decay_worker_matches_reference(final_set):
+    """dispatcher.decay_adjust (what install() routes ``parallel_map(process_decay_worker, ...)`` to) against the
+    reference's own worker (core/parallel_workers.py:24-39) on the synthetic 7.1 set: one batched call over all
+    (response, target) tasks, results in input order, untouched rows returned as copies."""
+    from impulcifer_pip313_b200.dispatcher import decay_adjust
+    g = load('decay_window_golden.npz')
+    keys = [tuple(n.split('-')) for n in g['names']]
+    tasks, tags = [], []
+    for target, k, _has in g['worker_rows']:
+        s, e = keys[int(k)]
+        tasks.append((s, e, final_set.irs[s][e].data, 48000, float(target)))
+        tags.append(f't{int(target * 1000)}_{s}_{e}')
+    out = decay_adjust(tasks)
+    assert [(o[0], o[1]) for o in out] == [(t[0], t[1]) for t in tasks]
+    for (s, e, y), task, tag in zip(out, tasks, tags):
+        changed = not np.array_equal(y, task[2])
+        assert changed == bool(g[f'worker_changed_{tag}']), tag
+        assert y is not task[2]
+        ref = g[f'worker_dec_{tag}']
+        assert np.max(np.abs(y[::29] - ref)) <= 1e-9 * np.max(np.abs(ref)), tag
+        assert_ck(y, g[f'worker_ck_{tag}'], what=tag)

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import impulcifer_oracle as O
-from _util import load, rel_peak_err
+from _util import MINPHASE_TOL_F5, MINPHASE_TOL_F10, load, rel_peak_err
 
 pytestmark = pytest.mark.gpu
 
@@ -293,15 +293,15 @@ def test_minphase_fir_golden(T):
     got10 = ops.minphase_fir(T.from_numpy(np.stack(gains10)).cuda(), fs).cpu().numpy()
     assert got5.shape == (4, 9600) and got10.shape == (4, 4800)
     for i in range(4):
-        # tolerance: see DESIGN.md "min-phase tolerance" (log of rounding noise at the type-II Nyquist null)
-        assert rel_peak_err(got5[i], g['minphase_f5'][i]) < 5e-6
-        assert rel_peak_err(got10[i], g['minphase_f10'][i]) < 5e-6
+        # gates: tests/_util.py MINPHASE_TOL_* (the reference's own reproducibility floor, measured)
+        assert rel_peak_err(got5[i], g['minphase_f5'][i]) < MINPHASE_TOL_F5
+        assert rel_peak_err(got10[i], g['minphase_f10'][i]) < MINPHASE_TOL_F10
         # magnitude response of the FIR (what the EQ stage actually relies on) is tight
         H_ref = np.abs(np.fft.rfft(g['minphase_f5'][i]))
         H_got = np.abs(np.fft.rfft(got5[i]))
         # ... everywhere except the Nyquist end, where the reference itself takes the log of rounding noise
         assert np.max(np.abs(H_got - H_ref)[:-8]) / np.max(H_ref) < 1e-7
-        assert np.max(np.abs(H_got - H_ref)) / np.max(H_ref) < 5e-5
+        assert np.max(np.abs(H_got - H_ref)) / np.max(H_ref) < 2e-6
 
 
 def test_resample_matches_port(T):

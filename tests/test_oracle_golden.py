@@ -9,7 +9,7 @@ import pytest
 
 import impulcifer_oracle as O
 from impulcifer_pip313_b200 import synth
-from _util import assert_ck, load, rel_peak_err
+from _util import MINPHASE_TOL_F5, MINPHASE_TOL_F10, assert_ck, load, rel_peak_err
 
 
 @pytest.fixture(scope="module")
@@ -151,10 +151,10 @@ def test_synth71_full_chain(synth_set):
         # two correct FFT libraries already differ by ~1e-7 of peak here, see DESIGN.md "min-phase tolerance"
         mp5 = O.minimum_phase_impulse_response(f, eq, fs=fs, f_res=5, normalize=False)
         assert mp5.shape == g['minphase_f5'][i].shape == (9600,)
-        assert rel_peak_err(mp5, g['minphase_f5'][i]) < 5e-6
+        assert rel_peak_err(mp5, g['minphase_f5'][i]) < MINPHASE_TOL_F5
         mp10 = O.minimum_phase_impulse_response(f, eq, fs=fs, f_res=10, normalize=True)
         assert mp10.shape == (4800,)
-        assert rel_peak_err(mp10, g['minphase_f10'][i]) < 5e-6
+        assert rel_peak_err(mp10, g['minphase_f10'][i]) < MINPHASE_TOL_F10
     rs = O.resample(irs['FL']['left'], 44100, 48000)
     assert len(rs) == len(g['resampled_FL_left_44100']) == int(np.ceil(int(g['tail']) * 147 / 160))
     assert rel_peak_err(rs, g['resampled_FL_left_44100']) < 1e-12
@@ -234,3 +234,15 @@ def test_savgol_matches_scipy():
     f = O.generate_frequencies(10, 24000, 1.01)
     assert len(f) == 783
     assert [O.window_size(f, o) for o in (1 / 3, 1 / 6, 1 / 5, 1 / 12, 1.3, 1.4, 2)] == [23, 13, 15, 7, 91, 99, 139]
+
+
+def test_apply_decay_window_matches_reference():
+    """a11 pin: oracle.apply_decay_window against the reference's own core/decay.py:383-403 output
+    (tests/golden/make_golden.py::decay_window)."""
+    g = load('decay_window_golden.npz')
+    x = np.random.default_rng(0).standard_normal(20000)
+    for i, prm in enumerate(g['fixed_params']):
+        got = O.apply_decay_window(x.copy(), (int(prm[0]), int(prm[1]), int(prm[2]), float(prm[3])))
+        assert got.shape == g[f'fixed_out_{i}'].shape
+        assert np.max(np.abs(got - g[f'fixed_out_{i}'])) <= 1e-14 * np.max(np.abs(x))
+    assert O.apply_decay_window(x, None) is x

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import impulcifer_oracle as O
-from _util import assert_ck, load, rel_peak_err
+from _util import MINPHASE_TOL_F5, MINPHASE_TOL_F10, assert_ck, load, rel_peak_err
 
 pytestmark = pytest.mark.gpu
 
@@ -119,9 +119,9 @@ def test_hrir_full_chain_matches_reference_golden(T, est48, synth_rec):
         fr2.equalize(max_gain=40, treble_f_lower=10000, treble_f_upper=fs / 2)
         assert np.max(np.abs(fr2.equalization - g['eqw_equalization'][i])) < 1e-8
         fir = fr2.minimum_phase_impulse_response(fs=fs, normalize=False, f_res=5)
-        assert fir.shape == (9600,) and rel_peak_err(fir, g['eqw_fir'][i]) < 5e-6
+        assert fir.shape == (9600,) and rel_peak_err(fir, g['eqw_fir'][i]) < MINPHASE_TOL_F5
         fr.equalization = -(fr.smoothed - np.mean(fr.smoothed))
-        assert rel_peak_err(fr.minimum_phase_impulse_response(fs=fs, f_res=10, normalize=True), g['minphase_f10'][i]) < 5e-6
+        assert rel_peak_err(fr.minimum_phase_impulse_response(fs=fs, f_res=10, normalize=True), g['minphase_f10'][i]) < MINPHASE_TOL_F10
 
     # next-row components: EQ-FIR application and set normalisation
     ir = h.irs['FL']['left'].copy()
@@ -369,7 +369,7 @@ def test_192khz_resample_smooth_minphase(T):
     fr.equalization = -(fr.smoothed - np.mean(fr.smoothed))
     fir = fr.minimum_phase_impulse_response(fs=48000, f_res=5, normalize=False)
     ref_fir = O.minimum_phase_impulse_response(f, fr.equalization, fs=48000, f_res=5, normalize=False)
-    assert fir.shape == (9600,) and rel_peak_err(fir, ref_fir) < 5e-6
+    assert fir.shape == (9600,) and rel_peak_err(fir, ref_fir) < MINPHASE_TOL_F5
 
 
 def test_equalization_firs_batch_matches_worker_golden(T):
@@ -389,7 +389,7 @@ def test_equalization_firs_batch_matches_worker_golden(T):
     out = equalization_firs([(s, e) for s, e in names], room, None, None, None, None, target, f, fs)
     assert [(s, e) for s, e, _ in out] == [(s, e) for s, e in names]
     for i, (_, _, fir) in enumerate(out):
-        assert fir.shape == (9600,) and rel_peak_err(fir, g['eqw_fir'][i]) < 5e-6
+        assert fir.shape == (9600,) and rel_peak_err(fir, g['eqw_fir'][i]) < MINPHASE_TOL_F5
 
 
 def test_magnitude_response_function(T):

@@ -4,14 +4,14 @@ FIR design + application, and the interaural microphone-mismatch estimator."""
 import numpy as np
 import pytest
 
-from _util import assert_ck, load, rel_peak_err
+from _util import MINPHASE_TOL_F5, MINPHASE_TOL_F10, assert_ck, load, rel_peak_err
 
 pytestmark = pytest.mark.gpu
 
 # dB curves: K8 magnitudes agree with numpy's rfft to ~1e-12 relative, so a dB value moves by < 1e-9
 DB_TOL = 2e-9
 # FIRs go through the homomorphic minimum-phase chain (tolerances of tests/test_ops_gpu.py)
-FIR_TOL = 5e-6
+FIR_TOL = MINPHASE_TOL_F10
 
 
 def room_curves(frequency):
