@@ -2,7 +2,8 @@
 """Headline benchmark: IR deconvolutions/s for the 6.15 s @ 48 kHz sweep (BASELINE.json), 7.1 layout.
 
     python bench.py --gpus N --steps K --warmup W              # this framework (one rank per GPU under torchrun)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's OWN CPU code (oracle/_ref) under
+                                                                     # its own pool; the oracle port if _ref is absent
 
 A "step" is one pass of the hot path over one batch of synthetic recording sets per GPU:
   deconvolution of all 14 (speaker, ear) columns of every set (K1) -> first-peak search (K2) -> pairwise
@@ -84,6 +85,70 @@ def cpu_throughput(test_signal, inv, n_oct, base_sets, sets_per_round, rounds, w
 
 
 # ---------------------------------------------------------------------------------------------------------
+# CPU arm, kind "reference": the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py) running the same
+# per-set path under its own pool, core.parallel_utils.parallel_map (a ProcessPoolExecutor per call with
+# max_workers = min(cpu_count, items), core/parallel_utils.py:97-152) — SURVEY.md 8(d).
+# ---------------------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def reference_available():
+    import ref_import
+    return ref_import.available()
+
+
+def _ref_init(base_sets, est):
+    import ref_import
+    ref_import.load()
+    import core.hrir as ref_hrir
+    _REF['est'] = est          # built once by the parent (fork: inherited, not re-derived per worker)
+    _REF['base'] = base_sets
+    _REF['hrir'] = ref_hrir
+    # the WAV container is not part of the path: hand the in-memory float64 tracks to open_recording
+    ref_hrir.read_wav = lambda file_path, expand=False: (FS, _REF['base'][int(file_path)])
+
+
+def _ref_one_set(i):
+    """HRIR.open_recording -> crop_heads -> align_ipsilateral_all -> align_onset_groups_peak_leftref -> crop_tails
+    (core/pipeline.py:565-601), the reference's own methods."""
+    import warnings
+    h = _REF['hrir'].HRIR(_REF['est'])
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        h.open_recording(str(i % len(_REF['base'])), LAYOUT)
+        h.crop_heads()
+        h.align_ipsilateral_all()
+        h.align_onset_groups_peak_leftref()
+        return h.crop_tails()
+
+
+def reference_throughput(base_sets, sets_per_round, rounds, warm=1, est=None):
+    """IRs/s of the reference's own code under its own process pool; one parallel_map call per round (the pool is
+    created inside the call, as the reference does for every stage)."""
+    import ref_import
+    ref_import.load()
+    from core.parallel_utils import parallel_map
+    if est is None:
+        from core.impulse_response_estimator import ImpulseResponseEstimator as RefEstimator
+        est = RefEstimator(min_duration=5.0, fs=FS)
+    workers = min(os.cpu_count() or 4, sets_per_round)
+    items = list(range(sets_per_round))
+    for _ in range(warm):
+        parallel_map(_ref_one_set, items[:workers], initializer=_ref_init, initargs=(base_sets, est))
+    times = []
+    for _ in range(rounds):
+        t0 = time.perf_counter()
+        tails = parallel_map(_ref_one_set, items, initializer=_ref_init, initargs=(base_sets, est))
+        times.append(time.perf_counter() - t0)
+    assert len(tails) == sets_per_round and all(int(t) > 0 for t in tails)
+    return sets_per_round * N_IRS / min(times), workers, times
+
+
+WORKLOAD = ("synthetic 7.1 layout (FL,FR,FC,SL,SR,BL,BR x 2 ears) 6.15 s@48 kHz sweep deconvolution + crop "
+            "(BASELINE.json configs[1])")
+
+
+# ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -146,28 +211,44 @@ def measured_peak():
 
 
 def run_reference(args, rank, world):
+    """Reference arm: rank 0 times the reference's own CPU implementation of the path on the box's host cores.
+    Each step is a bounded sample of the GPU arm's workload (same recording sets, same per-set path), sized so
+    --steps K ends within minutes; IR/s is per-set work, so the arms compare on the identical workload string."""
     if rank != 0:
         return
-    import impulcifer_oracle as O
-    ts = O.generate_test_signal(5.0, FS)
-    P, _, _ = O.sweep_parameters(FS)
-    inv = O.generate_inverse_filter(ts, P)
-    base = _host_sets(ts, N_BASE_SETS)
     cores = os.cpu_count() or 1
     per_step = max(cores, 4)
-    _, workers, t_all = cpu_throughput(ts, inv, P, base, per_step, rounds=args.steps, warm=min(args.warmup, 1))
+    if reference_available():
+        import ref_import
+        ref_import.load()
+        from core.impulse_response_estimator import ImpulseResponseEstimator as RefEstimator
+        est = RefEstimator(min_duration=5.0, fs=FS)
+        ts = est.test_signal
+        base = _host_sets(ts, N_BASE_SETS)
+        _, workers, t_all = reference_throughput(base, per_step, rounds=args.steps, warm=min(args.warmup, 1), est=est)
+        kind = "reference"
+        how = (f"{per_step} recording sets ({per_step * N_IRS} IRs) per step through the unmodified reference "
+               f"(oracle/_ref: HRIR.open_recording + crop_heads + align_* + crop_tails) under its own "
+               f"core.parallel_utils.parallel_map, ProcessPoolExecutor of {workers} workers created per call")
+    else:
+        import impulcifer_oracle as O
+        ts = O.generate_test_signal(5.0, FS)
+        P, _, _ = O.sweep_parameters(FS)
+        inv = O.generate_inverse_filter(ts, P)
+        base = _host_sets(ts, N_BASE_SETS)
+        _, workers, t_all = cpu_throughput(ts, inv, P, base, per_step, rounds=args.steps, warm=min(args.warmup, 1))
+        kind = "port"
+        how = (f"{per_step} recording sets ({per_step * N_IRS} IRs) per step through the oracle port of the "
+               f"reference path (oracle/_ref not staged), fork pool of {workers} processes")
     value = per_step * N_IRS / (sum(t_all) / len(t_all))
     line = {
         "impl": "reference", "metric": "IR deconvolutions/s (6.15s@48kHz sweep)", "value": value, "unit": "IR/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(t_all) / len(t_all), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic 7.1 layout (FL,FR,FC,SL,SR,BL,BR x 2 ears) 6.15 s@48 kHz sweep "
-                               "deconvolution + crop", "sets_per_step": per_step, "irs_per_set": N_IRS,
+        "config": {"workload": WORKLOAD, "sets_per_step_sample": per_step, "irs_per_set": N_IRS,
                    "samples_per_ir": 2 * FS + len(ts)},
-        "cpu_baseline": {"value": value, "unit": "IR/s", "cores": workers, "kind": "port",
-                         "sample": f"{per_step} recording sets ({per_step * N_IRS} IRs) per step through the oracle "
-                                   f"port of the reference path, fork pool of {workers} processes"},
+        "cpu_baseline": {"value": value, "unit": "IR/s", "cores": workers, "kind": kind, "sample": how},
         "e2e": {"value": value, "unit": "IR/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,10 +286,17 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_sets = max(cores, 4)
-        v, workers, times = cpu_throughput(est.test_signal, est.inverse_filter, est.n_octaves, base, n_sets, rounds=2)
-        cpu = {"value": v, "unit": "IR/s", "cores": workers, "kind": "port",
-               "sample": f"{n_sets} recording sets ({n_sets * N_IRS} IRs), best of 2 rounds, oracle port of "
-                         f"open_recording+crop_heads+align+crop_tails, fork pool of {workers} processes"}
+        if reference_available():
+            v, workers, times = reference_throughput(base, n_sets, rounds=2)
+            cpu = {"value": v, "unit": "IR/s", "cores": workers, "kind": "reference",
+                   "sample": f"{n_sets} recording sets ({n_sets * N_IRS} IRs), best of 2 rounds, the unmodified reference "
+                             f"(oracle/_ref) open_recording+crop_heads+align+crop_tails under its own "
+                             f"core.parallel_utils.parallel_map ({workers} worker processes)"}
+        else:
+            v, workers, times = cpu_throughput(est.test_signal, est.inverse_filter, est.n_octaves, base, n_sets, rounds=2)
+            cpu = {"value": v, "unit": "IR/s", "cores": workers, "kind": "port",
+                   "sample": f"{n_sets} recording sets ({n_sets * N_IRS} IRs), best of 2 rounds, oracle port of "
+                             f"open_recording+crop_heads+align+crop_tails, fork pool of {workers} processes"}
 
     import torch
     import torch.distributed as dist
@@ -386,8 +474,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
-            "config": {"workload": "synthetic 7.1 layout (FL,FR,FC,SL,SR,BL,BR x 2 ears) 6.15 s@48 kHz sweep "
-                                   "deconvolution + crop (BASELINE.json configs[1])",
+            "config": {"workload": WORKLOAD,
                        "sets_per_gpu_per_step": S, "irs_per_set": N_IRS, "samples_per_ir": L,
                        "sweep_samples": len(est), "fft_plan": f"{plan.n1}x{plan.n2}",
                        "tail_samples": tails, "l2_policy": "inputs larger than L2 "

@@ -457,6 +457,15 @@ def small_cases():
     for k, v in dcases.items():
         gold[f'dc_{k}_x'] = v.astype(np.float64)
         gold[f'dc_{k}_out'] = np.array([float(t) for t in ref.decay.decay_params(v.astype(np.float64), 48000)])
+    # steepest decays decay_params can measure (0 dB window, then a window just above the -200 dB floor + 10 dB):
+    # the refined pass then builds the longest window list it ever can (~3840 of K4's 4096)
+    for tag, fs, lev_db in (('steep48', 48000, -187.0), ('steep48b', 48000, -150.0), ('steep192', 192000, -187.0)):
+        w = int(0.03 * fs)
+        x = np.zeros(3 * fs)
+        x[:w] = 1.0
+        x[w:2 * w] = 10 ** (lev_db / 20)
+        gold[f'st_{tag}_x'] = x
+        gold[f'st_{tag}_out'] = np.array([float(t) for t in ref.decay.decay_params(x.copy(), fs)])
     np.savez_compressed(os.path.join(HERE, 'small_cases.npz'), **gold)
     print('small_cases written')
 

@@ -100,6 +100,24 @@ def test_lundeby_fuzz(T):
         assert abs(noise[i] - rn) < 1e-9
 
 
+def test_lundeby_steepest_possible_decay(T):
+    """The refined pass of decay_params builds 3 windows per 10 dB of the first-pass slope.  Window levels are clamped
+    to [-200 dB, 0 dB] 30 ms apart, so the slope is at most 200 dB / 30 ms and the list never exceeds 4000 windows
+    (k_lundeby holds 4096 and traps beyond).  These rows drive the reference to the steepest slopes it can measure
+    (3840 windows at 48 kHz, same at 192 kHz): integers must still be the reference's (golden st_steep*)."""
+    from impulcifer_pip313_b200 import ops
+    g = load('small_cases.npz')
+    for tag, fs in (('steep48', 48000), ('steep48b', 48000), ('steep192', 192000)):
+        x = g[f'st_{tag}_x']
+        ref = g[f'st_{tag}_out']
+        flat, offs, lens = _pack([x], T)
+        pk, knee, noise, win = [t.cpu().numpy() for t in ops.lundeby(flat, offs, lens, fs)]
+        assert (pk[0], knee[0], win[0]) == (int(ref[0]), int(ref[1]), int(ref[3])), tag
+        assert abs(noise[0] - ref[2]) < 1e-9, tag
+        assert 2 * fs / win[0] > 2900, (tag, win[0])  # really in the thousands-of-windows regime
+        assert O.decay_params(x, fs)[1] == int(ref[1])
+
+
 def test_view_max_hints_never_change_results(T):
     """impb_view.hint_max / hint_argmax only skip scans: peak_index and lundeby of a view must be identical with
     hints, without hints and on the materialised array (oracle), also when the hinted sample is faded or shifted
