@@ -62,6 +62,9 @@ SIGNATURES = {
     "impb_minphase_fir": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "impb_pack_tracks": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "impb_resample_out_len": (c_i64, [c_i64, c_i32, c_i32]),
+    "impb_resample_plan_create": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, C.POINTER(c_vp)]),
+    "impb_resample_plan_destroy": (None, [c_vp]),
+    "impb_resample_execute": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "impb_plan_probe": (c_i32, [c_i64, c_i32, c_i32, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i32 * 6),
                                 C.POINTER(c_i32 * 6)]),
     "impb_window_resample": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_i64,

@@ -92,6 +92,17 @@ template <typename T, int TILE, bool PRE = false> struct DeconvColIn {
     const int n2 = t * TILE + c;
     return n2 < a.N2 ? __ldg(a.tw + (size_t)e * a.N2 + n2) : mkc<T>(0, 0);
   }
+  // column walk of the staged copy: address of the sample feeding re (which=0) / im (which=1) of element (0, c),
+  // the number of leading rows that hold samples (0: the whole column is zero padding) and the row pitch
+  __device__ __forceinline__ const T* src_column(int b, int t, int c, int which, int* e_lim, int64_t* e_pitch) const {
+    const int n2 = t * TILE + c;
+    const int64_t r = a.row0 + 2 * (int64_t)b + which;
+    *e_pitch = a.N2;
+    if (n2 >= a.N2 || r >= a.nrows || n2 >= a.len) { *e_lim = 0; return reinterpret_cast<const T*>(a.rec); }
+    const int64_t o = a.in_offsets ? __ldg(a.in_offsets + r) : r * a.ld_in;
+    *e_lim = (int)((a.len - n2 + a.N2 - 1) / a.N2);  // e * N2 + n2 < len
+    return reinterpret_cast<const T*>(a.rec) + o + n2;
+  }
   // address of the f64 sample feeding re (which=0) / im (which=1) of element (e, c); nullptr = zero padding
   __device__ __forceinline__ const T* src(int b, int t, int e, int c, int which) const {
     const int n2 = t * TILE + c;
@@ -524,7 +535,10 @@ int32_t impb_deconv_plan_create(impb_ctx* ctx, const double* inv_filter_host, in
     pl->has64 = true;
   } else {
     Plan2D pf = p;
-    pf.tile = 2 * p.tile;
+    // FP32 tiles: 16 columns (128-byte rows, 98 KB, 2 CTAs per SM) by default; IMPB_F32_TILE8 plans 8 columns
+    // (64-byte rows, 49 KB: registers then allow 3 CTAs per SM) for A/B measurements
+    static const bool f32_narrow = getenv("IMPB_F32_TILE8") != nullptr;
+    pf.tile = f32_narrow ? p.tile : 2 * p.tile;
     pf.threads = p.threads;
     if (!make_subplan(p.N1, pf.tile, pf.threads, &pf.col) || !make_subplan(p.N2, pf.tile, pf.threads, &pf.row)) {
       delete pl;

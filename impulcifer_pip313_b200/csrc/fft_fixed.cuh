@@ -230,13 +230,26 @@ k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1,
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
   const int t = blockIdx.x, b = blockIdx.y;
   // adjacent lanes copy the re and the im part of one element: a warp instruction then fills 16 whole complex slots
-  // (contiguous shared-memory bytes) instead of the halves of 32 (which cost twice the shared-memory wavefronts)
-  for (int k = threadIdx.x; k < 2 * RX::S * TILE; k += NT) {
-    const int i = k >> 1, which = k & 1;
-    const int e = i / TILE, c = i % TILE;
-    T* dst = reinterpret_cast<T*>(&tile[fx_smem<false, TILE, RX::S>(e, c)]) + which;
-    const T* src = f.src(b, t, e, c, which);
-    if (src) cp_async_n<sizeof(T)>(dst, src); else *dst = (T)0;
+  // (contiguous shared-memory bytes) instead of the halves of 32 (which cost twice the shared-memory wavefronts).
+  // A thread keeps its column c and its re/im half for the whole tile and walks down the rows in steps of
+  // (NT/2)/TILE, so the source address is ONE pointer advanced by a constant stride and the bounds test one
+  // compare against a per-thread row limit: ~6 instructions per copy instead of the ~20 of a per-element
+  // src(b, t, e, c, which) call (the loop used to issue as many instructions as the butterflies of the tile).
+  {
+    static_assert((NT / 2) % TILE == 0, "a thread must stay in one column");
+    constexpr int ESTEP = (NT / 2) / TILE;
+    const int which = threadIdx.x & 1, i0 = threadIdx.x >> 1;
+    const int c = i0 % TILE, e0 = i0 / TILE;
+    int e_lim;        // rows [0, e_lim) of this column hold samples, the rest is zero padding
+    int64_t e_pitch;  // elements between consecutive rows of the column
+    const T* col = f.src_column(b, t, c, which, &e_lim, &e_pitch);
+    const T* src = col + (int64_t)e0 * e_pitch;
+    const int64_t step = (int64_t)ESTEP * e_pitch;
+#pragma unroll 4
+    for (int e = e0; e < RX::S; e += ESTEP, src += step) {
+      T* dst = reinterpret_cast<T*>(&tile[fx_smem<false, TILE, RX::S>(e, c)]) + which;
+      if (e < e_lim) cp_async_n<sizeof(T)>(dst, src); else *dst = (T)0;
+    }
   }
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");

@@ -11,6 +11,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -34,6 +36,11 @@ __device__ __forceinline__ double decay_gain(const double* dp, int64_t k) {
     wv = 0.0;
   }
   return exp10((wv - 1.0) * -level / 20.0);
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
 }
 
 __global__ void __launch_bounds__(256) k_resample(const double* __restrict__ src, int64_t ld_src, int64_t n,
@@ -118,7 +125,400 @@ __global__ void __launch_bounds__(256) k_decay_only(const double* __restrict__ s
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Run-structured polyphase kernel (rational ratios close to 1: 48 <-> 44.1 kHz = 147/160, 160/147).
+//
+// Output j = m*up + a (period m, phase a) reads taps[phi_a + i*up] * x[m*down + c_a - i], i = 0 .. ceil(ntaps/up),
+// with t_a = (a + n_pre_remove)*down - n_pre_pad, phi_a = t_a % up, c_a = t_a / up.  Within a period c_a mostly
+// advances by exactly one per output, so the period splits into a few RUNS of consecutive outputs whose input
+// windows are one sample apart (147/160: 13 runs of 11-12 outputs).  One thread owns one run of one period of one
+// row: RJ accumulators and a sliding window of RJ samples in registers, so a tap step costs ONE new sample plus RJ
+// taps for RJ multiply-adds.  Lanes of a warp are 32 consecutive periods of the same row and run: the taps are the
+// same for all lanes (broadcast LDS.128 from a [run][step][q] table in shared memory, built once per CTA) and the
+// sample addresses are `down` apart (padded to an odd pitch: conflict-free).  A CTA = one warp per run; it walks
+// over (row, block of 32 periods) items, the input window of the next item arriving by cp.async while the current
+// one is computed.  Each output is ONE chain of FMAs in ascending tap order: the values are those of k_resample.
+// ------------------------------------------------------------------------------------------------------------------
+struct RunDesc { int a0, len, e0; };  // first phase of the run, outputs in it, c_a0 - c_min
+
+struct RunGeom {
+  int up, down, pad;        // pad = 1 when down is even (odd lane pitch)
+  int n_steps, n_runs;
+  int c_min, span;          // window of one period block: samples [m0*down + c_min - (n_steps-1), ... + 32*down + span)
+  int tile_elems;           // doubles per staged input window (with padding)
+};
+
+__global__ void k_run_table(const double* __restrict__ taps, int64_t ntaps, int up, int down, int64_t n_pre_pad,
+                            int64_t n_pre_remove, const RunDesc* __restrict__ runs, int n_runs, int n_steps, int RJ,
+                            double* __restrict__ table) {
+  const int64_t total = (int64_t)n_runs * n_steps * RJ;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(k % RJ), i = (int)((k / RJ) % n_steps), s = (int)(k / ((int64_t)RJ * n_steps));
+    double v = 0.0;
+    if (q < runs[s].len) {
+      const int64_t t = ((int64_t)runs[s].a0 + q + n_pre_remove) * down - n_pre_pad;
+      const int64_t idx = t % up + (int64_t)i * up;
+      if (idx < ntaps) v = taps[idx];
+    }
+    table[k] = v;
+  }
+}
+
+template <int RJ, int PR, bool DECAY>
+__global__ void __launch_bounds__(448, 1)
+k_resample_runs(const double* __restrict__ src, int64_t ld_src, int64_t n, const double* __restrict__ decay,
+                const double* __restrict__ table_g, const RunDesc* __restrict__ runs, const RunGeom g, int64_t n_out,
+                int64_t batch, int64_t n_blocks, int64_t n_items, bool double_buffer, double* __restrict__ dst,
+                int64_t ld_dst) {
+  // PR rows per thread: a pair of taps fetched from shared memory (broadcast LDS.128 = two LSU wavefronts) feeds 2 PR
+  // multiply-adds; per tap step 12 + 2 PR wavefronts for 12 PR FMAs
+  extern __shared__ __align__(16) double rs_smem[];
+  double* table = rs_smem;                                  // [n_runs][n_steps][RJ]
+  double* xbuf = rs_smem + (size_t)g.n_runs * g.n_steps * RJ;  // 1 or 2 buffers of PR windows of tile_elems doubles
+  const int nthreads = blockDim.x;
+  for (int k = threadIdx.x; k < g.n_runs * g.n_steps * RJ; k += nthreads) table[k] = table_g[k];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = nthreads >> 5;
+  const int pitch = g.down + g.pad;
+  const int rel_total = 32 * g.down + g.span;
+  const size_t buf_elems = (size_t)PR * g.tile_elems;
+
+  auto stage = [&](int64_t item, double* buf) {
+    const int64_t rg = item / n_blocks, pb = item % n_blocks;
+    const int64_t n_lo = (pb * 32 - 1) * g.down + g.c_min - (g.n_steps - 1);  // periods are numbered from -1
+#pragma unroll
+    for (int pr = 0; pr < PR; ++pr) {
+      const int64_t r = rg * PR + pr;
+      double* bp = buf + (size_t)pr * g.tile_elems;
+      const bool row_ok = r < batch;
+      const double* x = src + (size_t)(row_ok ? r : 0) * ld_src;
+      const double* dp = DECAY && decay && row_ok ? decay + (size_t)r * 4 : nullptr;
+      const bool use_decay = DECAY && dp && !isnan(dp[0]);
+      int l = 0, e = threadIdx.x;  // rel = l * down + e without a division per element
+      while (e >= g.down) { e -= g.down; ++l; }
+      for (int rel = threadIdx.x; rel < rel_total; rel += nthreads) {
+        const int64_t k = n_lo + rel;
+        double* d = bp + rel + g.pad * l;
+        if (row_ok && k >= 0 && k < n) {
+          if (DECAY) {
+            double v = x[k];
+            if (use_decay) v *= decay_gain(dp, k);
+            *d = v;
+          } else {
+            cp_async8(d, x + k);
+          }
+        } else {
+          *d = 0.0;
+        }
+        e += nthreads;
+        while (e >= g.down) { e -= g.down; ++l; }
+      }
+    }
+    if (!DECAY) asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  int64_t item = blockIdx.x;
+  int cur = 0;
+  if (item < n_items) stage(item, xbuf);
+  for (; item < n_items; item += gridDim.x) {
+    const int64_t next = item + gridDim.x;
+    double* buf = xbuf + (size_t)cur * buf_elems;
+    if (double_buffer) {
+      if (next < n_items) stage(next, xbuf + (size_t)(cur ^ 1) * buf_elems);
+      if (!DECAY) {
+        if (next < n_items) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      }
+    } else if (!DECAY) {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();  // window of `item` (and, first time round, the tap table) is in shared memory
+    const int64_t rg = item / n_blocks, pb = item % n_blocks;
+    const int64_t m = pb * 32 + lane - 1;
+    for (int s = warp; s < g.n_runs; s += n_warps) {
+      const RunDesc rd = runs[s];
+      const double* tp = table + (size_t)s * g.n_steps * RJ;
+      const double* xl = buf + (size_t)lane * pitch;
+      // e(sigma) = e0 + sigma + n_steps - 1 is warp-uniform; the padded position adds pad * (e / down)
+      // (e < 3 * down is guaranteed by plan_runs, so e / down is two compares)
+      const int d1 = g.down, d2 = 2 * g.down, pad = g.pad;
+      auto xpos = [&](int e) -> int { return e + ((e >= d1) ? pad : 0) + ((e >= d2) ? pad : 0); };
+      const int ebase = rd.e0 + g.n_steps - 1;
+      double w[PR][RJ], acc[PR][RJ];
+#pragma unroll
+      for (int q = 0; q < RJ; ++q) {
+        const int pos = xpos(ebase + q);
+#pragma unroll
+        for (int pr = 0; pr < PR; ++pr) { w[pr][q] = xl[(size_t)pr * g.tile_elems + pos]; acc[pr][q] = 0.0; }
+      }
+      for (int i0 = 0; i0 < g.n_steps; i0 += RJ) {
+#pragma unroll
+        for (int u = 0; u < RJ; ++u) {
+          const int i = i0 + u;
+          // (measured: padding the steps to groups of 4 with one exit test per group, so that the loads of a group are
+          // straight-line code, was slower: 1.75 vs 1.62 ms — three more zero steps and spills at the 128-register cap)
+          if (i >= g.n_steps) break;
+          if (i > 0) {
+            const int pos = xpos(ebase - i);
+#pragma unroll
+            for (int pr = 0; pr < PR; ++pr) w[pr][(RJ - u) % RJ] = xl[(size_t)pr * g.tile_elems + pos];
+          }
+          const double2* t2 = reinterpret_cast<const double2*>(tp + (size_t)i * RJ);
+#pragma unroll
+          for (int q = 0; q < RJ; q += 2) {
+            const double2 t = t2[q >> 1];
+#pragma unroll
+            for (int pr = 0; pr < PR; ++pr) {
+              acc[pr][q] = fma(t.x, w[pr][(q - u + RJ) % RJ], acc[pr][q]);
+              acc[pr][q + 1] = fma(t.y, w[pr][(q + 1 - u + RJ) % RJ], acc[pr][q + 1]);
+            }
+          }
+        }
+      }
+      const int64_t j0 = m * g.up + rd.a0;
+#pragma unroll
+      for (int pr = 0; pr < PR; ++pr) {
+        const int64_t r = rg * PR + pr;
+        if (r >= batch) continue;
+        double* o = dst + (size_t)r * ld_dst + j0;
+#pragma unroll
+        for (int q = 0; q < RJ; ++q)
+          if (q < rd.len && j0 + q >= 0 && j0 + q < n_out) o[q] = acc[pr][q];
+      }
+    }
+    __syncthreads();  // every warp is done with `buf` before the next stage() overwrites it
+    if (double_buffer) cur ^= 1;
+    else if (next < n_items) stage(next, xbuf);
+  }
+}
+
+// ---- the same kernel with the taps in the KERNEL PARAMETER space (constant bank, CUDA >= 12.1: up to 32 764 B) -------
+// A/B variant, NOT the default.  A broadcast LDS.128 costs two LSU wavefronts (ncu: 14.3 shared-load wavefronts per
+// 12-FMA tap step of k_resample_runs<12,1>, LSU pipe 73 % busy), so the taps were moved out of the LSU: a launch
+// carries the [run][step][q] table of as many runs as fit 31 KB (3 of the 13 runs of 147/160) and the compiler feeds
+// them through the uniform datapath (SASS: LDCU.64 UR, c[0x0][UR+imm]; DFMA R, R, UR, R).  Measured on B200 for
+// 896 x 96 000 samples: 3.48 ms against 2.05 ms (one row per thread) / 1.62 ms (two rows) for the shared-memory table:
+// twelve uniform loads per step do not keep up with twelve DFMAs.  Kept behind IMPB_RESAMPLE_CONST=1 as evidence.
+constexpr int TAP_PARAM_DOUBLES = 3968;
+struct alignas(16) TapParams { double t[TAP_PARAM_DOUBLES]; };
+struct RunGroup { RunDesc r[4]; int n; };
+
+template <int RJ, bool DECAY>
+__global__ void __launch_bounds__(128)
+k_resample_runs_c(const double* __restrict__ src, int64_t ld_src, int64_t n, const double* __restrict__ decay,
+                  const __grid_constant__ TapParams tp, const __grid_constant__ RunGroup rg, const RunGeom g, int64_t n_out,
+                  int64_t row0, double* __restrict__ dst, int64_t ld_dst) {
+  extern __shared__ __align__(16) double rc_smem[];
+  const int nthreads = blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform: constant-bank loads
+  const int64_t pb = blockIdx.x, r = row0 + blockIdx.y;
+  const int pitch = g.down + g.pad;
+  {
+    const int rel_total = 32 * g.down + g.span;
+    const int64_t n_lo = (pb * 32 - 1) * g.down + g.c_min - (g.n_steps - 1);  // periods are numbered from -1
+    const double* x = src + (size_t)r * ld_src;
+    const double* dp = DECAY && decay ? decay + (size_t)r * 4 : nullptr;
+    const bool use_decay = DECAY && dp && !isnan(dp[0]);
+    int rel = threadIdx.x, l = 0, e = threadIdx.x;  // rel = l * down + e without a division per element
+    while (e >= g.down) { e -= g.down; ++l; }
+    for (; rel < rel_total; rel += nthreads) {
+      const int64_t k = n_lo + rel;
+      double* d = rc_smem + rel + g.pad * l;
+      if (k >= 0 && k < n) {
+        if (DECAY) {
+          double v = x[k];
+          if (use_decay) v *= decay_gain(dp, k);
+          *d = v;
+        } else {
+          cp_async8(d, x + k);
+        }
+      } else {
+        *d = 0.0;
+      }
+      e += nthreads;
+      while (e >= g.down) { e -= g.down; ++l; }
+    }
+    if (!DECAY) asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (warp >= rg.n) return;
+  const RunDesc rd = rg.r[warp];
+  const double* xl = rc_smem + (size_t)lane * pitch;
+  const int d1 = g.down, d2 = 2 * g.down, pad = g.pad;
+  auto xat = [&](int e) -> double { return xl[e + ((e >= d1) ? pad : 0) + ((e >= d2) ? pad : 0)]; };
+  const int ebase = rd.e0 + g.n_steps - 1;
+  const double2* t2 = reinterpret_cast<const double2*>(tp.t) + (size_t)warp * g.n_steps * (RJ / 2);
+  double w[RJ], acc[RJ];
+#pragma unroll
+  for (int q = 0; q < RJ; ++q) { w[q] = xat(ebase + q); acc[q] = 0.0; }
+  for (int i0 = 0; i0 < g.n_steps; i0 += RJ) {
+#pragma unroll
+    for (int u = 0; u < RJ; ++u) {
+      const int i = i0 + u;
+      if (i < g.n_steps) {
+        if (i > 0) w[(RJ - u) % RJ] = xat(ebase - i);
+#pragma unroll
+        for (int q = 0; q < RJ; q += 2) {
+          const double2 t = t2[(size_t)i * (RJ / 2) + (q >> 1)];
+          acc[q] = fma(t.x, w[(q - u + RJ) % RJ], acc[q]);
+          acc[q + 1] = fma(t.y, w[(q + 1 - u + RJ) % RJ], acc[q + 1]);
+        }
+      }
+    }
+  }
+  const int64_t j0 = (pb * 32 + lane - 1) * g.up + rd.a0;
+  double* o = dst + (size_t)r * ld_dst + j0;
+#pragma unroll
+  for (int q = 0; q < RJ; ++q)
+    if (q < rd.len && j0 + q >= 0 && j0 + q < n_out) o[q] = acc[q];
+}
+
 }  // namespace
+
+
+// Plans the run-structured kernel for (u, d, ntaps); returns false when the ratio has no long runs or the tables do
+// not fit shared memory (the caller then takes the generic kernels).
+struct RunPlan {
+  std::vector<RunDesc> runs;
+  RunGeom g;
+  int rj = 0;
+  size_t smem_table = 0, smem_tile = 0;
+  bool double_buffer = false;
+  int rows_per_thread = 1;  // PR of k_resample_runs
+};
+
+static bool plan_runs(int u, int d, int64_t ntaps, int64_t n_pre_pad, int64_t n_pre_remove, size_t smem_limit,
+                      RunPlan* out) {
+  if (u < 8 || ntaps < u) return false;
+  // phases a' = a + up continue the same formula one period later, so a period may start at ANY phase: start it at
+  // the first break of the unit-step pattern, else the run that straddles phase 0 is cut in two (14 runs instead of
+  // 13 for 147/160, which costs 10 KB of tap table).  Periods are then numbered from -1 (outputs j < 0 are skipped).
+  std::vector<int64_t> c((size_t)(2 * u));
+  for (int a = 0; a < 2 * u; ++a) {
+    const int64_t t = ((int64_t)a + n_pre_remove) * d - n_pre_pad;
+    if (t < 0) return false;
+    c[(size_t)a] = t / u;
+  }
+  int first = 0;
+  for (int a = 1; a <= u; ++a)
+    if (c[(size_t)a] != c[(size_t)(a - 1)] + 1) { first = a; break; }
+  int longest = 0;
+  std::vector<RunDesc> runs;
+  for (int a = first; a < first + u;) {
+    int len = 1;
+    while (a + len < first + u && len < 16 && c[(size_t)(a + len)] == c[(size_t)(a + len - 1)] + 1) ++len;
+    runs.push_back(RunDesc{a, len, 0});
+    longest = std::max(longest, len);
+    a += len;
+  }
+  if ((int)runs.size() > 14 || u / (double)runs.size() < 8.0) return false;  // short runs: no reuse to win
+  const int rj = longest <= 12 ? 12 : longest <= 14 ? 14 : 16;
+  int64_t c_min = c[(size_t)first], c_max = c[(size_t)first];
+  for (int a = first; a < first + u; ++a) { c_min = std::min(c_min, c[(size_t)a]); c_max = std::max(c_max, c[(size_t)a]); }
+  for (auto& r : runs) r.e0 = (int)(c[(size_t)r.a0] - c_min);
+  RunGeom g{};
+  g.up = u; g.down = d; g.pad = (d % 2 == 0) ? 1 : 0;
+  g.n_steps = (int)((ntaps + u - 1) / u);
+  g.n_runs = (int)runs.size();
+  g.c_min = (int)c_min;
+  g.span = (int)(c_max - c_min) + g.n_steps + rj;
+  const int rel_total = 32 * d + g.span;
+  g.tile_elems = (rel_total + g.pad * (rel_total / d + 1) + 1) & ~1;
+  out->smem_table = (size_t)g.n_runs * g.n_steps * rj * sizeof(double);
+  out->smem_tile = (size_t)g.tile_elems * sizeof(double);
+  if (g.span >= 3 * d) return false;  // the kernel resolves e / down with two compares
+  if (out->smem_table + out->smem_tile > smem_limit) return false;
+  // two rows per thread halve the tap wavefronts per multiply-add (the kernel's bound) and beat double buffering
+  out->rows_per_thread = (runs.size() <= 13 && out->smem_table + 2 * out->smem_tile <= smem_limit) ? 2 : 1;
+  out->double_buffer = out->smem_table + 2 * out->rows_per_thread * out->smem_tile <= smem_limit;
+  out->runs = std::move(runs);
+  out->g = g;
+  out->rj = rj;
+  return true;
+}
+
+template <int RJ, int PR>
+static cudaError_t launch_runs_pr(const RunPlan& rp, const double* src, int64_t ld_src, int64_t n, const double* decay,
+                                  const double* table, const RunDesc* runs_d, int64_t n_out, double* dst, int64_t ld_dst,
+                                  int64_t batch, int sms, cudaStream_t st) {
+  const int64_t periods = (n_out + rp.g.up - 1) / rp.g.up;
+  const int64_t n_blocks = (periods + 1 + 31) / 32;  // + period -1
+  const int64_t n_items = ((batch + PR - 1) / PR) * n_blocks;
+  const size_t smem = rp.smem_table + (rp.double_buffer ? 2 : 1) * PR * rp.smem_tile;
+  const int threads = 32 * rp.g.n_runs;
+  const unsigned grid = (unsigned)std::min<int64_t>(n_items, sms);
+  cudaError_t e;
+  if (decay) {
+    auto k = k_resample_runs<RJ, PR, true>;
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<grid, threads, smem, st>>>(src, ld_src, n, decay, table, runs_d, rp.g, n_out, batch, n_blocks, n_items,
+                                   rp.double_buffer, dst, ld_dst);
+  } else {
+    auto k = k_resample_runs<RJ, PR, false>;
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<grid, threads, smem, st>>>(src, ld_src, n, decay, table, runs_d, rp.g, n_out, batch, n_blocks, n_items,
+                                   rp.double_buffer, dst, ld_dst);
+  }
+  return cudaGetLastError();
+}
+
+template <int RJ>
+static cudaError_t launch_runs(const RunPlan& rp, const double* src, int64_t ld_src, int64_t n, const double* decay,
+                               const double* table, const RunDesc* runs_d, int64_t n_out, double* dst, int64_t ld_dst,
+                               int64_t batch, int sms, cudaStream_t st) {
+  return rp.rows_per_thread == 2 && batch > 1
+             ? launch_runs_pr<RJ, 2>(rp, src, ld_src, n, decay, table, runs_d, n_out, dst, ld_dst, batch, sms, st)
+             : launch_runs_pr<RJ, 1>(rp, src, ld_src, n, decay, table, runs_d, n_out, dst, ld_dst, batch, sms, st);
+}
+
+// ---- resample plan: host-side tap tables for the constant-bank kernel ------------------------------------------------
+struct impb_resample {
+  impb_ctx* ctx = nullptr;
+  int up = 1, down = 1;          // reduced by their gcd
+  int64_t ntaps = 0, n_pre_pad = 0, n_pre_remove = 0;
+  double* taps_dev = nullptr;    // [ntaps] for the generic kernels
+  bool runs_ok = false;
+  RunPlan rp;
+  std::vector<double> table;     // [n_runs][n_steps][rj]
+  double* table_dev = nullptr;   // the same table and the run descriptors on the device (k_resample_runs)
+  RunDesc* runs_dev = nullptr;
+};
+
+template <int RJ>
+static cudaError_t launch_runs_c(const impb_resample* p, const double* src, int64_t ld_src, int64_t n, const double* decay,
+                                 int64_t n_out, double* dst, int64_t ld_dst, int64_t batch, cudaStream_t st) {
+  const RunGeom& g = p->rp.g;
+  const int per_run = g.n_steps * RJ;
+  const int runs_per_launch = std::min(4, TAP_PARAM_DOUBLES / per_run);
+  const int64_t periods = (n_out + g.up - 1) / g.up;
+  const int64_t n_blocks = (periods + 1 + 31) / 32;  // + period -1
+  const size_t smem = p->rp.smem_tile;
+  cudaError_t e;
+  auto kd = k_resample_runs_c<RJ, true>;
+  auto kn = k_resample_runs_c<RJ, false>;
+  if ((e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  static TapParams tp;  // 31 KB: filled under the lock below, copied by value at launch
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  for (int s0 = 0; s0 < g.n_runs; s0 += runs_per_launch) {
+    RunGroup rg{};
+    rg.n = std::min(runs_per_launch, g.n_runs - s0);
+    for (int k = 0; k < rg.n; ++k) rg.r[k] = p->rp.runs[(size_t)(s0 + k)];
+    std::copy(p->table.begin() + (size_t)s0 * per_run, p->table.begin() + (size_t)(s0 + rg.n) * per_run, tp.t);
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+      const unsigned nb = (unsigned)std::min<int64_t>(65535, batch - b0);
+      const dim3 grid((unsigned)n_blocks, nb);
+      if (decay)
+        kd<<<grid, 32 * rg.n, smem, st>>>(src, ld_src, n, decay, tp, rg, g, n_out, b0, dst, ld_dst);
+      else
+        kn<<<grid, 32 * rg.n, smem, st>>>(src, ld_src, n, decay, tp, rg, g, n_out, b0, dst, ld_dst);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
 
 static int64_t gcd64(int64_t a, int64_t b) {
   while (b) { int64_t t = a % b; a = b; b = t; }
@@ -164,6 +564,33 @@ int32_t impb_window_resample(impb_ctx* ctx, const double* src, int64_t ld_src, i
   const int64_t half_len = (ntaps - 1) / 2;
   const int64_t n_pre_pad = d - half_len % d;
   const int64_t n_pre_remove = (half_len + n_pre_pad) / d;
+  static const bool no_runs = getenv("IMPB_RESAMPLE_NO_RUNS") != nullptr;
+  RunPlan rp;
+  if (!no_runs && plan_runs(u, d, ntaps, n_pre_pad, n_pre_remove, ctx->smem_optin, &rp)) {
+    double* table = nullptr;
+    RunDesc* runs_d = nullptr;
+    const size_t tbytes = rp.smem_table, rbytes = rp.runs.size() * sizeof(RunDesc);
+    cudaError_t e = cudaMallocAsync(&table, tbytes, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&runs_d, rbytes, st);
+    // the descriptors are a few hundred bytes of integers: a pageable-memory copy is staged by the driver before it
+    // returns, so the vector may go out of scope
+    if (e == cudaSuccess) e = cudaMemcpyAsync(runs_d, rp.runs.data(), rbytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+      k_run_table<<<64, 256, 0, st>>>(taps, ntaps, u, d, n_pre_pad, n_pre_remove, runs_d, rp.g.n_runs, rp.g.n_steps, rp.rj,
+                                      table);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+      const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+      e = rp.rj == 12   ? launch_runs<12>(rp, src, ld_src, n, decay, table, runs_d, n_out, dst, ld_dst, batch, sms, st)
+          : rp.rj == 14 ? launch_runs<14>(rp, src, ld_src, n, decay, table, runs_d, n_out, dst, ld_dst, batch, sms, st)
+                        : launch_runs<16>(rp, src, ld_src, n, decay, table, runs_d, n_out, dst, ld_dst, batch, sms, st);
+    }
+    if (table) cudaFreeAsync(table, st);
+    if (runs_d) cudaFreeAsync(runs_d, st);
+    if (e != cudaSuccess) return cuda_fail(e, "k_resample_runs");
+    return IMPB_OK;
+  }
   const unsigned bx = (unsigned)std::min<int64_t>((n_out + thr - 1) / thr, 4096);
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = (int)std::min<int64_t>(65535, batch - b0);
@@ -179,6 +606,97 @@ int32_t impb_window_resample(impb_ctx* ctx, const double* src, int64_t ld_src, i
     }
   }
   IMPB_CUDA(cudaGetLastError());
+  return IMPB_OK;
+}
+
+int32_t impb_resample_plan_create(impb_ctx* ctx, const double* taps_host, int64_t ntaps, int32_t up, int32_t down,
+                                  impb_resample** out) {
+  if (!ctx || !out || up < 1 || down < 1 || (ntaps > 0 && !taps_host) || ntaps < 0) {
+    set_error("impb_resample_plan_create: bad argument");
+    return IMPB_EINVAL;
+  }
+  DeviceGuard g(ctx->device);
+  impb_resample* p = new impb_resample();
+  p->ctx = ctx;
+  const int64_t gg = gcd64(up, down);
+  p->up = (int)(up / gg);
+  p->down = (int)(down / gg);
+  p->ntaps = ntaps;
+  if (ntaps > 0) {
+    const int64_t half_len = (ntaps - 1) / 2;
+    p->n_pre_pad = p->down - half_len % p->down;
+    p->n_pre_remove = (half_len + p->n_pre_pad) / p->down;
+    cudaError_t e = cudaMalloc(&p->taps_dev, sizeof(double) * ntaps);
+    if (e == cudaSuccess) e = cudaMemcpy(p->taps_dev, taps_host, sizeof(double) * ntaps, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete p; return cuda_fail(e, "resample taps upload"); }
+    static const bool no_runs = getenv("IMPB_RESAMPLE_NO_RUNS") != nullptr;
+    if (!no_runs && p->up > 1 &&
+        plan_runs(p->up, p->down, ntaps, p->n_pre_pad, p->n_pre_remove, ctx->smem_optin, &p->rp) &&
+        true) {
+      const RunGeom& rg = p->rp.g;
+      p->table.assign((size_t)rg.n_runs * rg.n_steps * p->rp.rj, 0.0);
+      for (int s = 0; s < rg.n_runs; ++s)
+        for (int q = 0; q < p->rp.runs[(size_t)s].len; ++q) {
+          const int64_t t = ((int64_t)p->rp.runs[(size_t)s].a0 + q + p->n_pre_remove) * p->down - p->n_pre_pad;
+          for (int i = 0; i < rg.n_steps; ++i) {
+            const int64_t idx = t % p->up + (int64_t)i * p->up;
+            if (idx < ntaps) p->table[((size_t)s * rg.n_steps + i) * p->rp.rj + q] = taps_host[idx];
+          }
+        }
+      cudaError_t e2 = cudaMalloc(&p->table_dev, p->table.size() * sizeof(double));
+      if (e2 == cudaSuccess) e2 = cudaMalloc(&p->runs_dev, p->rp.runs.size() * sizeof(RunDesc));
+      if (e2 == cudaSuccess)
+        e2 = cudaMemcpy(p->table_dev, p->table.data(), p->table.size() * sizeof(double), cudaMemcpyHostToDevice);
+      if (e2 == cudaSuccess)
+        e2 = cudaMemcpy(p->runs_dev, p->rp.runs.data(), p->rp.runs.size() * sizeof(RunDesc), cudaMemcpyHostToDevice);
+      if (e2 != cudaSuccess) { impb_resample_plan_destroy(p); return cuda_fail(e2, "resample run tables"); }
+      p->runs_ok = true;
+    }
+  }
+  *out = p;
+  return IMPB_OK;
+}
+
+void impb_resample_plan_destroy(impb_resample* p) {
+  if (!p) return;
+  DeviceGuard g(p->ctx->device);
+  cudaFree(p->taps_dev);
+  cudaFree(p->table_dev);
+  cudaFree(p->runs_dev);
+  delete p;
+}
+
+int32_t impb_resample_execute(impb_resample* p, const double* src, int64_t ld_src, int64_t n, const double* decay,
+                              double* dst, int64_t ld_dst, int64_t batch, void* stream) {
+  if (!p || !src || !dst || n < 0 || ld_src < n || batch < 0) {
+    set_error("impb_resample_execute: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (!p->runs_ok || n == 0 || batch == 0)
+    return impb_window_resample(p->ctx, src, ld_src, n, decay, p->taps_dev, p->ntaps, p->up, p->down, dst, ld_dst, batch,
+                                stream);
+  const int64_t n_out = (n * p->up + p->down - 1) / p->down;
+  if (ld_dst < n_out) { set_error("impb_resample_execute: ld_dst < ceil(n*up/down)"); return IMPB_EINVAL; }
+  DeviceGuard g(p->ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  // A/B switch: IMPB_RESAMPLE_CONST=1 feeds the taps through the kernel-parameter (constant) bank instead of shared
+  // memory — measured slower on B200 (3.5 ms vs 1.x ms for 896 x 96 000: the uniform-datapath loads do not keep up)
+  static const bool use_const = getenv("IMPB_RESAMPLE_CONST") != nullptr;
+  const int sms = p->ctx->sm_count > 0 ? p->ctx->sm_count : 148;
+  cudaError_t e;
+  if (use_const && p->rp.g.n_steps * p->rp.rj <= TAP_PARAM_DOUBLES) {
+    e = p->rp.rj == 12   ? launch_runs_c<12>(p, src, ld_src, n, decay, n_out, dst, ld_dst, batch, st)
+        : p->rp.rj == 14 ? launch_runs_c<14>(p, src, ld_src, n, decay, n_out, dst, ld_dst, batch, st)
+                         : launch_runs_c<16>(p, src, ld_src, n, decay, n_out, dst, ld_dst, batch, st);
+  } else {
+    e = p->rp.rj == 12   ? launch_runs<12>(p->rp, src, ld_src, n, decay, p->table_dev, p->runs_dev, n_out, dst, ld_dst,
+                                           batch, sms, st)
+        : p->rp.rj == 14 ? launch_runs<14>(p->rp, src, ld_src, n, decay, p->table_dev, p->runs_dev, n_out, dst, ld_dst,
+                                           batch, sms, st)
+                         : launch_runs<16>(p->rp, src, ld_src, n, decay, p->table_dev, p->runs_dev, n_out, dst, ld_dst,
+                                           batch, sms, st);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "k_resample_runs_c");
   return IMPB_OK;
 }
 

@@ -491,8 +491,10 @@ def window_resample(x, taps, up, down, decay=None):
     batch, n = x.shape
     g = math.gcd(int(up), int(down))
     n_out = _lib.lib().impb_resample_out_len(n, int(up), int(down))
+    g = math.gcd(int(up), int(down))
+    planned = isinstance(taps, np.ndarray) and int(up) // g > 1  # host taps, true rational ratio: ResamplePlan below
     tp = None
-    if taps is not None:
+    if taps is not None and not planned:
         tp = taps if isinstance(taps, torch.Tensor) else torch.as_tensor(np.asarray(taps, np.float64), device=dev)
     dc = None
     if decay is not None:
@@ -513,12 +515,55 @@ def window_resample(x, taps, up, down, decay=None):
         full = _decimation_plan(taps if isinstance(taps, np.ndarray) else tp, n, _dev(x)).execute(x)
         return full[:, ::d][:, :n_out].contiguous()
     out = torch.empty((batch, n_out), dtype=torch.float64, device=dev)
+    if planned:
+        # host taps (what nnresample hands to resample_poly): planned path, per-run tap tables in the kernel's
+        # parameter space (csrc/resample.cu: k_resample_runs_c); bit-identical to the generic kernels
+        plan = _resample_plan(taps, u, d, _dev(x))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().impb_resample_execute(plan.handle, x.data_ptr(), n, n,
+                                                        None if dc is None else dc.data_ptr(), out.data_ptr(), n_out,
+                                                        batch, _stream(x)), "impb_resample_execute")
+        return out
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().impb_window_resample(
             _lib.context(_dev(x)).handle, x.data_ptr(), n, n, None if dc is None else dc.data_ptr(),
             None if tp is None else tp.data_ptr(), 0 if tp is None else tp.numel(), u, d,
             out.data_ptr(), n_out, batch, _stream(x)), "impb_window_resample")
     return out
+
+
+class ResamplePlan:
+    """``impb_resample``: host tap tables of one (taps, up, down) on one device."""
+
+    def __init__(self, taps: np.ndarray, up: int, down: int, device: int = 0):
+        taps = np.ascontiguousarray(taps, dtype=np.float64)
+        self.ctx = _lib.context(device)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().impb_resample_plan_create(self.ctx.handle, taps.ctypes.data, taps.size, int(up), int(down),
+                                                        C.byref(h)), "impb_resample_plan_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().impb_resample_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_resample_plans = {}
+_resample_lock = threading.Lock()
+
+
+def _resample_plan(taps: np.ndarray, up: int, down: int, device: int) -> ResamplePlan:
+    key = (hash(taps.tobytes()), taps.size, int(up), int(down), int(device))
+    with _resample_lock:
+        plan = _resample_plans.get(key)
+        if plan is None:
+            if len(_resample_plans) > 16:
+                _resample_plans.clear()
+            plan = _resample_plans[key] = ResamplePlan(taps, up, down, device)
+    return plan
 
 
 _decim_plans = {}

@@ -246,6 +246,18 @@ IMPB_API int32_t impb_window_resample(impb_ctx* ctx, const double* src, int64_t 
                              const double* taps, int64_t ntaps, int32_t up, int32_t down, double* dst,
                              int64_t ld_dst, int64_t batch, void* stream);
 
+/* Planned form of the same operation for callers that hold the taps on the HOST (the reference does: nnresample
+ * designs the window with numpy and hands it to resample_poly, core/impulse_response.py:121-124).  The plan keeps
+ * per-run tap tables that travel to the kernel in its parameter space (constant bank), see csrc/resample.cu;
+ * ratios without long runs of unit-step outputs (and every up == 1 decimation) run the kernels of
+ * impb_window_resample on a device copy of the taps.  Results are bit-identical between the two entry points. */
+typedef struct impb_resample impb_resample;
+IMPB_API int32_t impb_resample_plan_create(impb_ctx* ctx, const double* taps_host, int64_t ntaps, int32_t up, int32_t down,
+                                  impb_resample** out);
+IMPB_API void impb_resample_plan_destroy(impb_resample* plan);
+IMPB_API int32_t impb_resample_execute(impb_resample* plan, const double* src, int64_t ld_src, int64_t n,
+                              const double* decay, double* dst, int64_t ld_dst, int64_t batch, void* stream);
+
 /* ---- output packing (next-row component) -------------------------------------------------------
  * Replaces the np.vstack / transpose / libsndfile PCM conversion of HRIR.write_wav (core/hrir.py:426-455) and
  * audio_io.write_wav (core/audio_io.py:82-97).  row_offsets: device int64[n_tracks], element offset of each
