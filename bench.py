@@ -415,22 +415,30 @@ def main():
         torch.cuda.synchronize()
         fp32["whole_path_ir_per_s"] = 3 * B / (a.elapsed_time(b) / 1e3)
     # secondary: per-IR frequency-response post-processing on the cropped responses of one step
-    for _ in range(2):
-        post = disp.postprocess(res)
-    torch.cuda.synchronize()
-    tp = []
-    for _ in range(3):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        post = disp.postprocess(res)
-        b.record()
+    def time_post(**kw):
+        for _ in range(2):
+            post = disp.postprocess(res, **kw)
         torch.cuda.synchronize()
-        tp.append(a.elapsed_time(b))
-    fr_ms = float(np.mean(tp))
-    fr_post = {"value": S * N_IRS / (fr_ms / 1e3), "unit": "IR/s", "ms_per_step": fr_ms, "fir_taps": int(post[0][3].shape[1]),
+        tp = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            post = disp.postprocess(res, **kw)
+            b.record()
+            torch.cuda.synchronize()
+            tp.append(a.elapsed_time(b))
+        return float(np.mean(tp)), int(post[0][3].shape[1])
+
+    fr_ms, fir_taps = time_post()
+    eqw_ms, _ = time_post(worker=True)
+    fr_post = {"value": S * N_IRS / (fr_ms / 1e3), "unit": "IR/s", "ms_per_step": fr_ms, "fir_taps": fir_taps,
                "what": "frequency_response + smoothen_fractional_octave(1/3) + minimum_phase_impulse_response(f_res=5) "
-                       "per cropped IR (BatchDispatcher.postprocess), device resident, one GPU"}
-    del post
+                       "per cropped IR (BatchDispatcher.postprocess), device resident, one GPU",
+               "equalization_worker": {
+                   "value": S * N_IRS / (eqw_ms / 1e3), "unit": "IR/s", "ms_per_step": eqw_ms,
+                   "what": "frequency_response + the whole process_equalization_worker arithmetic per cropped IR: "
+                           "smoothen_heavy_light (4 SG blends) + equalize(max_gain=40) on the device (K21) + "
+                           "minimum_phase_impulse_response(f_res=5)"}}
     bytes_per_ir = (8 + (8 if args.precision == 64 else 4)) * L
     peak, peak_src = measured_peak()
     achieved = B * bytes_per_ir / (k1_ms / 1e3) / 1e9

@@ -60,6 +60,7 @@ SIGNATURES = {
     "impb_minphase_destroy": (None, [c_vp]),
     "impb_minphase_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "impb_minphase_fir": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "impb_equalize": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "impb_pack_tracks": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "impb_resample_out_len": (c_i64, [c_i64, c_i32, c_i32]),
     "impb_resample_plan_create": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, C.POINTER(c_vp)]),

@@ -472,6 +472,130 @@ __global__ void k_homomorphic_window(double* __restrict__ w, int64_t n_fft) {
   w[i] = v;
 }
 
+
+// ================================================================================================
+// K21 — FrequencyResponse.equalize  (autoeq/frequency_response.py:1241-1310)
+// ================================================================================================
+// One CTA per curve, everything in shared memory (F <= EQ_MAXF points):
+//   gain = -error * gain_k;  clipped = gain > cap;  eq = where(clipped, cap, gain)
+//   kinks = indices i >= 1 where clipped changes;  every point within `half` of a kink is dropped, except the last two
+//   eq = InterpolatedUnivariateSpline(logf[keep], eq[keep], k=2)(logf)
+// The k = 2 interpolating spline of FITPACK (fpcurf with s = 0) puts its interior knots midway between the data sites,
+// t = [x0, x0, x0, (x1+x2)/2, ..., (x_{m-3}+x_{m-2})/2, x_{m-1}, x_{m-1}, x_{m-1}], so every site x_i (0 < i < m-1)
+// lies in knot interval i+1 and the collocation matrix is TRIDIAGONAL (B_{i-1}, B_i, B_{i+1} at x_i; c_0 = y_0,
+// c_{m-1} = y_{m-1}).  It is totally positive, so elimination without pivoting is stable; FITPACK solves the same
+// system with Givens rotations — agreement is to rounding (tests: <= 1e-9 dB against the reference golden).
+constexpr int EQ_MAXF = 2048;
+
+struct EqShared {
+  double x[EQ_MAXF];    // kept sites (log10 f)
+  double y[EQ_MAXF];    // kept values, then spline coefficients
+  double eq[EQ_MAXF];   // clipped gain at every point
+  double t[EQ_MAXF + 3];
+  double cp[EQ_MAXF];   // Thomas scratch
+  int keep[EQ_MAXF];
+  int m;
+};
+
+// quadratic B-spline values N_{l-2}, N_{l-1}, N_l at x inside knot interval [t_l, t_{l+1})  (de Boor recursion, fpbspl)
+__device__ __forceinline__ void bspl2(const double* t, int l, double x, double* h) {
+  double h0 = 1.0, h1, h2;
+  {  // degree 1
+    const double f = h0 / (t[l + 1] - t[l]);
+    h0 = f * (t[l + 1] - x);
+    h1 = f * (x - t[l]);
+  }
+  {  // degree 2
+    const double f0 = h0 / (t[l + 1] - t[l - 1]);
+    const double f1 = h1 / (t[l + 2] - t[l]);
+    h2 = f1 * (x - t[l]);
+    h1 = f0 * (x - t[l - 1]) + f1 * (t[l + 2] - x);
+    h0 = f0 * (t[l + 1] - x);
+  }
+  h[0] = h0; h[1] = h1; h[2] = h2;
+}
+
+__global__ void __launch_bounds__(256) k_equalize(const double* __restrict__ error, int64_t ld_err,
+                                                  const double* __restrict__ logf, const double* __restrict__ cap,
+                                                  const double* __restrict__ gain_k, int n, int half, int smoothen,
+                                                  double* __restrict__ out, int64_t ld_out, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char eq_raw[];
+  EqShared& sh = *reinterpret_cast<EqShared*>(eq_raw);
+  const int b = blockIdx.x;
+  const double* err = error + (size_t)b * ld_err;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double g = -err[i] * gain_k[i];
+    const bool cl = g > cap[i];
+    sh.eq[i] = cl ? cap[i] : g;
+    sh.keep[i] = cl ? 3 : 1;  // bit 1: clipped flag (scratch), bit 0: keep
+  }
+  __syncthreads();
+  if (!smoothen) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[(size_t)b * ld_out + i] = sh.eq[i];
+    if (threadIdx.x == 0 && status) status[b] = 0;
+    return;
+  }
+  // kink windows: a point is dropped when a change of the clipped flag lies within `half` points of it
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    bool doomed = false;
+    const int lo = max(i - half, 1), hi = min(i + half, n - 1);
+    for (int k = lo; k <= hi && !doomed; ++k) doomed = ((sh.keep[k] >> 1) != (sh.keep[k - 1] >> 1));
+    if (i >= n - 2) doomed = false;  // the last two points are never dropped
+    sh.cp[i] = doomed ? 0.0 : 1.0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+      if (sh.cp[i] != 0.0) { sh.x[m] = logf[i]; sh.y[m] = sh.eq[i]; ++m; }
+    sh.m = m;
+  }
+  __syncthreads();
+  const int m = sh.m;
+  if (m < 3) {  // dfitpack raises for m <= k; the host turns the status into the same kind of error
+    if (threadIdx.x == 0 && status) status[b] = 1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[(size_t)b * ld_out + i] = sh.eq[i];
+    return;
+  }
+  for (int j = threadIdx.x; j < m + 3; j += blockDim.x) {
+    double v;
+    if (j < 3) v = sh.x[0];
+    else if (j >= m) v = sh.x[m - 1];
+    else v = 0.5 * (sh.x[j - 2] + sh.x[j - 1]);  // t[3 + i] = (x[i+1] + x[i+2]) / 2
+    sh.t[j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // tridiagonal collocation system: row i (1 <= i <= m-2): a_i c_{i-1} + d_i c_i + u_i c_{i+1} = y_i
+    double* c = sh.y;
+    double* cpp = sh.cp;  // modified upper diagonal
+    cpp[0] = 0.0;         // row 0: c_0 = y_0
+    for (int i = 1; i <= m - 2; ++i) {
+      double h[3];
+      bspl2(sh.t, i + 1, sh.x[i], h);
+      const double den = h[1] - h[0] * cpp[i - 1];
+      cpp[i] = h[2] / den;
+      c[i] = (c[i] - h[0] * c[i - 1]) / den;
+    }
+    // row m-1: c_{m-1} = y_{m-1}; back substitution
+    for (int i = m - 2; i >= 1; --i) c[i] -= cpp[i] * c[i + 1];
+  }
+  __syncthreads();
+  // evaluate at every grid point (splev): interval by binary search over the interior knots t[3 .. m-1]
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double xv = fmin(fmax(logf[i], sh.t[2]), sh.t[m]);
+    int lo = 2, hi = m - 1;  // largest l in [2, m-1] with t[l] <= xv
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (sh.t[mid] <= xv) lo = mid; else hi = mid - 1;
+    }
+    double h[3];
+    bspl2(sh.t, lo, xv, h);
+    out[(size_t)b * ld_out + i] = h[0] * sh.y[lo - 2] + h[1] * sh.y[lo - 1] + h[2] * sh.y[lo];
+  }
+  if (threadIdx.x == 0 && status) status[b] = 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -778,6 +902,23 @@ int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_t ld_gain
     ColInvReal c3{ws_small, ps.N, ps.N2, fir_out + (size_t)b0 * ld_out, ld_out, mp->n, nullptr, 1.0 / (double)nt};
     if ((rc = mp->small.col_inv<TILE>(c3, nb, st))) return rc;
   }
+  IMPB_CUDA(cudaGetLastError());
+  return IMPB_OK;
+}
+
+int32_t impb_equalize(impb_ctx* ctx, const double* error, int64_t ld_err, const double* logf, const double* cap,
+                      const double* gain_k, int64_t n, int32_t half_window, int32_t smoothen, double* out, int64_t ld_out,
+                      int32_t* status, int64_t batch, void* stream) {
+  if (!ctx || !error || !logf || !cap || !gain_k || !out || n < 1 || n > EQ_MAXF || ld_err < n || ld_out < n ||
+      batch < 0 || half_window < 0) {
+    set_error("impb_equalize: bad argument (n must be 1..%d)", EQ_MAXF);
+    return IMPB_EINVAL;
+  }
+  if (batch == 0) return IMPB_OK;
+  DeviceGuard g(ctx->device);
+  IMPB_CUDA(cudaFuncSetAttribute(k_equalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EqShared)));
+  k_equalize<<<(unsigned)batch, 256, sizeof(EqShared), (cudaStream_t)stream>>>(error, ld_err, logf, cap, gain_k, (int)n,
+                                                                             half_window, smoothen, out, ld_out, status);
   IMPB_CUDA(cudaGetLastError());
   return IMPB_OK;
 }

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import ops
 from .constants import IPSILATERAL_PAIRS, ONSET_GROUPS, SPEAKER_DELAYS, speaker_side
-from .frequency_response import minimum_phase_batch, next_fast_len, smoothen_batch
+from .frequency_response import equalize_batch, minimum_phase_batch, next_fast_len, smoothen_batch
 from .hrir import ingest_layout
 from .impulse_response import frequency_response_batch
 
@@ -409,7 +409,7 @@ class BatchDispatcher:
         return out
 
     # ---- per-IR frequency-response post-processing -----------------------------------------------------------
-    def postprocess(self, results, window_size=1 / 3, f_res=5, normalize=False):
+    def postprocess(self, results, window_size=1 / 3, f_res=5, normalize=False, worker=False):
         """frequency_response -> smoothen_fractional_octave(window_size) -> minimum-phase FIR of the inverse
         smoothed response, for every row of every set (sets of equal tail share launches).
         Returns per set ``(frequency[F], raw[n,F], smoothed[n,F], fir[n,taps])`` as CUDA tensors."""
@@ -423,14 +423,32 @@ class BatchDispatcher:
         for tail, idxs in by_tail.items():
             data = torch.cat([results[i].data for i in idxs]) if len(idxs) > 1 else results[idxs[0]].data
             raw = frequency_response_batch(data, self.fs)
-            sm = smoothen_batch(grid, raw, window_size, 1, window_size, 1, 100.0, 10000.0)
-            eq = -(sm - sm.mean(dim=1, keepdim=True))
-            fir = minimum_phase_batch(grid, eq, fs=self.fs, f_res=f_res, normalize=normalize)
+            if worker:  # the whole EQ-worker arithmetic, equalize() included (core/parallel_workers.py:98-131)
+                sm, _eq, fir = equalization_worker_batch(grid, raw, self.fs, f_res=f_res)
+            else:
+                sm = smoothen_batch(grid, raw, window_size, 1, window_size, 1, 100.0, 10000.0)
+                eq = -(sm - sm.mean(dim=1, keepdim=True))
+                fir = minimum_phase_batch(grid, eq, fs=self.fs, f_res=f_res, normalize=normalize)
             n = results[idxs[0]].data.shape[0]
             for k, i in enumerate(idxs):
                 sl = slice(k * n, (k + 1) * n)
                 out[i] = (grid, raw[sl], sm[sl], fir[sl])
         return out
+
+
+def equalization_worker_batch(frequency, raw, fs, max_gain=40, f_res=5):
+    """The arithmetic of ``process_equalization_worker`` (reference core/parallel_workers.py:98-131) for rows of raw
+    responses already on the device: error = raw - mean(raw) (flat target), ``smoothen_heavy_light`` (four
+    Savitzky-Golay blends), ``equalize(max_gain, treble 10 kHz .. fs/2)`` (K21) and the ``f_res``-Hz minimum-phase
+    FIR.  CUDA tensors in and out: ``(error_smoothed, equalization, fir)``."""
+    import torch
+    err = raw - raw.mean(dim=1, keepdim=True)
+    light = smoothen_batch(frequency, err, 1 / 6, 1, 1 / 3, 1, 100, 10000)
+    heavy = smoothen_batch(frequency, err, 1 / 3, 1, 1.3, 1, 1000, 6000)
+    err_s = smoothen_batch(frequency, torch.maximum(light, heavy), 1 / 3, 1, 1 / 3, 1, 100, 10000)
+    eq = equalize_batch(frequency, err_s, max_gain=max_gain, treble_f_lower=10000, treble_f_upper=fs / 2)
+    fir = minimum_phase_batch(frequency, eq, fs=fs, f_res=f_res, normalize=False)
+    return err_s, eq, fir
 
 
 def equalization_firs(items, room_frs, hp_left, hp_right, eq_left, eq_right, target, common_freq, estimator_fs,
@@ -441,7 +459,7 @@ def equalization_firs(items, room_frs, hp_left, hp_right, eq_left, eq_right, tar
     ``items``: [(speaker, side), ...].  Returns ``[(speaker, side, fir), ...]`` in input order, like
     ``parallel_map`` does.  The error curves are summed on the host exactly as the worker does; the four
     Savitzky-Golay blends of ``smoothen_heavy_light`` and the minimum-phase design run as ONE launch each over all
-    items; ``FrequencyResponse.equalize`` (kink set + k=2 spline) stays per item on the host."""
+    items, and so does ``FrequencyResponse.equalize`` (K21: gain clip, kink windows, k=2 spline): no per-item loop."""
     from .frequency_response import FrequencyResponse
     items = list(items)
     if not items:
@@ -464,16 +482,21 @@ def equalization_firs(items, room_frs, hp_left, hp_right, eq_left, eq_right, tar
     raw = np.stack([fr.raw for fr in frs])
     if np.any(np.isnan(err)) or np.any(np.isnan(raw)):
         raise ValueError('NaN values present, cannot smoothen!')
-    # smoothen_heavy_light for every item at once (reference autoeq/frequency_response.py:1181-1239)
-    light = smoothen_batch(freq, err, 1 / 6, 1, 1 / 3, 1, 100, 10000)
-    heavy = smoothen_batch(freq, err, 1 / 3, 1, 1.3, 1, 1000, 6000)
-    both = smoothen_batch(freq, np.concatenate([raw, np.maximum(light, heavy)]), 1 / 3, 1, 1 / 3, 1, 100, 10000)
+    # smoothen_heavy_light for every item at once (reference autoeq/frequency_response.py:1181-1239), device resident
+    # from here to the FIR taps: one upload of the summed error rows, one download of the filters
+    import torch
+    from .frequency_response import _to_dev
+    err_d, raw_d = _to_dev(err), _to_dev(raw)
+    light = smoothen_batch(freq, err_d, 1 / 6, 1, 1 / 3, 1, 100, 10000)
+    heavy = smoothen_batch(freq, err_d, 1 / 3, 1, 1.3, 1, 1000, 6000)
+    both = smoothen_batch(freq, torch.cat([raw_d, torch.maximum(light, heavy)]), 1 / 3, 1, 1 / 3, 1, 100, 10000)
     n = len(frs)
-    for i, fr in enumerate(frs):
-        fr.smoothed, fr.error_smoothed = both[i], both[n + i]
-        fr.equalize(max_gain=max_gain, treble_f_lower=10000, treble_f_upper=estimator_fs / 2)
-    firs = minimum_phase_batch(freq, np.stack([fr.equalization for fr in frs]), fs=estimator_fs, f_res=f_res,
-                               normalize=False)
+    # FrequencyResponse.equalize for every item in ONE launch (K21), straight from the smoothed error rows
+    eq, status = equalize_batch(freq, both[n:], max_gain=max_gain, treble_f_lower=10000, treble_f_upper=estimator_fs / 2,
+                                return_status=True)
+    firs = minimum_phase_batch(freq, eq, fs=estimator_fs, f_res=f_res, normalize=False).cpu().numpy()
+    if int(status.max().item()) != 0:
+        raise ValueError("equalize: too few points left for the k=2 interpolating spline (m > k must hold)")
     return [(spk, side, firs[i]) for i, (spk, side) in enumerate(items)]
 
 

@@ -113,6 +113,31 @@ def smoothen_batch(frequency, data, window_size_oct=DEFAULT_SMOOTHING_WINDOW_SIZ
     return y.cpu().numpy() if is_np else y
 
 
+def equalize_batch(frequency, error, max_gain=DEFAULT_MAX_GAIN, smoothen=True, treble_f_lower=DEFAULT_TREBLE_F_LOWER,
+                   treble_f_upper=DEFAULT_TREBLE_F_UPPER, treble_max_gain=DEFAULT_TREBLE_MAX_GAIN,
+                   treble_gain_k=DEFAULT_TREBLE_GAIN_K, return_status=False):
+    """K21 on rows of (smoothed) error curves that share ``frequency``: the ``equalization`` curves of
+    ``FrequencyResponse.equalize`` (reference :1241-1305).  numpy in -> numpy out, CUDA tensor in -> CUDA tensor out.
+    The two log-frequency sigmoids (gain cap, gain factor) and the 1/12-octave kink window are host constants of the
+    grid, exactly as the reference derives them."""
+    frequency = np.asarray(frequency, dtype=np.float64)
+    is_np = isinstance(error, np.ndarray)
+    if is_np and np.any(np.isnan(error)):
+        raise ValueError('NaN values detected during equalization, interpolating data with default parameters.')
+    e = _to_dev(np.atleast_2d(error)) if is_np else (error if error.dim() == 2 else error[None, :])
+    cap = sigmoid(frequency, treble_f_lower, treble_f_upper, a_normal=max_gain, a_treble=treble_max_gain)
+    gain_k = sigmoid(frequency, treble_f_lower, treble_f_upper, a_normal=1.0, a_treble=treble_gain_k)
+    half = (window_size(frequency, 1 / 12) - 1) // 2
+    eq, status = ops.equalize(e, np.log10(frequency), cap, gain_k, half, smoothen)
+    if return_status:  # the caller checks (and synchronises) when it reads its results
+        return (eq.cpu().numpy(), status) if is_np else (eq, status)
+    if is_np:
+        if int(status.max().item()) != 0:  # fewer than 3 points survive the kink windows: dfitpack's error
+            raise ValueError("equalize: too few points left for the k=2 interpolating spline (m > k must hold)")
+        return eq.cpu().numpy()
+    return eq
+
+
 def minphase_gain_grid(frequency, equalization, fs, f_res, normalize):
     """Host part of minimum_phase_impulse_response (reference :653-676) for rows of ``equalization``:
     log-f interpolation onto linspace(0, fs//2, n) on the device, then the dB -> linear shaping.
@@ -348,12 +373,12 @@ class FrequencyResponse:
         self.reset(raw=False, smoothed=False, error=False, error_smoothed=False, equalization=True, parametric_eq=True,
                    fixed_band_eq=True, equalized_raw=True, equalized_smoothed=True, target=False)
 
-    # ---- a17: stays on the host (SURVEY.md §7 "keep on host in v1") -------------------------------------
+    # ---- a17 = K21 ----------------------------------------------------------------------------------------
     def equalize(self, max_gain=DEFAULT_MAX_GAIN, smoothen=True, treble_f_lower=DEFAULT_TREBLE_F_LOWER,
                  treble_f_upper=DEFAULT_TREBLE_F_UPPER, treble_max_gain=DEFAULT_TREBLE_MAX_GAIN,
                  treble_gain_k=DEFAULT_TREBLE_GAIN_K):
-        """Reference :1241-1310."""
-        from scipy.interpolate import InterpolatedUnivariateSpline
+        """Reference :1241-1310 (clip to the sigmoid gain cap, drop the kink windows, k=2 spline over log f) on the
+        device (``impb_equalize``)."""
         self.equalization = []
         self.equalized_raw = []
         if len(self.error_smoothed):
@@ -362,24 +387,11 @@ class FrequencyResponse:
             error = self.error
         else:
             raise ValueError('Error data is missing. Call FrequencyResponse.compensate().')
-        if np.any(np.isnan(np.asarray(error, dtype=float))):
+        error = np.asarray(error, dtype=float)
+        if np.any(np.isnan(error)):
             raise ValueError('NaN values detected during equalization, interpolating data with default parameters.')
-        cap = self._sigmoid(treble_f_lower, treble_f_upper, a_normal=max_gain, a_treble=treble_max_gain)
-        gain = -error * self._sigmoid(treble_f_lower, treble_f_upper, a_normal=1.0, a_treble=treble_gain_k)
-        clipped = gain > cap
-        kinks = np.flatnonzero(np.concatenate(([clipped[0]], clipped[1:] != clipped[:-1])))
-        if len(kinks) and kinks[0] == 0:
-            kinks = kinks[1:]
-        self.equalization = np.where(clipped, cap, gain)
-        if smoothen:
-            half = (self._window_size(1 / 12) - 1) // 2
-            n = len(self.equalization)
-            keep = np.ones(n, dtype=bool)
-            for i in kinks:
-                keep[i - min(i, half): i + 1 + min(n - i - 1, half)] = False
-            keep[n - 2:] = True  # the last two points are never dropped
-            spline = InterpolatedUnivariateSpline(np.log10(self.frequency[keep]), self.equalization[keep], k=2)
-            self.equalization = spline(np.log10(self.frequency))
+        self.equalization = equalize_batch(self.frequency, error[None, :], max_gain, smoothen, treble_f_lower,
+                                           treble_f_upper, treble_max_gain, treble_gain_k)[0]
         self.equalized_raw = self.raw + self.equalization
         if len(self.smoothed):
             self.equalized_smoothed = self.smoothed + self.equalization

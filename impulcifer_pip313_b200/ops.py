@@ -426,6 +426,27 @@ def savgol_blend(y, w_normal, it_normal, w_treble, it_treble, k_treble):
     return out
 
 
+# ---- K21 --------------------------------------------------------------------------------------------
+def equalize(error, logf, cap, gain_k, half_window, smoothen=True):
+    """rows of error curves -> (equalization rows, int32 status per row) — ``impb_equalize`` (K21)."""
+    torch = _torch()
+    if error.dim() == 1:
+        error = error[None, :]
+    error = error.contiguous()
+    dev = error.device
+    batch, n = error.shape
+    tabs = [t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t, np.float64), device=dev)
+            for t in (logf, cap, gain_k)]
+    out = torch.empty_like(error)
+    status = torch.zeros(batch, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_equalize(_lib.context(_dev(error)).handle, error.data_ptr(), n, tabs[0].data_ptr(),
+                                            tabs[1].data_ptr(), tabs[2].data_ptr(), n, int(half_window),
+                                            1 if smoothen else 0, out.data_ptr(), n, status.data_ptr(), batch,
+                                            _stream(error)), "impb_equalize")
+    return out, status
+
+
 # ---- K12 + K13 ------------------------------------------------------------------------------------
 class MinPhasePlan:
     def __init__(self, n: int, device: int = 0):

@@ -223,6 +223,16 @@ IMPB_API int32_t impb_savgol_blend(impb_ctx* ctx, const double* y, int64_t n, in
                           const double* edge_treble, const double* k_treble, double* out, int64_t ld_out,
                           int64_t batch, void* stream);
 
+/* ---- K21: equalization curve ---------------------------------------------------------------------------------
+ * Replaces FrequencyResponse.equalize, autoeq/frequency_response.py:1241-1310, for rows of error curves on one
+ * frequency grid: gain = -error * gain_k clipped to cap (both [n], the host's log-frequency sigmoids), kink windows
+ * of +-half_window points dropped (not the last two points), k = 2 interpolating spline over log10 f re-evaluated on
+ * the grid (smoothen = 0: clipped gain only).  status (nullable, device int32[batch]): 1 where fewer than 3 points
+ * survive (the reference raises from dfitpack there).  n <= 2048. */
+IMPB_API int32_t impb_equalize(impb_ctx* ctx, const double* error, int64_t ld_err, const double* logf, const double* cap,
+                      const double* gain_k, int64_t n, int32_t half_window, int32_t smoothen, double* out,
+                      int64_t ld_out, int32_t* status, int64_t batch, void* stream);
+
 /* ---- K12+K13: minimum-phase FIR ---------------------------------------------------------------------------
  * Replaces scipy firwin2 + minimum_phase(method='homomorphic', half=True) as called by
  * FrequencyResponse.minimum_phase_impulse_response, autoeq/frequency_response.py:672-680.

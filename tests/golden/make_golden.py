@@ -14,6 +14,7 @@ stubs only, no arithmetic restated) and records what the reference itself comput
   room_chain_golden.npz  room / headphone FR chains, channel-balance FIRs, microphone-mismatch estimator on the same set
   decay_chain_golden.npz decay times, reflection levels, decay-adjustment parameters, virtual bass on the same set
   decay_window_golden.npz  ``apply_decay_window`` on fixed parameters + ``process_decay_worker`` on the same set (a11 pin)
+  equalize_golden.npz    ``FrequencyResponse.equalize`` on clipped / unclipped error curves (a17 pin)
   small_cases.npz        tiny estimators from the reference's own tests (fs=2000/0.05 s, fs=48000/1 s)
 """
 import os
@@ -403,6 +404,39 @@ def decay_window():
     print('decay_window: changed', [bool(gold[k]) for k in gold if k.startswith('worker_changed_')])
 
 
+def equalize_cases():
+    """a17 pin: the reference's own ``FrequencyResponse.equalize`` (autoeq/frequency_response.py:1241-1310) on error
+    curves that clip against the gain cap in one, several and no regions (kink windows + k=2 FITPACK spline), with the
+    default arguments and with the EQ worker's (max_gain=40, treble 10 kHz .. fs/2)."""
+    rng = np.random.default_rng(21)
+    f = FrequencyResponse.generate_frequencies(f_step=1.01, f_min=10, f_max=24000)
+    lf = np.log10(f)
+    curves = [
+        -3 * np.sin(2.2 * lf) - 2 * np.cos(5 * lf),                                  # never clipped (|gain| < 6)
+        -9 * np.sin(2.2 * lf) - 2 * np.cos(5 * lf),                                  # several clipped regions
+        -12 * np.exp(-((lf - 2.3) / 0.15) ** 2) + 1.5 * np.sin(9 * lf),              # one clipped hump
+        -20 * (lf < 1.4) + 2 * np.sin(7 * lf),                                       # clipped from the first point on
+        -15 * (lf > 4.2) - 3 * np.cos(3 * lf),                                       # clipped up to the last point
+        6 * rng.standard_normal(len(f)).cumsum() / np.sqrt(np.arange(1, len(f) + 1)),  # rough curve, many kinks
+        -45 * np.exp(-((lf - 3.0) / 0.3) ** 2) + 3 * np.sin(4 * lf),                 # clips even against 40 dB
+    ]
+    gold = {'frequency': f, 'error_smoothed': np.stack(curves)}
+    for tag, kw in (('default', {}), ('worker', dict(max_gain=40, treble_f_lower=10000, treble_f_upper=24000.0)),
+                    ('nosmooth', dict(smoothen=False)), ('treble', dict(treble_max_gain=0.0, treble_gain_k=0.5))):
+        out = []
+        for e in curves:
+            fr = FrequencyResponse(name='eq', frequency=f.copy(), raw=np.zeros(len(f)), error=e.copy(),
+                                   error_smoothed=e.copy(), smoothed=np.ones(len(f)))
+            fr.equalize(**kw)
+            out.append(np.asarray(fr.equalization, dtype=np.float64))
+            if tag == 'default':
+                assert np.allclose(fr.equalized_smoothed, 1.0 + fr.equalization)
+        gold[f'eq_{tag}'] = np.stack(out)
+    np.savez_compressed(os.path.join(HERE, 'equalize_golden.npz'), **gold)
+    clipped = [(int(np.sum(-c > 6))) for c in curves]
+    print('equalize_cases: points above the 6 dB cap per curve', clipped)
+
+
 def small_cases():
     gold = {}
     rng = np.random.default_rng(7)
@@ -472,7 +506,7 @@ def small_cases():
 
 if __name__ == '__main__':
     only = sys.argv[1:]
-    for fn in (demo_room, synth71, room_chain, decay_chain, decay_window, small_cases):
+    for fn in (demo_room, synth71, room_chain, decay_chain, decay_window, equalize_cases, small_cases):
         if not only or fn.__name__ in only:
             fn()
     for f in sorted(os.listdir(HERE)):

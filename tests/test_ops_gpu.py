@@ -373,3 +373,38 @@ def test_resample_batched_ratios_match_port(T, fs_new, fs_old):
         xr = x[r].copy() if np.isnan(prm[r, 0]) else O.apply_decay_window(
             x[r].copy(), (int(prm[r, 0]), int(prm[r, 1]), int(prm[r, 2]), float(prm[r, 3])))
         assert rel_peak_err(got[r], O.resample(xr, fs_new, fs_old)) < 1e-12, r
+
+
+def test_equalize_matches_reference(T):
+    """K21 against the reference's own FrequencyResponse.equalize (tests/golden/make_golden.py::equalize_cases):
+    unclipped curves, one / many clipped regions, clipping from the first and up to the last point, the EQ worker's
+    arguments, smoothen=False and a treble-limited gain; object API and batched API."""
+    from impulcifer_pip313_b200.frequency_response import FrequencyResponse, equalize_batch
+    g = load('equalize_golden.npz')
+    f, err = g['frequency'], g['error_smoothed']
+    cases = (('default', {}), ('worker', dict(max_gain=40, treble_f_lower=10000, treble_f_upper=24000.0)),
+             ('nosmooth', dict(smoothen=False)), ('treble', dict(treble_max_gain=0.0, treble_gain_k=0.5)))
+    for tag, kw in cases:
+        got = equalize_batch(f, err, **kw)
+        assert got.shape == g[f'eq_{tag}'].shape
+        assert np.max(np.abs(got - g[f'eq_{tag}'])) < 1e-9, tag
+        dev = equalize_batch(f, T.from_numpy(err).cuda(), **kw)
+        assert np.array_equal(dev.cpu().numpy(), got)
+    fr = FrequencyResponse(name='eq', frequency=f.copy(), raw=np.zeros(len(f)), error=err[1].copy(),
+                           error_smoothed=err[1].copy(), smoothed=np.ones(len(f)))
+    fr.equalize()
+    assert np.max(np.abs(fr.equalization - g['eq_default'][1])) < 1e-9
+    assert np.allclose(fr.equalized_raw, fr.equalization) and np.allclose(fr.equalized_smoothed, 1.0 + fr.equalization)
+    with pytest.raises(ValueError, match='NaN values detected'):
+        bad = err[0].copy()
+        bad[5] = np.nan
+        FrequencyResponse(name='eq', frequency=f.copy(), raw=np.zeros(len(f)), error=bad).equalize()
+    with pytest.raises(ValueError, match='Error data is missing'):
+        FrequencyResponse(name='eq', frequency=f.copy(), raw=np.zeros(len(f))).equalize()
+    # clamp / invert behaviour of the reference's tests/test_frequency_response_core.py:73-96
+    fr3 = FrequencyResponse(name='t', frequency=f, raw=np.zeros(len(f)), error=np.full(len(f), -10.0))
+    fr3.equalize(max_gain=6.0, smoothen=False)
+    assert np.allclose(fr3.equalization, 6.0, atol=1e-9)
+    fr4 = FrequencyResponse(name='t', frequency=f, raw=np.zeros(len(f)), error=np.full(len(f), 3.0))
+    fr4.equalize(max_gain=6.0)
+    assert np.allclose(fr4.equalization, -3.0, atol=1e-9) and np.allclose(fr4.equalized_raw, -3.0, atol=1e-9)
