@@ -210,6 +210,157 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2], [3], [4] as extra keys of the JSON line (device resident, one rank's GPU each;
+# `value` / `config` stay configs[1]).  Synthetic inputs of the named shapes, CUDA-event timing.
+# ---------------------------------------------------------------------------------------------------------
+def _time_ms(fn, reps=3, warm=1):
+    import torch
+    for _ in range(warm):
+        out = fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.mean(ts)), out
+
+
+def named_config3(dev, local_rank, peak, sets=8):
+    """configs[2]: synthetic 192 kHz 32-bit sweep recordings (7.1 layout) -> deconvolution + crop chain -> resample
+    to 48 kHz (1:4 decimation through the FFT plan) -> fractional-octave smoothing -> 9 600-tap minimum-phase FIR."""
+    import torch
+    from impulcifer_pip313_b200 import ops, synth
+    from impulcifer_pip313_b200.dispatcher import BatchDispatcher
+    from impulcifer_pip313_b200.estimator import ImpulseResponseEstimator
+    from impulcifer_pip313_b200.frequency_response import FrequencyResponse, minimum_phase_batch, smoothen_batch
+    from impulcifer_pip313_b200.impulse_response import frequency_response_batch, resample_taps
+    fs = 192000
+    est = ImpulseResponseEstimator(min_duration=5.0, fs=fs, device=local_rank)
+    rec = synth.recording_set(est.test_signal, fs, LAYOUT, seed=7)
+    base = torch.from_numpy(rec).to(dev)
+    batch = torch.stack([base * (0.6 + 0.05 * i) for i in range(sets)])
+    del base
+    disp = BatchDispatcher(est, LAYOUT)
+    up, down, taps = resample_taps(48000, fs)
+    grid = FrequencyResponse.generate_frequencies(f_step=1.01, f_min=10, f_max=24000)
+    L = 2 * fs + len(est)
+
+    def chain():
+        res = disp.process(batch)
+        by_tail = {}
+        for r in res:
+            by_tail.setdefault(r.tail_ind, []).append(r.data)
+        firs = []
+        for tail, rows in by_tail.items():
+            x = torch.cat(rows)
+            y = ops.window_resample(x, taps, up, down)
+            raw = frequency_response_batch(y, 48000)
+            sm = smoothen_batch(grid, raw, 1 / 3, 1, 1 / 3, 1, 100.0, 10000.0)
+            firs.append(minimum_phase_batch(grid, -(sm - sm.mean(dim=1, keepdim=True)), fs=48000, f_res=5,
+                                            normalize=False))
+        return firs
+
+    ms, firs = _time_ms(chain)
+    plan = est.plan(L)
+    B = sets * N_IRS
+    out = torch.empty((B, L), dtype=torch.float64, device=dev)
+    lay = disp._layout
+    offs = (torch.arange(sets, device=dev, dtype=torch.int64)[:, None] * (2 * batch.shape[2]) + lay['offs'][None, :]).reshape(-1)
+    k1_ms, _ = _time_ms(lambda: plan.execute(batch.reshape(-1), out=out, length=L, row_offsets=offs))
+    achieved = B * 16 * L / (k1_ms / 1e3) / 1e9
+    return {"workload": "synthetic 192 kHz 32-bit sweep recordings (7.1 layout) -> deconvolution + crop -> resample to "
+                        "48 kHz -> smoothen_fractional_octave(1/3) -> minimum_phase (9 600 taps) (BASELINE.json configs[2])",
+            "sets": sets, "irs": B, "samples_per_ir": L, "fft_plan": f"{plan.n1}x{plan.n2}", "ms": ms,
+            "value": B / (ms / 1e3), "unit": "IR/s", "fir_taps": int(firs[0].shape[1]),
+            "roofline": {"bound": "hbm", "kernel": "K1 deconvolution at 192 kHz (half-width tiles)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_ir": 16 * L,
+                         "irs_per_launch": B, "ms_per_launch": k1_ms}}
+
+
+def named_config4(dev, local_rank, peak, sets=8):
+    """configs[3]: TrueHD 11-channel layout (22 responses per set) -> deconvolution + crop chain, then per set the
+    specific room corrections against a target and the headphone compensation curves, batched over `sets` sets."""
+    import torch
+    from impulcifer_pip313_b200 import HRIR, ImpulseResponse, synth
+    from impulcifer_pip313_b200 import room_correction as rc
+    from impulcifer_pip313_b200.dispatcher import BatchDispatcher
+    from impulcifer_pip313_b200.estimator import ImpulseResponseEstimator
+    from impulcifer_pip313_b200.frequency_response import FrequencyResponse
+    est = ImpulseResponseEstimator(min_duration=5.0, fs=FS, device=local_rank)
+    layout = synth.LAYOUT_TRUEHD_11
+    rec = torch.from_numpy(synth.recording_set(est.test_signal, FS, layout, seed=5)).to(dev)
+    batch = torch.stack([rec * (0.6 + 0.05 * i) for i in range(sets)])
+    hp = synth.recording_set(est.test_signal, FS, ['FL', 'FR'], seed=6)
+    disp = BatchDispatcher(est, layout)
+    g48 = FrequencyResponse.generate_frequencies(f_step=1.01, f_min=10, f_max=FS / 2)
+    target = FrequencyResponse(name='t', frequency=g48.copy(), raw=-1.2 * (np.log10(g48) - 3.0))
+
+    def chain():
+        out = []
+        hh = HRIR(est)
+        hh.ingest(hp, FS, ['FL', 'FR'])
+        left, right = rc.headphone_compensation(hh)
+        for res in disp.process(batch):
+            h = HRIR(est)
+            h.irs = {}
+            for name, row in zip(res.names, res.data):
+                spk, side = name.split('-')
+                ir = ImpulseResponse(np.zeros(0), FS)
+                ir._set_device(row)
+                h.irs.setdefault(spk, {})[side] = ir
+            out.append(rc.calculate_specific_room_corrections(h, target, limit=400))
+        return out, left, right
+
+    ms, (frs, left, right) = _time_ms(chain, reps=2)
+    n_irs = sets * 2 * len(layout)
+    return {"workload": "TrueHD 11-channel layout (22 responses per set) -> deconvolution + crop -> specific room "
+                        "corrections + headphone compensation, batched (BASELINE.json configs[3])",
+            "sets": sets, "irs": n_irs, "ms": ms, "value": n_irs / (ms / 1e3), "unit": "IR/s",
+            "room_curves": int(sum(len(p) for f in frs for p in f.values()))}
+
+
+def throughput_sweep(dev, disp, base_d, n_samples, world, rank, S, totals=(1024, 4096, 16384, 65536)):
+    """configs[4]: `total` synthetic recording sets sharded over the ranks (set s -> rank s mod G), generated ON THE
+    DEVICE from seeds in batches of S sets (never staged from the host); only the hot-path calls are timed (CUDA events
+    around each process(), summed), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    gen = torch.Generator(device=dev)
+    out = []
+    buf = torch.empty((S, 2, n_samples), dtype=torch.float64, device=dev)
+    for total in totals:
+        mine = len(range(rank, total, world))
+        gen.manual_seed(977 * total + rank)
+        done, ms = 0, 0.0
+        while done < mine:
+            nb = min(S, mine - done)
+            g = 0.5 + 0.5 * torch.rand((nb, 1, 1), generator=gen, device=dev, dtype=torch.float64)
+            idx = (torch.arange(nb, device=dev) + done) % base_d.shape[0]
+            torch.mul(base_d[idx], g, out=buf[:nb])
+            buf[:nb] += 2e-6 * torch.randn((nb, 2, n_samples), generator=gen, device=dev, dtype=torch.float64)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            disp.process(buf[:nb])
+            b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+            done += nb
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out.append({"recording_sets": total, "irs": total * N_IRS, "ms": ms, "value": total * N_IRS / (ms / 1e3),
+                    "unit": "IR/s"})
+    return {"workload": "throughput sweep: 1k-64k synthetic 7.1 recording sets generated on the device from seeds, "
+                        "sharded set s -> rank s mod G (BASELINE.json configs[4])", "n_gpus": world,
+            "sets_per_launch": S, "points": out}
+
+
 def run_reference(args, rank, world):
     """Reference arm: rank 0 times the reference's own CPU implementation of the path on the box's host cores.
     Each step is a bounded sample of the GPU arm's workload (same recording sets, same per-set path), sized so
@@ -266,6 +417,8 @@ def main():
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
+    ap.add_argument("--no-named-configs", action="store_true", help="skip configs[2..4] (192 kHz, TrueHD, sweep)")
+    ap.add_argument("--sweep", default="1024,4096,16384,65536", help="total recording sets of the throughput sweep")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -317,7 +470,6 @@ def main():
         g = 0.5 + 0.5 * torch.rand(1, generator=gen, device=dev, dtype=torch.float64)
         batch[s] = base_d[s % N_BASE_SETS] * g
         batch[s] += 2e-6 * torch.randn((2, n_samples), generator=gen, device=dev, dtype=torch.float64)
-    del base_d
     disp = BatchDispatcher(est, LAYOUT)
 
     def barrier():
@@ -441,6 +593,15 @@ def main():
                            "minimum_phase_impulse_response(f_res=5)"}}
     bytes_per_ir = (8 + (8 if args.precision == 64 else 4)) * L
     peak, peak_src = measured_peak()
+    # ---- the other named configs (extra keys): sweep on every rank (it is sharded), configs 3 / 4 on rank 0 at N=1 ----
+    extra = {}
+    if not args.no_named_configs and args.precision == 64:
+        extra["throughput_sweep"] = throughput_sweep(dev, disp, base_d, n_samples, world, rank, S,
+                                                     totals=tuple(int(v) for v in args.sweep.split(',')))
+        if world == 1:
+            extra["config3_192khz"] = named_config3(dev, local_rank, peak)
+            extra["config4_truehd"] = named_config4(dev, local_rank, peak)
+    del base_d
     achieved = B * bytes_per_ir / (k1_ms / 1e3) / 1e9
 
     # ---- end to end: pinned host recordings in, cropped responses out, copies inside the timed region -------------
@@ -451,7 +612,7 @@ def main():
         for _ in range(2):
             disp.process_host(host_in, out=host_out)
         barrier()
-        steps = max(2, min(args.steps, 5))
+        steps = args.steps  # the same step count as the device-resident `value`
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         a.record()
@@ -509,6 +670,7 @@ def main():
         if fp32 is not None:
             fp32["frac_of_peak"] = fp32["achieved_gbs"] / peak
             line["fp32_fast_path"] = fp32
+        line.update(extra)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

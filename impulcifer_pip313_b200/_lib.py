@@ -144,6 +144,17 @@ def context(device: int = 0) -> Context:
     return ctx
 
 
+def default_device() -> int:
+    """Device index for objects created without an explicit device: ``IMPULCIFER_B200_DEVICE`` when set (a process
+    pinned to one GPU), else the calling THREAD's current torch device, so one dispatcher thread per GPU
+    (``torch.cuda.set_device(i)`` in each) uploads to its own GPU."""
+    env = os.environ.get("IMPULCIFER_B200_DEVICE")
+    if env is not None:
+        return int(env)
+    import torch
+    return int(torch.cuda.current_device()) if torch.cuda.is_available() else 0
+
+
 def current_stream_ptr(device) -> int:
     import torch
     return torch.cuda.current_stream(device).cuda_stream

@@ -79,6 +79,7 @@ def magnitude_response(x, fs):
     x = np.ascontiguousarray(x, dtype=np.float64)
     nfft = len(x)
     half = int(np.ceil(nfft / 2))
-    dev = torch.device("cuda", int(os.environ.get("IMPULCIFER_B200_DEVICE", "0")))
+    from ._lib import default_device
+    dev = torch.device("cuda", default_device())
     mag = ops.magnitude_db(torch.from_numpy(x).to(dev)).cpu().numpy()[0]
     return np.arange(half) * (fs / nfft), mag

@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(256) k_first_peak(const double* __restrict__ x
   const double guard = 0.999 * height * m;
   // a peak candidate is a sample >= guard: nothing before the first block whose maximum reaches it can qualify
   int64_t k0 = 0;
-  if (va.blk_max) {
+  if (va.blk_max && guard <= m) {  // guard > max|x| (peak_height > ~1.001): no candidate exists, argmax|x| is the
+                                   // answer and it may sit anywhere, so no block may be skipped
     const double* bm = va.blk_max + (r0 + r) * va.nblk;
     int64_t skip = n;
     for (int64_t q = 0; q < va.nblk; ++q)

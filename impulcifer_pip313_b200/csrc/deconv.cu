@@ -651,6 +651,10 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
     nblk = (pl->precision == 64 ? pl->e64.fft.p : pl->e32.fft.p).col.radix[0];  // R0 of the column pass
     IMPB_CUDA(cudaMemsetAsync(blockmax_out, 0, sizeof(double) * batch * nblk, st));
   }
+  if (pl->precision == 64 && !out_f64) {  // the FP64 engine stores doubles: a float32 `out` would be overrun 2x
+    set_error("impb_deconv_execute: a precision-64 plan writes float64 output (out_f64 must be 1)");
+    return IMPB_EINVAL;
+  }
   const int64_t pairs = (batch + 1) / 2;
   const int ns = pl->nstreams;
   const cudaStream_t user = st;

@@ -20,8 +20,8 @@ from . import _lib
 
 def _hann_rising(n: int) -> np.ndarray:
     """First half of scipy.signal.windows.hann(n) for even n."""
-    k = np.arange(n // 2)
-    return 0.5 - 0.5 * np.cos(2.0 * np.pi * k / (n - 1))
+    from scipy.signal.windows import hann  # the reference's own window (ulp-identical envelope, core/..estimator.py:109-131)
+    return hann(n)[:n // 2]
 
 
 def _next_pow2(n: int) -> int:
@@ -134,7 +134,7 @@ class ImpulseResponseEstimator(object):
         self.test_signal = self.generate_test_signal(min_duration)
         self.duration = len(self.test_signal) / self.fs
         self.inverse_filter = self.generate_inverse_filter()
-        self.device = int(os.environ.get("IMPULCIFER_B200_DEVICE", "0")) if device is None else int(device)
+        self.device = _lib.default_device() if device is None else int(device)
         if precision is None:
             precision = 32 if os.environ.get("IMPULCIFER_B200_PRECISION", "fp64").lower() == "fp32" else 64
         self.precision = int(precision)
@@ -182,7 +182,13 @@ class ImpulseResponseEstimator(object):
     def plan(self, max_len: int, precision=None, device=None) -> DeconvPlan:
         precision = self.precision if precision is None else int(precision)
         device = self.device if device is None else int(device)
-        key = (id(self.inverse_filter), len(self.inverse_filter), precision, device)
+        # keyed on a fingerprint of the inverse filter's CONTENT: an in-place edit (est.inverse_filter *= g) or a
+        # reassignment that reuses the id must not keep serving the stale device spectrum
+        inv = self.inverse_filter
+        n_inv = len(inv)
+        # (O(1) fingerprint: buffer address, length and four samples; hashing 2.4 MB on every call would cost ~1 ms)
+        key = ((inv.ctypes.data if isinstance(inv, np.ndarray) else id(inv), float(inv[0]), float(inv[n_inv // 3]),
+                float(inv[n_inv // 2]), float(inv[-1])), n_inv, precision, device)
         if self._plan_key != key[:2]:
             self._plans = {}
             self._plan_key = key[:2]

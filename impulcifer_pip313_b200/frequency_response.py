@@ -40,8 +40,8 @@ _KEYS = 'raw error error_smoothed equalization equalized_raw equalized_smoothed 
 
 
 def _device_index():
-    import os
-    return int(os.environ.get("IMPULCIFER_B200_DEVICE", "0"))
+    from ._lib import default_device
+    return default_device()
 
 
 def _to_dev(a):
@@ -197,7 +197,7 @@ class FrequencyResponse:
         self._sort()
 
     def copy(self, name=None):
-        return FrequencyResponse(
+        return type(self)(  # the merged class after install(), not the bare shim
             name=self.name + '_copy' if name is None else name, frequency=self._init_data(self.frequency),
             raw=self._init_data(self.raw), error=self._init_data(self.error), smoothed=self._init_data(self.smoothed),
             error_smoothed=self._init_data(self.error_smoothed), equalization=self._init_data(self.equalization),
@@ -271,7 +271,7 @@ class FrequencyResponse:
 
     def center(self, frequency=1000):
         """Reference :903-940."""
-        ee = FrequencyResponse(name='equal_energy', frequency=self.frequency.copy(), raw=self.raw.copy())
+        ee = type(self)(name='equal_energy', frequency=self.frequency.copy(), raw=self.raw.copy())
         ee.interpolate()
         if isinstance(frequency, (list, np.ndarray)) and len(frequency) > 1:
             diff = np.mean(ee.raw[np.logical_and(ee.frequency >= frequency[0], ee.frequency <= frequency[1])])

@@ -20,8 +20,8 @@ EPSILON = 1e-20
 
 
 def _device_index():
-    import os
-    return int(os.environ.get("IMPULCIFER_B200_DEVICE", "0"))
+    from ._lib import default_device
+    return default_device()
 
 
 @functools.lru_cache(maxsize=16)
@@ -91,7 +91,7 @@ class ImpulseResponse:
         return deepcopy(self)
 
     def __deepcopy__(self, memo):
-        out = ImpulseResponse.__new__(ImpulseResponse)
+        out = type(self).__new__(type(self))  # keeps the merged class install() builds (plot mix-ins, overrides)
         out.fs = self.fs
         out._host = None if self._host is None else self._host.copy()
         out._dev = None if self._dev is None else self._dev.clone()

@@ -23,7 +23,8 @@ _SINGLE_SPEAKER = "SINGLE"
 def _device():
     import os
     import torch
-    return torch.device("cuda", int(os.environ.get("IMPULCIFER_B200_DEVICE", "0")))
+    from ._lib import default_device
+    return torch.device("cuda", default_device())
 
 
 class MicrophoneMatchingCorrector:

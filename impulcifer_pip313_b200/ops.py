@@ -44,6 +44,7 @@ def as_index_tensor(values, device):
 
 # ---- K2 -------------------------------------------------------------------------------------------
 _win_cache = {}
+_win_lock = threading.Lock()
 
 
 def _dev_window(win, device):
@@ -55,11 +56,12 @@ def _dev_window(win, device):
     if arr.size == 0:
         return None
     key = (arr.tobytes(), str(device))
-    t = _win_cache.get(key)
-    if t is None:
-        if len(_win_cache) > 64:
-            _win_cache.clear()
-        t = _win_cache[key] = torch.as_tensor(arr, device=device)
+    with _win_lock:  # dispatcher threads of different GPUs share this cache
+        t = _win_cache.get(key)
+        if t is None:
+            if len(_win_cache) > 64:
+                _win_cache.clear()
+            t = _win_cache[key] = torch.as_tensor(arr, device=device)
     return t
 
 

@@ -69,13 +69,14 @@ def next_fast_len_5smooth(target: int) -> int:
 
 
 def hann(n: int) -> np.ndarray:
-    """scipy.signal.windows.hann(n) (symmetric): 0.5 - 0.5 cos(2 pi k / (n-1))."""
+    """scipy.signal.windows.hann(n) (symmetric).  SciPy is the reference's own dependency (pyproject.toml:31-33) and
+    evaluates the window as general_cosine over linspace(-pi, pi, n), which differs from 0.5 - 0.5 cos(2 pi k/(n-1))
+    in the last ulp; calling it keeps the sweep envelope (core/impulse_response_estimator.py:109-131), the crop fades
+    and the decay windows bit-identical to the reference's."""
+    from scipy.signal.windows import hann as _hann
     if n <= 0:
         return np.zeros(0)
-    if n == 1:
-        return np.ones(1)
-    k = np.arange(n)
-    return 0.5 - 0.5 * np.cos(2.0 * np.pi * k / (n - 1))
+    return _hann(int(n))
 
 
 def hamming(n: int) -> np.ndarray:
