@@ -628,10 +628,63 @@ def main():
         ms = float(t.item())
         return world * S * N_IRS * steps / (ms / 1e3), steps, int(disp.host_bytes_out), int(host_in.numel() * host_in.element_size())
 
-    pcm = torch.empty((S, 2, n_samples), dtype=torch.int32).pin_memory()
-    pcm.copy_(torch.round(batch * 2.0 ** 31).clamp(-2.0 ** 31, 2.0 ** 31 - 1).to(torch.int32).cpu())
-    e2e_value, e2e_steps, n_out_bytes, h2d_bytes = e2e_run(pcm)
-    del pcm
+    # The PCM path is the designed multi-GPU step: ONE shared page-locked input arena holding all
+    # world x S recording sets in set order, ONE shared result arena; rank r owns sets s = r (mod world)
+    # (DeviceShard), DMAs them out of the input arena and lands their responses in its result slots.  No collective:
+    # the step ends with the barrier after which rank 0 reads every set in set order.
+    from impulcifer_pip313_b200.arena import HostArena, ResultArena
+    from impulcifer_pip313_b200.dispatcher import DeviceShard
+    tag = os.environ.get("MASTER_PORT", str(os.getpid()))
+    total_sets = world * S
+    max_tail = int(max(tails)) if tails else 96000
+    max_tail = max(max_tail, 2 * FS)
+    in_bytes = total_sets * 2 * n_samples * 4
+    out_bytes_arena = ResultArena.nbytes(total_sets, N_IRS, max_tail)
+    if rank == 0:
+        a_in, a_out = HostArena(f"impb_in_{tag}", in_bytes, True), HostArena(f"impb_out_{tag}", out_bytes_arena, True)
+    barrier()
+    if rank != 0:
+        a_in, a_out = HostArena(f"impb_in_{tag}", in_bytes, False), HostArena(f"impb_out_{tag}", out_bytes_arena, False)
+    a_in.register()
+    a_out.register()
+    rec_arena = a_in.view(np.int32, 0, (total_sets, 2, n_samples))
+    res_arena = ResultArena(a_out, total_sets, N_IRS, max_tail)
+    shard = DeviceShard(world, rank)
+    # every rank writes (first-touches) the PCM samples of the sets it owns
+    rec_arena[rank::world].copy_(torch.round(batch * 2.0 ** 31).clamp(-2.0 ** 31, 2.0 ** 31 - 1).to(torch.int32).cpu())
+    barrier()
+
+    def e2e_sharded():
+        for _ in range(2):
+            shard.run(disp, rec_arena, res_arena)
+        barrier()
+        steps = args.steps  # the same step count as the device-resident `value`
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(steps):
+            shard.run(disp, rec_arena, res_arena)
+        b.record()
+        wall_ms = (time.perf_counter() - t0) * 1e3  # run() returns after its D2H stream has drained
+        barrier()
+        ms = max(a.elapsed_time(b), wall_ms)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        return world * S * N_IRS * steps / (ms / 1e3), steps, int(disp.host_bytes_out), S * 2 * n_samples * 4
+
+    e2e_value, e2e_steps, n_out_bytes, h2d_bytes = e2e_sharded()
+    arena_check = None
+    if rank == 0:  # the gather is complete and in set order: every slot holds a set of the right shape
+        tails_seen = [res_arena.get(s)[0] for s in range(total_sets)]
+        arena_check = {"sets_in_arena": total_sets, "all_present": bool(all(t > 0 for t in tails_seen)),
+                       "input_arena_bytes": in_bytes, "result_arena_bytes": out_bytes_arena,
+                       "owner_of_set": "s mod n_gpus (DeviceShard)"}
+    barrier()
+    del rec_arena, res_arena
+    a_in.close()
+    a_out.close()
     host64 = torch.empty((S, 2, n_samples), dtype=torch.float64).pin_memory()
     host64.copy_(batch.cpu())
     e2e64_value, _, _, h2d64_bytes = e2e_run(host64)
@@ -650,8 +703,10 @@ def main():
                        f"({batch.numel() * 8 / 2**20:.0f} MiB of recordings per step)", "parallelism": f"sets x{world}"},
             "e2e": {"value": e2e_value, "unit": "IR/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": n_out_bytes, "steps": e2e_steps,
-                    "api": "BatchDispatcher.process_host on pinned host int32 PCM recordings (PCM_32 WAV samples), "
-                           "chunked H2D / compute / D2H overlap",
+                    "api": "DeviceShard.run -> BatchDispatcher.process_host: int32 PCM recordings (PCM_32 WAV samples) in ONE "
+                           "shared page-locked input arena, results into ONE shared result arena in set order "
+                           "(set s -> rank s mod n_gpus), chunked H2D / compute / D2H overlap, no collective",
+                    "result_arena": arena_check,
                     "float64_host_buffers": {"value": e2e64_value, "h2d_bytes_per_step": h2d64_bytes}},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -337,7 +337,7 @@ class BatchDispatcher:
         return results
 
     # ---- host buffers in, host buffers out ------------------------------------------------------------------
-    def process_host(self, recordings, out=None, chunk_sets=None, precision=None):
+    def process_host(self, recordings, out=None, chunk_sets=None, precision=None, out_sets=None):
         """``process`` for recordings that live in (pinned) HOST memory: ``[S, n_tracks, n_samples]`` float64,
         float32 or int32 PCM (the samples of a PCM WAV exactly as stored; scaled by 2^-31 inside K1).
 
@@ -376,9 +376,13 @@ class BatchDispatcher:
             fin.record(compute)
             d2h.wait_event(fin)
             with torch.cuda.stream(d2h):
-                for r in part:
+                for j, r in enumerate(part):
                     n = r.data.numel()
-                    if out is not None:
+                    if out_sets is not None:  # fixed slot per set (ResultArena.data rows, page-locked)
+                        if n > out_sets.shape[1]:
+                            raise ValueError(f"result of {n} samples does not fit the arena slot of {out_sets.shape[1]}")
+                        host = out_sets[len(results) + j, :n].view(r.data.shape)
+                    elif out is not None:
                         host = out[off:off + n].view(r.data.shape)
                     else:
                         host = torch.empty(r.data.shape, dtype=r.data.dtype).pin_memory()
@@ -578,7 +582,8 @@ class DeviceShard:
 
     def gather(self, local_results, n_sets: int, dst: int = 0):
         """Collect ``{set_index: picklable result}`` from every rank on ``dst`` in set order
-        (``torch.distributed.gather_object``; identity when world_size == 1)."""
+        (``torch.distributed.gather_object``; identity when world_size == 1).  Kept for small metadata; sample data
+        goes through ``run`` / ``ResultArena`` (shared page-locked memory, no pickling)."""
         if self.world_size == 1:
             return [local_results[i] for i in range(n_sets)]
         import torch.distributed as dist
@@ -590,3 +595,20 @@ class DeviceShard:
         for part in bucket:
             merged.update(part)
         return [merged[i] for i in range(n_sets)]
+
+    def run(self, dispatcher, recordings_host, results, chunk_sets=None, precision=None):
+        """The designed multi-GPU step: this rank takes the recording sets it owns (s mod G) out of the
+        shared input arena ``recordings_host`` [n_sets, tracks, samples] (page-locked), runs the hot path on its GPU and
+        lands every set's cropped responses in its slot of ``results`` (``ResultArena``) — the final result gather IS
+        that D2H copy.  No collective; the caller closes the step with a barrier, after which every rank sees all sets
+        in set order.  Returns the number of sets processed here."""
+        n_sets = recordings_host.shape[0]
+        mine = recordings_host[self.rank::self.world_size]      # strided view: sets rank, rank + G, ...
+        slots = results.data[self.rank::self.world_size]
+        if mine.shape[0] == 0:
+            return 0
+        part = dispatcher.process_host(mine, chunk_sets=chunk_sets, precision=precision, out_sets=slots)
+        for k, r in enumerate(part):
+            results.put_meta(self.rank + k * self.world_size, r)
+        assert self.rank + (len(part) - 1) * self.world_size < n_sets
+        return len(part)

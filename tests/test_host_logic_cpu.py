@@ -142,6 +142,71 @@ dist.destroy_process_group()
     assert "GATHER_OK" in r.stdout
 
 
+def test_device_shard_arena_two_ranks_gloo(tmp_path):
+    """The designed N > 1 step on CPU (gloo, world_size 2): one shared input arena, one shared result arena, rank r
+    owns sets s = r (mod 2), every set's result lands in its slot in set order with no collective on the data path
+    (the GPU compute is replaced by a stand-in dispatcher; the partition, slot and metadata logic is the product's)."""
+    script = tmp_path / "arena_worker.py"
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np, torch
+import torch.distributed as dist
+from impulcifer_pip313_b200 import DeviceShard
+from impulcifer_pip313_b200.arena import HostArena, ResultArena
+from impulcifer_pip313_b200.dispatcher import SetResult
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n_sets, n_irs, max_tail, n_samples = 5, 4, 64, 100
+in_bytes = n_sets * 2 * n_samples * 4
+out_bytes = ResultArena.nbytes(n_sets, n_irs, max_tail)
+if rank == 0:
+    a_in, a_out = HostArena("impb_test_in", in_bytes, True), HostArena("impb_test_out", out_bytes, True)
+dist.barrier()
+if rank != 0:
+    a_in, a_out = HostArena("impb_test_in", in_bytes, False), HostArena("impb_test_out", out_bytes, False)
+rec = a_in.view(np.int32, 0, (n_sets, 2, n_samples))
+res = ResultArena(a_out, n_sets, n_irs, max_tail)
+sh = DeviceShard(world, rank)
+for s in sh.owned(n_sets):
+    rec[s] = s + 1          # every rank fills the sets it owns
+dist.barrier()
+
+class StandIn:              # process_host of the real dispatcher, without a GPU: tail depends on the set's content
+    def process_host(self, recordings, chunk_sets=None, precision=None, out_sets=None):
+        out = []
+        for k in range(recordings.shape[0]):
+            v = int(recordings[k, 0, 0])
+            tail = 10 + v
+            data = torch.full((n_irs, tail), float(v), dtype=torch.float64)
+            out_sets[k, :n_irs * tail].view(n_irs, tail).copy_(data)
+            out.append(SetResult([f"S{{i}}-left" for i in range(n_irs)], out_sets[k, :n_irs * tail].view(n_irs, tail), tail,
+                                 np.arange(n_irs) + v, np.arange(n_irs), np.arange(n_irs) + 100 * v))
+        return out
+
+done = sh.run(StandIn(), rec, res)
+assert done == len(sh.owned(n_sets))
+dist.barrier()
+if rank == 0:
+    for s in range(n_sets):
+        tail, data, peaks, crop, knees = res.get(s)
+        assert tail == 11 + s and tuple(data.shape) == (n_irs, tail)
+        assert float(data.min()) == float(data.max()) == s + 1
+        assert peaks.tolist() == [s + 1 + i for i in range(n_irs)] and knees.tolist() == [100 * (s + 1) + i for i in range(n_irs)]
+    print("ARENA_OK")
+dist.barrier()
+del rec, res
+a_in.close(); a_out.close()
+dist.destroy_process_group()
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29572", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "ARENA_OK" in r.stdout
+
+
 def test_next_row_host_constants_match_reference_formulas():
     """Host-side pieces of the next-row chains (no device work): the correction-limit mask, the microphone band taper,
     the virtual-bass filter constants and the golden fixtures they were pinned with."""
