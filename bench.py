@@ -645,11 +645,13 @@ def main():
     barrier()
     if rank != 0:
         a_in, a_out = HostArena(f"impb_in_{tag}", in_bytes, False), HostArena(f"impb_out_{tag}", out_bytes_arena, False)
-    a_in.register()
-    a_out.register()
     rec_arena = a_in.view(np.int32, 0, (total_sets, 2, n_samples))
     res_arena = ResultArena(a_out, total_sets, N_IRS, max_tail)
     shard = DeviceShard(world, rank)
+    # every rank page-locks the slices it DMAs: the recording sets it owns and their result slots
+    set_bytes = 2 * n_samples * 4
+    pinned_in = a_in.register_ranges([(s * set_bytes, set_bytes) for s in shard.owned(total_sets)])
+    pinned_out = a_out.register_ranges(res_arena.slot_ranges(shard.owned(total_sets)))
     # every rank writes (first-touches) the PCM samples of the sets it owns
     rec_arena[rank::world].copy_(torch.round(batch * 2.0 ** 31).clamp(-2.0 ** 31, 2.0 ** 31 - 1).to(torch.int32).cpu())
     barrier()
@@ -680,6 +682,7 @@ def main():
         tails_seen = [res_arena.get(s)[0] for s in range(total_sets)]
         arena_check = {"sets_in_arena": total_sets, "all_present": bool(all(t > 0 for t in tails_seen)),
                        "input_arena_bytes": in_bytes, "result_arena_bytes": out_bytes_arena,
+                       "page_locked_per_rank_bytes": [int(pinned_in), int(pinned_out)],
                        "owner_of_set": "s mod n_gpus (DeviceShard)"}
     barrier()
     del rec_arena, res_arena

@@ -31,6 +31,11 @@ class HostArena:
             self.shm = shared_memory.SharedMemory(name=name, create=True, size=max(self.nbytes, 1))
         else:
             self.shm = shared_memory.SharedMemory(name=name)
+            try:  # Python < 3.13 registers attached segments with the resource tracker, which would unlink the
+                from multiprocessing import resource_tracker  # owner's segment when this process exits
+                resource_tracker.unregister(self.shm._name, 'shared_memory')
+            except Exception:
+                pass
         self._registered = False
         self._np = np.ndarray((self.nbytes,), dtype=np.uint8, buffer=self.shm.buf)
 
@@ -45,6 +50,35 @@ class HostArena:
         self._registered = True
         return True
 
+    def register_ranges(self, ranges) -> int:
+        """Page-lock only the byte ranges ``[(offset, nbytes), ...]`` this process will DMA (the sets a rank owns):
+        registering the whole arena in every rank pins it G times over and runs into the locked-memory limit
+        (8 ranks x 23 GB failed on the 8-GPU box).  Ranges are widened to page boundaries and merged.  Returns the
+        number of bytes registered."""
+        import torch
+        if not torch.cuda.is_available() or self.nbytes == 0:
+            return 0
+        page = 4096
+        base = self._np.ctypes.data
+        spans = sorted(((base + int(o)) // page * page, -(-(base + int(o) + int(n)) // page) * page) for o, n in ranges if n > 0)
+        merged = []
+        for a, b in spans:
+            if merged and a <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], b)
+            else:
+                merged.append([a, b])
+        end = -(-(base + self.nbytes) // page) * page
+        total = 0
+        self._ranges = getattr(self, "_ranges", [])
+        for a, b in merged:
+            b = min(b, end)
+            rc = torch.cuda.cudart().cudaHostRegister(a, b - a, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister({self.name}, {b - a} B at +{a - base}) failed with {rc}")
+            self._ranges.append(a)
+            total += b - a
+        return total
+
     def view(self, dtype, offset: int, shape):
         """torch tensor over ``shape`` elements of ``dtype`` starting ``offset`` bytes into the arena."""
         import torch
@@ -54,10 +88,13 @@ class HostArena:
 
     def close(self):
         import torch
-        if self._registered and torch.cuda.is_available():
+        if torch.cuda.is_available() and (self._registered or getattr(self, "_ranges", None)):
             torch.cuda.synchronize()
-            torch.cuda.cudart().cudaHostUnregister(self._np.ctypes.data)
-            self._registered = False
+            if self._registered:
+                torch.cuda.cudart().cudaHostUnregister(self._np.ctypes.data)
+            for a in getattr(self, "_ranges", []):
+                torch.cuda.cudart().cudaHostUnregister(a)
+            self._registered, self._ranges = False, []
         self._np = None
         try:
             self.shm.close()
@@ -81,6 +118,12 @@ class ResultArena:
         meta_bytes = self.n_sets * self.meta_cols * 8
         self.meta = arena.view(np.int64, offset, (self.n_sets, self.meta_cols))
         self.data = arena.view(np.float64, offset + meta_bytes, (self.n_sets, self.n_irs * self.max_tail))
+        self.data_offset = offset + meta_bytes
+        self.slot_bytes = self.n_irs * self.max_tail * 8
+
+    def slot_ranges(self, sets):
+        """Byte ranges of the data slots of ``sets`` inside the arena (for ``HostArena.register_ranges``)."""
+        return [(self.data_offset + int(s) * self.slot_bytes, self.slot_bytes) for s in sets]
 
     @staticmethod
     def nbytes(n_sets: int, n_irs: int, max_tail: int) -> int:

@@ -362,7 +362,12 @@ class BatchDispatcher:
         ready = []
         with torch.cuda.stream(h2d):
             for a, b in bounds:
-                stage[a:b].copy_(recordings[a:b], non_blocking=True)
+                src = recordings[a:b]
+                if src.is_contiguous():
+                    stage[a:b].copy_(src, non_blocking=True)
+                else:  # sets of a strided shard view (DeviceShard: every G-th set of the shared arena): one DMA per
+                    for i in range(a, b):  # set, straight from the page-locked arena (a strided copy_ would first
+                        stage[i].copy_(recordings[i], non_blocking=True)  # gather on the host)
                 ev = torch.cuda.Event()
                 ev.record(h2d)
                 ready.append(ev)
