@@ -24,6 +24,8 @@ template <typename T> struct Fft2D {
   bool col_fixed = false, row_fixed = false;
   int* perm_col = nullptr;     // device copies of the digit-reversal maps
   int* perm_row = nullptr;
+  int* inv_col = nullptr;      // their inverses (natural index -> position): mirror-bin lookups of paired real rows
+  int* inv_row = nullptr;
   std::vector<int> h_perm_col, h_perm_row;
 
   int init(const Plan2D& plan) {
@@ -77,11 +79,20 @@ template <typename T> struct Fft2D {
     IMPB_CUDA(cudaMalloc(&perm_row, p.N2 * sizeof(int)));
     IMPB_CUDA(cudaMemcpy(perm_col, h_perm_col.data(), p.N1 * sizeof(int), cudaMemcpyHostToDevice));
     IMPB_CUDA(cudaMemcpy(perm_row, h_perm_row.data(), p.N2 * sizeof(int), cudaMemcpyHostToDevice));
+    std::vector<int> ic((size_t)p.N1), ir((size_t)p.N2);
+    for (int i = 0; i < p.N1; ++i) ic[(size_t)h_perm_col[i]] = i;
+    for (int i = 0; i < p.N2; ++i) ir[(size_t)h_perm_row[i]] = i;
+    IMPB_CUDA(cudaMalloc(&inv_col, p.N1 * sizeof(int)));
+    IMPB_CUDA(cudaMalloc(&inv_row, p.N2 * sizeof(int)));
+    IMPB_CUDA(cudaMemcpy(inv_col, ic.data(), p.N1 * sizeof(int), cudaMemcpyHostToDevice));
+    IMPB_CUDA(cudaMemcpy(inv_row, ir.data(), p.N2 * sizeof(int), cudaMemcpyHostToDevice));
     return IMPB_OK;
   }
 
   void release() {
     cudaFree(tw); cudaFree(tab_col); cudaFree(tab_row); cudaFree(perm_col); cudaFree(perm_row);
+    cudaFree(inv_col); cudaFree(inv_row);
+    inv_col = inv_row = nullptr;
     for (int s = 0; s < 2; ++s) {
       cudaFree(fx_col[s]); cudaFree(fx_row[s]); cudaFree(fxf_col[s]); cudaFree(fxf_row[s]);
       fx_col[s] = fx_row[s] = fxf_col[s] = fxf_row[s] = nullptr;

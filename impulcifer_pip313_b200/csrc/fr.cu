@@ -234,6 +234,11 @@ struct impb_minphase {
   double* hamming = nullptr;  // [numtaps]
   double* nyq_S = nullptr;    // [nf/2 + 1] kernel of the Nyquist-bin imprint (see NyquistImprint below)
   double win_sum = 0.0;       // sum(hamming)
+  void* tab = nullptr;        // FirwinTab[nf/2 + 1]: per-bin constants of the firwin2 synthesis for sampling rate tab_fs
+  int tab_fs = 0;
+  double2* pos_a = nullptr;   // [nf] position-order copies for the row-pass loader: {dx, df}
+  double2* pos_b = nullptr;   //      {cos, sin} with the Hermitian sign / zeroing folded in
+  int* pos_j = nullptr;       //      np.interp interval
   int64_t chunk = 256;
 };
 
@@ -246,6 +251,18 @@ namespace {
 // of its phase ramp  -(numtaps-1)/2 * 1j * pi * x / nyq.  To land on the same value the ramp is rebuilt
 // with the reference's exact sequence of IEEE operations (numpy divides a complex array by a real scalar
 // by multiplying with fl(1/nyq); verified bit-identical on the host for every supported rate).
+// Everything of the firwin2 grid that does not depend on the filter is tabulated once per (plan, sampling rate): where
+// grid frequency x_k falls in the gain grid (np.interp's interval j, x - f_j, f_{j+1} - f_j), the phase-ramp factor
+// exp(i a_k) with the reference's rounded angle a_k, and the Nyquist-imprint weight W_k = -(2/nf) d_k S_k.  The per-
+// filter work of a bin is then two gain loads, one division and one multiply-add (np.interp's exact operation order)
+// instead of an interval search and a large-argument sincos per (filter, bin): RowInvFirwin 270 -> see profiles/.
+struct FirwinTab {
+  double dx, df;   // x - f_j, f_{j+1} - f_j  (df = 0: take g[j] as is — last grid point or an exact hit)
+  double cs, sn;   // cos / sin of fl(fl(b x) / nyq)
+  double w;        // Nyquist-imprint weight
+  int j, pad;
+};
+
 struct FirwinSpec {
   const double* gain;  // [batch, ld]
   int64_t ld, n, nf;
@@ -255,37 +272,48 @@ struct FirwinSpec {
   double b;        // fl(-(numtaps - 1) / 2 * pi)
   double step_f;   // (fs // 2) / (n - 1)         : np.linspace(0, fs // 2, n)
   double f_stop;
+  const FirwinTab* tab;
+  const double2* pos_a;
+  const double2* pos_b;
+  const int* pos_j;
   __device__ __forceinline__ double fgrid(int64_t i) const { return i == n - 1 ? f_stop : __dmul_rn((double)i, step_f); }
-  // np.interp(x_kk, freq, gain) at firwin2 grid point kk in [0, nf/2]; *x_out = the grid frequency
-  __device__ __forceinline__ double fx_at(int bidx, int64_t kk, double* x_out) const {
-    const int64_t half = nf / 2;
-    const double x = kk == half ? nyq : __dmul_rn((double)kk, step_x);
-    *x_out = x;
-    const double* g = gain + (size_t)bidx * ld;
+  // grid frequency of firwin2 point kk in [0, nf/2], its np.interp interval j and the reference's phase-ramp angle
+  __device__ __forceinline__ double xgrid(int64_t kk) const { return kk == nf / 2 ? nyq : __dmul_rn((double)kk, step_x); }
+  __device__ __forceinline__ int64_t interval(double x) const {
     int64_t j = (int64_t)floor(x / step_f);
     j = max((int64_t)0, min(j, n - 1));
     while (j > 0 && fgrid(j) > x) --j;
     while (j < n - 1 && fgrid(j + 1) <= x) ++j;
-    if (j == n - 1) return g[j];
-    const double fj = fgrid(j);
-    if (fj == x) return g[j];
-    const double slope = __ddiv_rn(g[j + 1] - g[j], fgrid(j + 1) - fj);
-    return __dadd_rn(__dmul_rn(slope, x - fj), g[j]);
+    return j;
   }
-  // the reference's phase-ramp angle at x, with its exact rounding sequence
   __device__ __forceinline__ double angle(double x) const { return __dmul_rn(__dmul_rn(b, x), rnyq); }
+  // np.interp(x_kk, freq, gain) from the table
+  __device__ __forceinline__ double fx_at(int bidx, const FirwinTab& t) const {
+    const double* g = gain + (size_t)bidx * ld;
+    const double g0 = g[t.j];
+    if (t.df == 0.0) return g0;
+    const double slope = __ddiv_rn(g[t.j + 1] - g0, t.df);
+    return __dadd_rn(__dmul_rn(slope, t.dx), g0);
+  }
   __device__ __forceinline__ double2 at(int bidx, int64_t k) const {
     const int64_t half = nf / 2;
     const bool mirror = k > half;
     const int64_t kk = mirror ? nf - k : k;
-    double x;
-    const double fx = fx_at(bidx, kk, &x);
-    double sn, cs;
-    sincos(angle(x), &sn, &cs);
-    double2 v = make_double2(fx * cs, fx * sn);
+    const FirwinTab t = tab[kk];
+    const double fx = fx_at(bidx, t);
+    double2 v = make_double2(fx * t.cs, fx * t.sn);
     if (kk == 0 || kk == half) v.y = 0.0;  // c2r transforms ignore these imaginary parts
     if (mirror) v.y = -v.y;
     return v;
+  }
+  // the same value for the bin stored at workspace position `pos` (coalesced position-order tables)
+  __device__ __forceinline__ double2 at_pos(int bidx, size_t pos) const {
+    const double2 a = pos_a[pos], cssn = pos_b[pos];
+    const double* g = gain + (size_t)bidx * ld;
+    const int j = pos_j[pos];
+    double fx = g[j];
+    if (a.y != 0.0) fx = __dadd_rn(__dmul_rn(__ddiv_rn(g[j + 1] - fx, a.y), a.x), fx);
+    return make_double2(fx * cssn.x, fx * cssn.y);
   }
 };
 
@@ -324,22 +352,67 @@ __global__ void __launch_bounds__(256) k_mp_nyq_table(const double* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) k_mp_nyq_imprint(const FirwinSpec spec, int64_t numtaps,
-                                                        const double* __restrict__ S, double win_sum,
-                                                        double* __restrict__ out) {
-  const int bidx = blockIdx.x;
+__global__ void __launch_bounds__(256) k_firwin_table(const FirwinSpec spec, int64_t numtaps, const double* __restrict__ S,
+                                                      FirwinTab* __restrict__ tab) {
   const int64_t half = spec.nf / 2;
+  const int64_t kk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (kk > half) return;
   const double PI_HI = 3.141592653589793116, PI_LO = 1.2246467991473532e-16;
+  const double x = spec.xgrid(kk);
+  const int64_t j = spec.interval(x);
+  FirwinTab t;
+  t.j = (int)j;
+  t.pad = 0;
+  const double fj = spec.fgrid(j);
+  if (j == spec.n - 1 || fj == x) { t.dx = 0.0; t.df = 0.0; }
+  else { t.dx = x - fj; t.df = spec.fgrid(j + 1) - fj; }
+  const double a = spec.angle(x);
+  sincos(a, &t.sn, &t.cs);
+  // d_k = a_k - phi_k with phi_k = -pi (numtaps - 1) k / nf in double-double ((numtaps-1) k / nf is exact)
+  const double tt = (double)((numtaps - 1) * kk) / (double)spec.nf;
+  const double p_hi = PI_HI * tt;
+  const double p_lo = fma(PI_HI, tt, -p_hi) + PI_LO * tt;
+  const double d = (a + p_hi) + p_lo;
+  t.w = (kk >= 1 && kk < half) ? -(2.0 / (double)spec.nf) * d * S[kk] : 0.0;
+  tab[kk] = t;
+}
+
+__global__ void __launch_bounds__(256) k_firwin_pos_table(const FirwinTab* __restrict__ tab, int64_t nf,
+                                                          const int* __restrict__ perm1, const int* __restrict__ perm2,
+                                                          int N1, int N2, double2* __restrict__ pos_a,
+                                                          double2* __restrict__ pos_b, int* __restrict__ pos_j) {
+  const int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (pos >= nf) return;
+  const int row = (int)(pos / N2), e = (int)(pos % N2);
+  const int64_t k = (int64_t)perm1[row] + (int64_t)N1 * perm2[e];
+  const int64_t half = nf / 2;
+  const bool mirror = k > half;
+  const int64_t kk = mirror ? nf - k : k;
+  const FirwinTab t = tab[kk];
+  pos_a[pos] = make_double2(t.dx, t.df);
+  pos_b[pos] = make_double2(t.cs, (kk == 0 || kk == half) ? 0.0 : (mirror ? -t.sn : t.sn));
+  pos_j[pos] = t.j;
+}
+
+// H[nyq] of every filter: sum_k fx_k W_k (+ the firwin2 Nyquist term) as a fixed-order two-level sum (deterministic):
+// grid (IMPRINT_SLICES, filters) partial sums, then one thread per filter adds them in slice order
+constexpr int IMPRINT_SLICES = 16;
+// np.interp of every filter's gain curve onto the firwin2 grid, once, in natural bin order (fully parallel and
+// coalesced: one thread per (filter, bin)), fused with the partial sums of the Nyquist imprint.  The transform's loader
+// then needs one 8-byte load per (filter, bin) instead of a dependent table -> interval -> gain chain at the low
+// occupancy of a 98 KB-tile FFT pass.  fxn: [filters][nf/2 + 1].
+__global__ void __launch_bounds__(256) k_firwin_fx(const FirwinSpec spec, double* __restrict__ fxn,
+                                                   double* __restrict__ part) {
+  const int bidx = blockIdx.y;
+  const int64_t half = spec.nf / 2;
+  const int64_t per = (half + 1 + IMPRINT_SLICES - 1) / IMPRINT_SLICES;
+  const int64_t lo = blockIdx.x * per, hi = min(half + 1, (blockIdx.x + 1) * per);
   double acc = 0.0;
-  for (int64_t k = 1 + threadIdx.x; k < half; k += blockDim.x) {
-    double x;
-    const double fx = spec.fx_at(bidx, k, &x);
-    const double a = spec.angle(x);
-    const double t = (double)((numtaps - 1) * k) / (double)spec.nf;  // exact: nf is a power of two
-    const double p_hi = PI_HI * t;
-    const double p_lo = fma(PI_HI, t, -p_hi) + PI_LO * t;
-    const double d = (a + p_hi) + p_lo;  // a_k - phi_k
-    acc += fx * d * S[k];
+  for (int64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+    const FirwinTab t = spec.tab[k];
+    const double fx = spec.fx_at(bidx, t);
+    fxn[(size_t)bidx * (half + 1) + k] = fx;
+    acc += fx * t.w;  // t.w = 0 for k = 0 and k = nf/2
   }
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   __shared__ double sm[8];
@@ -348,12 +421,38 @@ __global__ void __launch_bounds__(256) k_mp_nyq_imprint(const FirwinSpec spec, i
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += sm[w];
-    double x;
-    const double fxh = spec.fx_at(bidx, half, &x);
-    double sn, cs;
-    sincos(spec.angle(x), &sn, &cs);
-    out[bidx] = -(2.0 / (double)spec.nf) * t + (fxh * cs) * win_sum / (double)spec.nf;
+    part[(size_t)bidx * IMPRINT_SLICES + blockIdx.x] = t;
   }
+}
+__global__ void __launch_bounds__(256) k_mp_nyq_partial(const FirwinSpec spec, double* __restrict__ part) {
+  const int bidx = blockIdx.y;
+  const int64_t half = spec.nf / 2;
+  const int64_t per = (half + IMPRINT_SLICES - 1) / IMPRINT_SLICES;
+  const int64_t lo = max((int64_t)1, blockIdx.x * per), hi = min(half, (blockIdx.x + 1) * per);
+  double acc = 0.0;
+#pragma unroll 4
+  for (int64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) {
+    const FirwinTab t = spec.tab[k];
+    acc += spec.fx_at(bidx, t) * t.w;
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    part[(size_t)bidx * IMPRINT_SLICES + blockIdx.x] = t;
+  }
+}
+__global__ void k_mp_nyq_finish(const FirwinSpec spec, const double* __restrict__ part, double win_sum, int rows,
+                                double* __restrict__ out) {
+  const int bidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bidx >= rows) return;
+  double t = 0.0;
+  for (int q = 0; q < IMPRINT_SLICES; ++q) t += part[(size_t)bidx * IMPRINT_SLICES + q];
+  const FirwinTab th = spec.tab[spec.nf / 2];
+  out[bidx] = t + (spec.fx_at(bidx, th) * th.cs) * win_sum / (double)spec.nf;
 }
 
 struct RowInvFirwin {  // row DIT whose input is synthesised from the gain curve
@@ -398,6 +497,283 @@ struct ColInvReal {
     double r = v.x * scale;
     if (win) r *= win[m];
     out[(size_t)b * ld + m] = r;
+  }
+};
+
+// ---- two real filters per complex transform ---------------------------------------------------------------------------
+// Every transform of the minimum-phase chain maps real rows to Hermitian spectra or back, so filters 2p and 2p+1 ride as
+// re / im of ONE complex transform (the trick K1 plays with the two ears): half the butterflies, half the workspace
+// traffic.  Inverse transforms pack trivially (Z = A + iB at every bin).  After a forward transform the two spectra are
+// A[k] = (Z[k] + conj Z[N-k]) / 2 and B[k] = (Z[k] - conj Z[N-k]) / 2i; the loader of the NEXT (inverse) pass reads
+// the mirror bin through the inverse digit-reversal maps, so no separate split pass exists.
+struct Mirror {
+  const int *perm1, *perm2, *inv1, *inv2;
+  int N1, N2;
+  int64_t N;
+  // position of bin N - k for the bin at position (row, e); *k = its natural index
+  __device__ __forceinline__ size_t of(int row, int e, int64_t* k) const {
+    const int64_t kk = (int64_t)perm1[row] + (int64_t)N1 * perm2[e];
+    *k = kk;
+    const int64_t km = kk == 0 ? 0 : N - kk;
+    return (size_t)inv1[(int)(km % N1)] * N2 + inv2[(int)(km / N1)];
+  }
+};
+__device__ __forceinline__ void split_pair(double2 z, double2 zm, double2* a, double2* b) {
+  *a = make_double2(0.5 * (z.x + zm.x), 0.5 * (z.y - zm.y));
+  *b = make_double2(0.5 * (z.y + zm.y), -0.5 * (z.x - zm.x));
+}
+
+struct RowInvFirwin2 {  // row DIT over the synthesised spectra of filters 2b (re) and 2b+1 (im)
+  FirwinSpec spec;
+  int rows;  // filters in this launch
+  double2* ws;
+  const double2* tw;
+  int64_t N;
+  int N1, N2;
+  const int* perm1;
+  const int* perm2;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int row = t * TILE + c;
+    if (row >= N1) return make_double2(0.0, 0.0);
+    const size_t pos = (size_t)row * N2 + e;
+    const double2 a = spec.at_pos(2 * b, pos);
+    if (2 * b + 1 >= rows) return a;
+    const double2 bb = spec.at_pos(2 * b + 1, pos);
+    return make_double2(a.x - bb.y, a.y + bb.x);
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int row = t * TILE + c;
+    if (row >= N1) return;
+    const size_t idx = (size_t)row * N2 + e;
+    ws[(size_t)b * N + idx] = cmul(v, cconj(tw[idx]));
+  }
+};
+
+// firwin2's irfft through the FORWARD engine: ifft(Z) = conj(fft(conj Z)) / N.  The synthesised spectrum is then read
+// in NATURAL bin order by the column pass (coalesced table and gain-curve reads; as the input of the inverse engine
+// it was gathered in digit-reversed order, four scattered 8-byte gain loads per bin, L2-bandwidth bound), and only
+// the numtaps kept time samples (29 % of the 2^16) are scattered on the way out.
+struct ColFwdFirwin2 {
+  FirwinSpec spec;
+  int rows;
+  double2* ws;
+  const double2* tw;
+  int64_t N;
+  int N2;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return make_double2(0.0, 0.0);
+    const int64_t k = (int64_t)e * N2 + n2;
+    const double2 a = spec.at(2 * b, k);
+    if (2 * b + 1 >= rows) return make_double2(a.x, -a.y);
+    const double2 bb = spec.at(2 * b + 1, k);
+    return make_double2(a.x - bb.y, -(a.y + bb.x));  // conj(A + iB)
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return;
+    const size_t idx = (size_t)e * N2 + n2;
+    ws[(size_t)b * N + idx] = cmul(v, tw[idx]);
+  }
+};
+
+struct ColFwdFirwinFx2 {  // the same pass fed from the precomputed fx rows (k_firwin_fx)
+  const double* fxn;        // [rows][nf/2 + 1]
+  const FirwinTab* tab;
+  int64_t nf;
+  int rows;
+  double2* ws;
+  const double2* tw;
+  int64_t N;
+  int N2;
+  __device__ __forceinline__ double2 one(int bidx, int64_t kk, bool mirror, const FirwinTab& t, int64_t half) const {
+    const double fx = fxn[(size_t)bidx * (half + 1) + kk];
+    double2 v = make_double2(fx * t.cs, fx * t.sn);
+    if (kk == 0 || kk == half) v.y = 0.0;
+    if (mirror) v.y = -v.y;
+    return v;
+  }
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return make_double2(0.0, 0.0);
+    const int64_t k = (int64_t)e * N2 + n2, half = nf / 2;
+    const bool mirror = k > half;
+    const int64_t kk = mirror ? nf - k : k;
+    const FirwinTab tb = tab[kk];
+    const double2 a = one(2 * b, kk, mirror, tb, half);
+    if (2 * b + 1 >= rows) return make_double2(a.x, -a.y);
+    const double2 bb = one(2 * b + 1, kk, mirror, tb, half);
+    return make_double2(a.x - bb.y, -(a.y + bb.x));  // conj(A + iB)
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return;
+    const size_t idx = (size_t)e * N2 + n2;
+    ws[(size_t)b * N + idx] = cmul(v, tw[idx]);
+  }
+};
+
+struct RealOut2Op {  // conj(fft(conj Z))[m]: out[2b, m] = Re v, out[2b+1, m] = -Im v (scaled, windowed), m < keep
+  double* out;
+  int64_t ld, keep;
+  int rows;
+  const double* win;
+  double scale;
+  __device__ __forceinline__ void operator()(int b, size_t, int64_t m, double2 v) const {
+    if (m >= keep) return;
+    const double s = win ? scale * win[m] : scale;
+    out[(size_t)(2 * b) * ld + m] = v.x * s;
+    if (2 * b + 1 < rows) out[(size_t)(2 * b + 1) * ld + m] = -v.y * s;
+  }
+};
+
+struct ColInvReal2 {  // column DIT -> two real rows: out[2b, m] = Re v, out[2b+1, m] = Im v (scaled, windowed)
+  const double2* ws;
+  int64_t N;
+  int N2;
+  double* out;
+  int64_t ld, keep;
+  int rows;
+  const double* win;  // may be nullptr
+  double scale;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return make_double2(0.0, 0.0);
+    return ws[(size_t)b * N + (size_t)e * N2 + n2];
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int n2 = t * TILE + c;
+    const int64_t m = (int64_t)e * N2 + n2;
+    if (n2 >= N2 || m >= keep) return;
+    double r0 = v.x * scale, r1 = v.y * scale;
+    if (win) { r0 *= win[m]; r1 *= win[m]; }
+    out[(size_t)(2 * b) * ld + m] = r0;
+    if (2 * b + 1 < rows) out[(size_t)(2 * b + 1) * ld + m] = r1;
+  }
+};
+
+struct RealColIn2 {  // rows 2b (re) and 2b+1 (im) in, column DIF
+  const double* x;
+  int64_t ld, n;
+  int rows;
+  double2* ws;
+  const double2* tw;
+  int64_t N;
+  int N2;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int n2 = t * TILE + c;
+    const int64_t i = (int64_t)e * N2 + n2;
+    if (n2 >= N2 || i >= n) return make_double2(0.0, 0.0);
+    return make_double2(x[(size_t)(2 * b) * ld + i], 2 * b + 1 < rows ? x[(size_t)(2 * b + 1) * ld + i] : 0.0);
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int n2 = t * TILE + c;
+    if (n2 >= N2) return;
+    const size_t idx = (size_t)e * N2 + n2;
+    ws[(size_t)b * N + idx] = cmul(v, tw[idx]);
+  }
+};
+
+// min over k of the positive |A[k]|, |B[k]| of a paired spectrum (scipy: h_temp[h_temp > 0].min() per filter).
+// grid = (slices, pairs); positive doubles order like their bit patterns, so the slices meet in an integer atomicMin
+// (out must be preset to +inf).
+__global__ void __launch_bounds__(256) k_min_positive_pair(const double2* __restrict__ ws, const Mirror mir,
+                                                           const double* __restrict__ nyq_val, int rows,
+                                                           double* __restrict__ out) {
+  const int b = blockIdx.y;
+  const double2* z = ws + (size_t)b * mir.N;
+  double va = INFINITY, vb = INFINITY;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < mir.N; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k;
+    const size_t im = mir.of((int)(idx / mir.N2), (int)(idx % mir.N2), &k);
+    double2 a, bb;
+    split_pair(z[idx], z[im], &a, &bb);
+    double ma = hypot(a.x, a.y), mb = hypot(bb.x, bb.y);
+    if (nyq_val && 2 * k == mir.N) {
+      ma = fabs(nyq_val[2 * b]);
+      if (2 * b + 1 < rows) mb = fabs(nyq_val[2 * b + 1]);
+    }
+    if (ma > 0.0) va = fmin(va, ma);
+    if (mb > 0.0) vb = fmin(vb, mb);
+  }
+  for (int o = 16; o; o >>= 1) {
+    va = fmin(va, __shfl_xor_sync(0xffffffffu, va, o));
+    vb = fmin(vb, __shfl_xor_sync(0xffffffffu, vb, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(reinterpret_cast<unsigned long long*>(out + 2 * b), (unsigned long long)__double_as_longlong(va));
+    if (2 * b + 1 < rows)
+      atomicMin(reinterpret_cast<unsigned long long*>(out + 2 * b + 1), (unsigned long long)__double_as_longlong(vb));
+  }
+}
+
+__global__ void k_fill_inf(double* __restrict__ p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = INFINITY;
+}
+
+struct RowInvPairLogMag {  // load 0.5 log(|A| + 1e-7 min+) + i 0.5 log(|B| + 1e-7 min+) from the paired spectrum
+  const double2* src;
+  const double* minpos;
+  const double* nyq_val;
+  int rows;
+  Mirror mir;
+  double2* ws;
+  const double2* tw;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int row = t * TILE + c;
+    if (row >= mir.N1) return make_double2(0.0, 0.0);
+    const double2* z = src + (size_t)b * mir.N;
+    int64_t k;
+    const size_t im = mir.of(row, e, &k);
+    double2 a, bb;
+    split_pair(z[(size_t)row * mir.N2 + e], z[im], &a, &bb);
+    double ma = hypot(a.x, a.y), mb = hypot(bb.x, bb.y);
+    const bool two = 2 * b + 1 < rows;
+    if (nyq_val && 2 * k == mir.N) {
+      ma = fabs(nyq_val[2 * b]);
+      if (two) mb = fabs(nyq_val[2 * b + 1]);
+    }
+    const double la = 0.5 * log(ma + 1e-7 * minpos[2 * b]);
+    const double lb = two ? 0.5 * log(mb + 1e-7 * minpos[2 * b + 1]) : 0.0;
+    return make_double2(la, lb);
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int row = t * TILE + c;
+    if (row >= mir.N1) return;
+    const size_t idx = (size_t)row * mir.N2 + e;
+    ws[(size_t)b * mir.N + idx] = cmul(v, cconj(tw[idx]));
+  }
+};
+
+struct RowInvPairExp {  // load exp(A) + i exp(B) from the paired spectrum of two cepstra
+  const double2* src;
+  int rows;
+  Mirror mir;
+  double2* ws;
+  const double2* tw;
+  __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
+    const int row = t * TILE + c;
+    if (row >= mir.N1) return make_double2(0.0, 0.0);
+    const double2* z = src + (size_t)b * mir.N;
+    int64_t k;
+    const size_t im = mir.of(row, e, &k);
+    double2 a, bb;
+    split_pair(z[(size_t)row * mir.N2 + e], z[im], &a, &bb);
+    double s, cs;
+    sincos(a.y, &s, &cs);
+    const double m = exp(a.x);
+    double2 ea = make_double2(m * cs, m * s);
+    if (2 * b + 1 >= rows) return ea;
+    sincos(bb.y, &s, &cs);
+    const double m2 = exp(bb.x);
+    return make_double2(ea.x - m2 * s, ea.y + m2 * cs);
+  }
+  __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
+    const int row = t * TILE + c;
+    if (row >= mir.N1) return;
+    const size_t idx = (size_t)row * mir.N2 + e;
+    ws[(size_t)b * mir.N + idx] = cmul(v, cconj(tw[idx]));
   }
 };
 
@@ -810,6 +1186,10 @@ int32_t impb_minphase_create(impb_ctx* ctx, int64_t n, const double* hamming_hos
     cudaError_t e = cudaMalloc(&mp->hamming, mp->numtaps * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(mp->hamming, hamming_host, mp->numtaps * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&mp->nyq_S, (mp->nf / 2 + 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&mp->tab, (mp->nf / 2 + 1) * sizeof(FirwinTab));
+    if (e == cudaSuccess) e = cudaMalloc(&mp->pos_a, mp->nf * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&mp->pos_b, mp->nf * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc(&mp->pos_j, mp->nf * sizeof(int));
     if (e == cudaSuccess) {
       k_mp_nyq_table<<<(unsigned)(mp->nf / 2 + 1), 256>>>(mp->hamming, mp->numtaps, mp->nf, mp->nyq_S);
       e = cudaDeviceSynchronize();
@@ -829,17 +1209,22 @@ void impb_minphase_destroy(impb_minphase* mp) {
   mp->small.release();
   cudaFree(mp->hamming);
   cudaFree(mp->nyq_S);
+  cudaFree(mp->tab);
+  cudaFree(mp->pos_a);
+  cudaFree(mp->pos_b);
+  cudaFree(mp->pos_j);
   delete mp;
 }
 
 static int64_t minphase_per_filter_bytes(const impb_minphase* mp) {
-  // complex nf | complex numtaps | real numtaps (h / cepstrum) | real numtaps (|H|) | window | minpos | nyq imprint
-  return mp->nf * 16 + mp->numtaps * 16 + mp->numtaps * 8 + mp->numtaps * 8 + 16;
+  // per filter (two filters share one complex transform): half a complex nf | two halves of complex numtaps |
+  // real numtaps (h / cepstrum) | minpos | nyq imprint; rounded up for an odd filter count by the caller's + slack
+  return mp->nf * 8 + mp->numtaps * 16 + mp->numtaps * 8 + 16 + (mp->nf / 2 + 1) * 8;  // + fx row
 }
 
 int64_t impb_minphase_workspace_bytes(const impb_minphase* mp, int64_t batch) {
   if (!mp || batch < 1) return 0;
-  return std::min<int64_t>(batch, mp->chunk) * minphase_per_filter_bytes(mp) + mp->numtaps * 8 + 256;
+  return (std::min<int64_t>(batch, mp->chunk) + 1) * minphase_per_filter_bytes(mp) + mp->numtaps * 8 + 256;
 }
 
 int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_t ld_gain, int32_t fs, double* fir_out,
@@ -851,56 +1236,78 @@ int32_t impb_minphase_fir(impb_minphase* mp, const double* gain, int64_t ld_gain
   if (batch == 0) return IMPB_OK;
   DeviceGuard g(mp->ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t cb = std::min<int64_t>(batch, mp->chunk);
+  const int64_t cb = std::min<int64_t>(batch, mp->chunk);  // filters per chunk (even, see impb_minphase_create)
+  const int64_t cp = (cb + 1) / 2;                         // pairs per chunk
   char* w = (char*)workspace;
-  double2* ws_big = (double2*)w;            w += cb * mp->nf * 16;
-  double2* ws_small = (double2*)w;          w += cb * mp->numtaps * 16;
-  double* real_buf = (double*)w;            w += cb * mp->numtaps * 8;
-  double* mag = (double*)w;                 w += cb * mp->numtaps * 8;
-  double* minpos = (double*)w;              w += cb * 8;
-  double* nyq_val = (double*)w;             w += cb * 8;
-  static const bool fft_nyquist = getenv("IMPB_MINPHASE_FFT_NYQUIST") != nullptr;  // diagnostic: transform-computed bin
+  double2* ws_big = (double2*)w;            w += cp * mp->nf * 16;
+  double2* ws_a = (double2*)w;              w += cp * mp->numtaps * 16;
+  double2* ws_b = (double2*)w;              w += cp * mp->numtaps * 16;
+  double* real_buf = (double*)w;            w += 2 * cp * mp->numtaps * 8;
+  double* minpos = (double*)w;              w += 2 * cp * 8;
+  double* nyq_val = (double*)w;             w += 2 * cp * 8;
+  double* fxn = (double*)w;                 w += 2 * cp * (mp->nf / 2 + 1) * 8;
   w = (char*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
   double* hwin = (double*)w;
+  static const bool fft_nyquist = getenv("IMPB_MINPHASE_FFT_NYQUIST") != nullptr;  // diagnostic: transform-computed bin
   const Plan2D& pb = mp->big.p;
   const Plan2D& ps = mp->small.p;
   const int64_t nt = mp->numtaps;
+  const Mirror mir{mp->small.perm_col, mp->small.perm_row, mp->small.inv_col, mp->small.inv_row, ps.N1, ps.N2, ps.N};
   k_homomorphic_window<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(hwin, nt);
   for (int64_t b0 = 0; b0 < batch; b0 += cb) {
-    const int nb = (int)std::min<int64_t>(cb, batch - b0);
+    const int nb = (int)std::min<int64_t>(cb, batch - b0);  // filters
+    const int np = (nb + 1) / 2;                            // complex transforms
     int rc;
-    // 1. firwin2: h = irfft(fx * shift)[:numtaps] * hamming
+    // 1. firwin2: h = irfft(fx * shift)[:numtaps] * hamming, two filters per transform
     const double nyq = 0.5 * (double)fs;
     const int64_t nfreqs = mp->nf / 2 + 1;
     FirwinSpec spec{gain + (size_t)b0 * ld_gain, ld_gain, mp->n, mp->nf, nyq / (double)(nfreqs - 1), nyq, 1.0 / nyq,
                     (-(double)(nt - 1) / 2.0) * 3.141592653589793, (double)(fs / 2) / (double)(mp->n - 1),
-                    (double)(fs / 2)};
-    RowInvFirwin ri{spec, ws_big, mp->big.tw, pb.N, pb.N1, pb.N2, mp->big.perm_col, mp->big.perm_row};
-    if ((rc = mp->big.row_inv<TILE>(ri, nb, st))) return rc;
-    ColInvReal c1{ws_big, pb.N, pb.N2, real_buf, nt, nt, mp->hamming, 1.0 / (double)mp->nf};
-    if ((rc = mp->big.col_inv<TILE>(c1, nb, st))) return rc;
-    // 2. |fft(h, n_fft)|
-    RealColIn ci{real_buf, nt, nt, ws_small, mp->small.tw, ps.N, ps.N2};
-    if ((rc = mp->small.col_fwd<TILE>(ci, nb, st))) return rc;
-    k_mp_nyq_imprint<<<nb, 256, 0, st>>>(spec, nt, mp->nyq_S, mp->win_sum, nyq_val);
-    RowFwdOp<AbsOp> ra{ws_small, ps.N, ps.N1, ps.N2, mp->small.perm_col, mp->small.perm_row,
-                       AbsOp{mag, ps.N, fft_nyquist ? nullptr : nyq_val}};
-    if ((rc = mp->small.row_fwd<TILE>(ra, nb, st))) return rc;
-    k_min_positive<<<nb, 256, 0, st>>>(mag, ps.N, minpos);
-    // 3. cepstrum = ifft(0.5 log(|H| + 1e-7 min+)).real * homomorphic window
-    RowInvLogMag rl{mag, minpos, ws_small, mp->small.tw, ps.N, ps.N1, ps.N2};
-    if ((rc = mp->small.row_inv<TILE>(rl, nb, st))) return rc;
-    ColInvReal c2{ws_small, ps.N, ps.N2, real_buf, nt, nt, hwin, 1.0 / (double)nt};
-    if ((rc = mp->small.col_inv<TILE>(c2, nb, st))) return rc;
+                    (double)(fs / 2), (const FirwinTab*)mp->tab, mp->pos_a, mp->pos_b, mp->pos_j};
+    if (mp->tab_fs != fs) {  // per-bin constants of this sampling rate (stream ordered; one rate per plan in practice)
+      k_firwin_table<<<(unsigned)((nfreqs + 255) / 256), 256, 0, st>>>(spec, nt, mp->nyq_S, (FirwinTab*)mp->tab);
+      k_firwin_pos_table<<<(unsigned)((mp->nf + 255) / 256), 256, 0, st>>>((const FirwinTab*)mp->tab, mp->nf, mp->big.perm_col,
+                                                                        mp->big.perm_row, pb.N1, pb.N2, mp->pos_a, mp->pos_b,
+                                                                        mp->pos_j);
+      mp->tab_fs = fs;
+    }
+    // fx rows + imprint partial sums (in ws_a, free until step 2), then the imprints
+    k_firwin_fx<<<dim3(IMPRINT_SLICES, nb), 256, 0, st>>>(spec, fxn, (double*)ws_a);
+    k_mp_nyq_finish<<<(nb + 127) / 128, 128, 0, st>>>(spec, (const double*)ws_a, mp->win_sum, nb, nyq_val);
+    static const bool inv_engine = getenv("IMPB_FIRWIN_INVERSE_ENGINE") != nullptr;  // A/B: the gathered DIT loader
+    if (inv_engine) {
+      RowInvFirwin2 ri{spec, nb, ws_big, mp->big.tw, pb.N, pb.N1, pb.N2, mp->big.perm_col, mp->big.perm_row};
+      if ((rc = mp->big.row_inv<TILE>(ri, np, st))) return rc;
+      ColInvReal2 c1{ws_big, pb.N, pb.N2, real_buf, nt, nt, nb, mp->hamming, 1.0 / (double)mp->nf};
+      if ((rc = mp->big.col_inv<TILE>(c1, np, st))) return rc;
+    } else {
+      ColFwdFirwinFx2 cf{fxn, (const FirwinTab*)mp->tab, mp->nf, nb, ws_big, mp->big.tw, pb.N, pb.N2};
+      if ((rc = mp->big.col_fwd<TILE>(cf, np, st))) return rc;
+      RowFwdOp<RealOut2Op> rf1{ws_big, pb.N, pb.N1, pb.N2, mp->big.perm_col, mp->big.perm_row,
+                               RealOut2Op{real_buf, nt, nt, nb, mp->hamming, 1.0 / (double)mp->nf}};
+      if ((rc = mp->big.row_fwd<TILE>(rf1, np, st))) return rc;
+    }
+    // 2. Z = fft(h_a + i h_b, n_fft), kept in position order
+    RealColIn2 ci{real_buf, nt, nt, nb, ws_a, mp->small.tw, ps.N, ps.N2};
+    if ((rc = mp->small.col_fwd<TILE>(ci, np, st))) return rc;
+    RowPlain<double, TILE> rf{ws_a, ws_a, nullptr, ps.N, ps.N1, ps.N2, 0, 0};
+    if ((rc = mp->small.row_fwd<TILE>(rf, np, st))) return rc;
+    const double* nv = fft_nyquist ? nullptr : nyq_val;
+    k_fill_inf<<<(2 * np + 255) / 256, 256, 0, st>>>(minpos, 2 * np);
+    k_min_positive_pair<<<dim3(8, np), 256, 0, st>>>(ws_a, mir, nv, nb, minpos);
+    // 3. cepstra = ifft(0.5 log(|H| + 1e-7 min+)).real * homomorphic window
+    RowInvPairLogMag rl{ws_a, minpos, nv, nb, mir, ws_b, mp->small.tw};
+    if ((rc = mp->small.row_inv<TILE>(rl, np, st))) return rc;
+    ColInvReal2 c2{ws_b, ps.N, ps.N2, real_buf, nt, nt, nb, hwin, 1.0 / (double)nt};
+    if ((rc = mp->small.col_inv<TILE>(c2, np, st))) return rc;
     // 4. h_min = ifft(exp(fft(cepstrum))).real[:n]
-    RealColIn ci2{real_buf, nt, nt, ws_small, mp->small.tw, ps.N, ps.N2};
-    if ((rc = mp->small.col_fwd<TILE>(ci2, nb, st))) return rc;
-    RowFwdOp<ExpOp> re{ws_small, ps.N, ps.N1, ps.N2, mp->small.perm_col, mp->small.perm_row, ExpOp{ws_small, ps.N}};
-    if ((rc = mp->small.row_fwd<TILE>(re, nb, st))) return rc;
-    RowPlain<double, TILE> rp{ws_small, ws_small, mp->small.tw, ps.N, ps.N1, ps.N2, 1, 0};
-    if ((rc = mp->small.row_inv<TILE>(rp, nb, st))) return rc;
-    ColInvReal c3{ws_small, ps.N, ps.N2, fir_out + (size_t)b0 * ld_out, ld_out, mp->n, nullptr, 1.0 / (double)nt};
-    if ((rc = mp->small.col_inv<TILE>(c3, nb, st))) return rc;
+    RealColIn2 ci2{real_buf, nt, nt, nb, ws_a, mp->small.tw, ps.N, ps.N2};
+    if ((rc = mp->small.col_fwd<TILE>(ci2, np, st))) return rc;
+    if ((rc = mp->small.row_fwd<TILE>(rf, np, st))) return rc;
+    RowInvPairExp re{ws_a, nb, mir, ws_b, mp->small.tw};
+    if ((rc = mp->small.row_inv<TILE>(re, np, st))) return rc;
+    ColInvReal2 c3{ws_b, ps.N, ps.N2, fir_out + (size_t)b0 * ld_out, ld_out, mp->n, nb, nullptr, 1.0 / (double)nt};
+    if ((rc = mp->small.col_inv<TILE>(c3, np, st))) return rc;
   }
   IMPB_CUDA(cudaGetLastError());
   return IMPB_OK;
