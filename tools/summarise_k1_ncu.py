@@ -1,5 +1,5 @@
-"""profiles/r01_k1_ncu_full.md + k1_traffic.json from an `ncu --set full` report of the K1 launch triple.
-usage: python tools/summarise_k1_ncu.py gpurun_out/k1_full_r01c.ncu-rep"""
+"""profiles/<tag>_k1_ncu_full.md (+ k1_traffic.json for the FP64 capture) from an `ncu --set full` report of the K1
+launch triple.  usage: python tools/summarise_k1_ncu.py gpurun_out/k1_full.ncu-rep [tag=r02] [precision=64]"""
 import csv
 import json
 import os
@@ -9,8 +9,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
 rep = sys.argv[1]
+tag = sys.argv[2] if len(sys.argv) > 2 else 'r02'
+prec = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+suffix = '' if prec == 64 else '_f32'
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-open('profiles/r01_k1_ncu_raw.csv', 'w').write(raw)
+open(f'profiles/{tag}_k1_ncu_raw{suffix}.csv', 'w').write(raw)
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 
@@ -26,11 +29,13 @@ def val(r, name):
 
 
 hbm = json.load(open('MEASURED_PEAKS.json')).get('hbm_gbs', 6535.7) if os.path.exists('MEASURED_PEAKS.json') else 6535.7
-out = ["# Round 1 — K1 (sweep deconvolution), `ncu --set full --clock-control none`, B200 (final build of the round)", "",
+pipe = 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active' if prec == 64 else \
+    'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'
+out = [f"# {tag} — K1 (sweep deconvolution, FP{prec}), `ncu --set full --clock-control none`, B200", "",
        "Command (after the same command exited 0 without ncu):",
-       "`ncu --set full --clock-control none --import-source on -k regex:k_fx -s 6 -c 3 python tools/quick_bench.py 224 64 2`",
-       "(224 IRs = 112 ear pairs per launch, FP64, N = 768 x 768).  Raw metric dump: `r01_k1_ncu_raw.csv`.", "",
-       "| kernel | time us | DRAM rd MB | DRAM wr MB | DRAM GB/s | DRAM % | LSU wavefronts % | FP64 pipe % | issue % | warps % | regs "
+       f"`ncu --set full --clock-control none --import-source on -k regex:k_fx -s 6 -c 3 python tools/quick_bench.py 224 {prec} 2`",
+       f"(224 IRs = 112 ear pairs per launch, N = 768 x 768).  Raw metric dump: `{tag}_k1_ncu_raw{suffix}.csv`.", "",
+       f"| kernel | time us | DRAM rd MB | DRAM wr MB | DRAM GB/s | DRAM % | LSU wavefronts % | {'FP64' if prec == 64 else 'FMA'} pipe % | issue % | warps % | regs "
        "| long_sb | mio | lg | short_sb | barrier |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
 tot_b = tot_t = 0.0
 for r in data:
@@ -42,7 +47,7 @@ for r in data:
     out.append(f"| {n} | {t:.1f} | {rd / 1e6:.0f} | {wr / 1e6:.0f} | {(rd + wr) / t / 1e3:.0f} | "
                f"{g('dram__cycles_active.avg.pct_of_peak_sustained_elapsed'):.1f} | "
                f"{g('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed'):.1f} | "
-               f"{g('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'):.1f} | "
+               f"{g(pipe):.1f} | "
                f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
                f"{g('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {g('launch__registers_per_thread'):.0f} | "
                f"{g('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio'):.2f} | "
@@ -51,19 +56,15 @@ for r in data:
                f"{g('smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio'):.2f} | "
                f"{g('smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio'):.2f} |")
 per_ir = tot_b / 224
+alg = 6260320 if prec == 64 else 3130160
 out += ["", "(stall columns: warps stalled per issued instruction.)", "",
-        f"DRAM traffic of the launch triple: {tot_b / 1e9:.2f} GB for 224 IRs = **{per_ir / 1e6:.2f} MB per IR** against 6.26 MB "
-        f"algorithmic ({tot_b / tot_t / 1e3:.0f} GB/s = {100 * tot_b / tot_t / 1e3 / hbm:.0f} % of the measured {hbm:.1f} GB/s copy "
-        "peak while the kernels run): the complex workspace (9.4 MB per pair) makes a round trip through HBM between consecutive "
-        "passes because one launch covers 112 pairs (1 GB of workspace, L2 is 126 MB).  L2-sized chunks and a persistent "
-        "software-pipelined kernel with an L2-resident workspace ring were both measured slower (DESIGN.md).", "",
-        "Reading: the passes sit at 58-80 % of the SM load/store data path (`l1tex__data_pipe_lsu_wavefronts`) AND at 45-69 % of "
-        "HBM bandwidth in real traffic, with the FP64 pipe at 29-54 %: the triple is co-limited by shared-memory/L1 wavefronts "
-        "and DRAM, not by the algorithmic-bytes yardstick.  The final pass is the TMA-fed kernel (`UTMALDG.2D` in SASS): its tile "
-        "arrives through a tensor map with the hardware 128-byte swizzle instead of per-thread loads."]
-open('profiles/r01_k1_ncu_full.md', 'w').write("\n".join(out) + "\n")
-json.dump({"dram_bytes_per_ir": per_ir,
-           "source": "profiles/r01_k1_ncu_full.md (ncu --set full, 224 IRs per launch triple, final build of round 1)"},
-          open('profiles/k1_traffic.json', 'w'))
+        f"DRAM traffic of the launch triple: {tot_b / 1e9:.2f} GB for 224 IRs = **{per_ir / 1e6:.2f} MB per IR** against "
+        f"{alg / 1e6:.2f} MB algorithmic ({tot_b / tot_t / 1e3:.0f} GB/s = {100 * tot_b / tot_t / 1e3 / hbm:.0f} % of the measured "
+        f"{hbm:.1f} GB/s copy peak while the kernels run).  Sum of the three kernels: {tot_t:.1f} us for 224 IRs."]
+open(f'profiles/{tag}_k1_ncu_full{suffix}.md', 'w').write("\n".join(out) + "\n")
+if prec == 64:
+    json.dump({"dram_bytes_per_ir": per_ir,
+               "source": f"profiles/{tag}_k1_ncu_full.md (ncu --set full, 224 IRs per launch triple)"},
+              open('profiles/k1_traffic.json', 'w'))
 print("\n".join(out[6:12]))
 print(per_ir)
