@@ -61,6 +61,10 @@ SIGNATURES = {
     "impb_minphase_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "impb_minphase_fir": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "impb_equalize": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "impb_set_heads": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64] + [c_vp] * 8 + [c_vp]),
+    "impb_set_shift": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64] + [c_vp] * 10 + [c_vp]),
+    "impb_set_shift2": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "impb_set_tails": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_i64, c_i64, c_i64] + [c_vp] * 5 + [c_vp]),
     "impb_pack_tracks": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "impb_resample_out_len": (c_i64, [c_i64, c_i32, c_i32]),
     "impb_resample_plan_create": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, C.POINTER(c_vp)]),
@@ -78,6 +82,14 @@ class View(C.Structure):
     _fields_ = [("shift", c_vp), ("valid_lo", c_vp), ("valid_hi", c_vp), ("fade_in", c_vp), ("fade_in_len", c_i64),
                 ("hint_max", c_vp), ("hint_argmax", c_vp), ("blk_max", c_vp), ("nblk", c_i64), ("blk_len", c_i64),
                 ("blk_first", c_i64)]
+
+
+class SetLayout(C.Structure):
+    """``impb_set_layout`` of include/impb.h."""
+    _fields_ = [("n", c_i32), ("n_spk", c_i32), ("left", c_vp), ("right", c_vp), ("delay", c_vp), ("spk_of_row", c_vp),
+                ("n_pairs", c_i32), ("pa", c_vp), ("pb", c_vp), ("n_pos", c_i32), ("pos_rows", c_vp), ("pos_k", c_vp),
+                ("n_neg", c_i32), ("neg_rows", c_vp), ("neg_k", c_vp), ("n_groups", c_i32), ("gl", c_vp),
+                ("g_ref", c_i32), ("n_grows", c_i32), ("g_rows", c_vp), ("g_of_row", c_vp)]
 
 
 class ImpbError(RuntimeError):

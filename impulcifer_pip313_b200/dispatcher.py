@@ -187,6 +187,11 @@ class BatchDispatcher:
             lay['g_of_row'] = torch.as_tensor(g_of_row, device=device, dtype=torch.int64)
             lay['g_ref'] = [i for i, g in enumerate(groups) if g[0] == 'FL'][0] if 'FL' in spk_list else -1
             lay['set_rows'] = torch.arange(len(plan), device=device, dtype=torch.int64)
+            # the same tables for the device-side bookkeeping kernels (K22, csrc/setplan.cu)
+            lay['dev'] = ops.SetLayoutDev(
+                device, len(plan), left, right, [int(np.round(SPEAKER_DELAYS[s] * fs)) + head for s in spk_list],
+                [row_of[f"{a}-left"] for a, _ in pairs], [row_of[f"{b}-right"] for _, b in pairs], pos_rows, pos_k,
+                neg_rows, neg_k, [row_of[f"{g[0]}-left"] for g in groups], lay['g_ref'], g_rows, g_of_row)
         self._layout = lay
         return lay
 
@@ -243,85 +248,77 @@ class BatchDispatcher:
                                    view=None if e_blk is None else dict(blocks=(e_blk, blk_len, blk_first)))
             launches += 3
             mark('first peaks')
-            pk = peaks.view(S, n)
-            pl, pr = pk[:, lay['left']], pk[:, lay['right']]
-            first = torch.where(pl < pr, pl, pr)
-            crop_sp = torch.clamp(first - lay['delay'][None, :], min=0)
-            crop = torch.zeros((S, n), device=dev, dtype=torch.int64)
-            crop[:, lay['left']] = crop_sp
-            crop[:, lay['right']] = crop_sp
-            crop = crop.reshape(-1)
-            n1 = L - crop
-            off1 = rows * L + crop
-            # max |E row| and where: lets the view kernels skip their max scans (impb_view.hint_*)
-            hint_arg = e_arg - crop
-            # From here on nothing is materialised: the cropped, faded and shifted responses are VIEWS over E
-            # (impb_view: start offset, composite shift, surviving index range, fade-in table).
-            window_in = hann(head * 2)[:head] if head > 0 else None
-            # 3. ipsilateral onset alignment (ref :921-955): lag of the first 30 ms, K6
+            # From here on nothing is materialised and nothing is read back: the cropped, faded and shifted responses
+            # are VIEWS over E (impb_view: start offset, composite shift, surviving index range, fade-in table) and
+            # the integer bookkeeping between the kernels runs on the device (K22, csrc/setplan.cu).
+            ld = lay['dev']
             seg = int(fs * self.segment_ms / 1000)
-            shift = torch.zeros((S, n), device=dev, dtype=torch.int64)
-            if len(lay['pairs']):
-                n1v = n1.view(S, n)
-                ra = (set_base * n + lay['pa'][None, :]).reshape(-1)
-                rb = (set_base * n + lay['pb'][None, :]).reshape(-1)
-                la = torch.clamp(n1v[:, lay['pa']], max=seg).reshape(-1)
-                lb = torch.clamp(n1v[:, lay['pb']], max=seg).reshape(-1)
-                lags = ops.xcorr_lag(flatE, off1[ra], la, off1[rb], lb, max_seg_len=seg, fade_in=window_in).view(S, -1)
-                launches += 1
-                shift.index_add_(1, lay['pos_rows'], torch.clamp(lags, min=0)[:, lay['pos_k']])
-                shift.index_add_(1, lay['neg_rows'], torch.clamp(-lags, min=0)[:, lay['neg_k']])
-            shift = shift.reshape(-1)
-            mark('head crop + ipsilateral lag')
-            lo = torch.clamp(shift, min=0)
-            hi = torch.maximum(torch.minimum(n1 + shift, n1), lo)
-            # 4. group onset alignment against FL-left (ref :957-1001): K2 on the shifted views of the leaders
-            shift2 = torch.zeros((S, n), device=dev, dtype=torch.int64)
-            if 'FL' in lay['speakers'] and len(lay['groups']) > 1:
-                rg = (set_base * n + lay['gl'][None, :]).reshape(-1)
-                gp = ops.peak_index(flatE, off1[rg], n1[rg], max_len=L,
-                                    view=dict(shift=shift[rg], valid_lo=lo[rg], valid_hi=hi[rg], fade_in=window_in,
-                                              hint_max=e_max[rg], hint_argmax=hint_arg[rg])).view(S, -1)
-                launches += 4
-                d = gp - gp[:, lay['g_ref']:lay['g_ref'] + 1]
-                shift2.index_add_(1, lay['g_rows'], -d[:, lay['g_of_row']])
-            elif 'FL' not in lay['speakers']:
+            window_in = hann(head * 2)[:head] if head > 0 else None
+            if 'FL' not in lay['speakers']:
                 raise RuntimeError("Cannot find FL left channel reference for onset alignment.")
-            shift2 = shift2.reshape(-1)
+            # pairwise head crop (ref core/hrir.py:573-606) + the segments of the ipsilateral pairs
+            crop, n1, off1, hint_arg, xs = ops.set_heads(ld, peaks, e_arg, L, seg, S)
+            launches += 1
+            # 3. ipsilateral onset alignment (ref :921-955): lag of the first 30 ms, K6
+            lags = None
+            if xs is not None:
+                lags = ops.xcorr_lag(flatE, xs[0], xs[1], xs[2], xs[3], max_seg_len=seg, fade_in=window_in)
+                launches += 1
+            with_groups = len(lay['groups']) > 1
+            shift, lo, hi, gi, gm = ops.set_shift(ld, lags, n1, off1, hint_arg, e_max, S, with_groups)
+            launches += 1
+            mark('head crop + ipsilateral lag')
+            # 4. group onset alignment against FL-left (ref :957-1001): K2 on the shifted views of the leaders
+            gp = None
+            if with_groups:
+                gp = ops.peak_index(flatE, gi[0], gi[1], max_len=L,
+                                    view=dict(shift=gi[2], valid_lo=gi[3], valid_hi=gi[4], fade_in=window_in, hint_max=gm,
+                                              hint_argmax=gi[5]))
+                launches += 4
+            ops.set_shift2(ld, gp, n1, S, shift, lo, hi)  # shift is now the composite shift, [lo, hi) what survives
+            launches += 1
             mark('group onset peaks')
-            # two length-preserving shifts compose into one shift plus a surviving range
-            total = shift + shift2
-            lo = torch.clamp(lo + shift2, min=0)
-            hi = torch.maximum(torch.minimum(hi + shift2, n1), lo)
-            view = dict(shift=total, valid_lo=lo, valid_hi=hi, fade_in=window_in, hint_max=e_max, hint_argmax=hint_arg)
-            # 5. Lundeby knee per response (K4) -> per-set tail index (ref :614-653): the one host sync
+            view = dict(shift=shift, valid_lo=lo, valid_hi=hi, fade_in=window_in, hint_max=e_max, hint_argmax=hint_arg)
+            # 5. Lundeby knee per response (K4) -> per-set tail index and ragged output geometry (ref :614-653), on
+            #    the device: the final gather is launched without the host having seen a single integer
             _, knee, _, _ = ops.lundeby(flatE, off1, n1, fs, max_len=L, view=view)
             launches += 7  # peak_index (init, max, first peak, final) + window max + block sums + Lundeby
             mark('Lundeby')
-            # everything that does not depend on the results is prepared while the device is still busy
             seconds_per_octave = len(est) / est.fs / est.n_octaves
             fade_out = 2 * int(fs * seconds_per_octave * (1 / 24))
             window_out = hann(fade_out)[fade_out // 2:]
-            ops._dev_window(window_out, dev)
-            row_in_set = np.arange(n)[None, :]
-            host = torch.stack([knee, n1, peaks, crop]).cpu().numpy()
-            mark('host sync')
-            knees_h, n1_h, peaks_h, crop_h = (host[i].reshape(S, n) for i in range(4))
-            if head > 0 and n1_h.min() < head:
-                raise ValueError("an impulse response is shorter than the fade-in; use the HRIR class for such files")
-            tails = np.minimum(n1_h.min(axis=1), next_fast_len(knees_h.max(axis=1))).tolist()
-            if min(tails) < len(window_out):
-                raise ValueError("negative dimensions are not allowed")
-            # one ragged gather for all sets: set s owns n rows of tails[s] samples in a flat buffer
-            tails_np = np.asarray(tails, dtype=np.int64)
-            set_off = np.concatenate([[0], np.cumsum(tails_np * n)])
-            geom = np.stack([np.repeat(tails_np, n),
-                             (set_off[:-1, None] + row_in_set * tails_np[:, None]).reshape(-1)])
-            geom_d = torch.from_numpy(geom).to(dev, non_blocking=True)
-            flat = ops.gather_rows(flatE, off1, geom_d[0], geom_d[1], int(set_off[-1]), int(tails_np.max()), shift=total,
+            # knee <= first peak of the cropped view + 2 s; the views start within head + delay + |shifts| of it
+            tail_bound = min(int(L), next_fast_len(int(2 * fs) + 8192))
+            tails_d, set_off_d, out_len_d, dst_off_d, flags_d = ops.set_tails(ld, knee, n1, S, head, len(window_out),
+                                                                              tail_bound, L)
+            flat = ops.gather_rows(flatE, off1, out_len_d, dst_off_d, S * n * tail_bound, tail_bound, shift=shift,
                                    valid_lo=lo, valid_hi=hi, fade_in=window_in, fade_out=window_out)
-            launches += 1
+            launches += 2
             mark('tail gather launch')
+            # ---- the ONE host read of the step, after its last launch: integers the results report -----------------
+            ints = torch.cat([knee, n1, peaks, crop, tails_d, set_off_d, flags_d]).cpu().numpy()
+            mark('host sync')
+            B4 = 4 * B
+            knees_h, n1_h, peaks_h, crop_h = (ints[i * B:(i + 1) * B].reshape(S, n) for i in range(4))
+            tails_np, set_off, flags = ints[B4:B4 + S], ints[B4 + S:B4 + 2 * S + 1], int(ints[-1])
+            if flags & 1:
+                raise ValueError("an impulse response is shorter than the fade-in; use the HRIR class for such files")
+            if flags & 2:
+                raise ValueError("negative dimensions are not allowed")
+            if flags & 4:
+                # a tail above the preallocated bound (onsets more than 8192 samples into the cropped views): redo the
+                # geometry exactly on the host and gather again, as round 1 did for every batch
+                tails_np = np.minimum(n1_h.min(axis=1), next_fast_len(knees_h.max(axis=1))).astype(np.int64)
+                if tails_np.min() < len(window_out):
+                    raise ValueError("negative dimensions are not allowed")
+                set_off = np.concatenate([[0], np.cumsum(tails_np * n)])
+                geom = np.stack([np.repeat(tails_np, n),
+                                 (set_off[:-1, None] + np.arange(n)[None, :] * tails_np[:, None]).reshape(-1)])
+                geom_d = torch.from_numpy(geom).to(dev)
+                flat = ops.gather_rows(flatE, off1, geom_d[0], geom_d[1], int(set_off[-1]), int(tails_np.max()),
+                                       shift=shift, valid_lo=lo, valid_hi=hi, fade_in=window_in, fade_out=window_out)
+                launches += 1
+            tails = tails_np.tolist()
             # host-only bookkeeping after the last launch: it overlaps the gather
             side_msgs = self._side_warnings(lay, peaks_h)
             offs_l = set_off.tolist()

@@ -428,6 +428,116 @@ def savgol_blend(y, w_normal, it_normal, w_treble, it_treble, k_treble):
     return out
 
 
+# ---- K22: per-set integer bookkeeping ---------------------------------------------------------------------
+class SetLayoutDev:
+    """Device copy of a recording-set layout (``impb_set_layout``): keeps the int32 / int64 index tensors alive."""
+
+    def __init__(self, device, n, left, right, delay, pa, pb, pos_rows, pos_k, neg_rows, neg_k, gl, g_ref, g_rows,
+                 g_of_row):
+        torch = _torch()
+        i32 = lambda v: torch.as_tensor(np.asarray(v, dtype=np.int32).reshape(-1), device=device)
+        spk_of_row = np.zeros(n, dtype=np.int32)
+        for k, (a, b) in enumerate(zip(left, right)):
+            spk_of_row[a] = spk_of_row[b] = k
+        self.t = dict(left=i32(left), right=i32(right),
+                      delay=torch.as_tensor(np.asarray(delay, dtype=np.int64), device=device), spk_of_row=i32(spk_of_row),
+                      pa=i32(pa), pb=i32(pb), pos_rows=i32(pos_rows), pos_k=i32(pos_k), neg_rows=i32(neg_rows),
+                      neg_k=i32(neg_k), gl=i32(gl), g_rows=i32(g_rows), g_of_row=i32(g_of_row))
+        t = self.t
+        ptr = lambda k: t[k].data_ptr() if t[k].numel() else None
+        self.n, self.n_pairs, self.n_groups = int(n), len(pa), len(gl)
+        self.c = _lib.SetLayout(int(n), len(left), ptr('left'), ptr('right'), ptr('delay'), ptr('spk_of_row'),
+                                len(pa), ptr('pa'), ptr('pb'), len(pos_rows), ptr('pos_rows'), ptr('pos_k'),
+                                len(neg_rows), ptr('neg_rows'), ptr('neg_k'), len(gl), ptr('gl'), int(g_ref),
+                                len(g_rows), ptr('g_rows'), ptr('g_of_row'))
+        self.device = device
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def set_heads(lay: SetLayoutDev, peaks, e_arg, L, seg, S):
+    """-> crop, n1, off1, hint_arg [S*n] and (xa_off, xa_len, xb_off, xb_len) [S*n_pairs] (None without pairs)."""
+    torch = _torch()
+    dev = peaks.device
+    B = S * lay.n
+    out = torch.empty((4, B), dtype=torch.int64, device=dev)
+    x = torch.empty((4, S * lay.n_pairs), dtype=torch.int64, device=dev) if lay.n_pairs else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_set_heads(
+            _lib.context(_dev(peaks)).handle, C.byref(lay.c), peaks.data_ptr(), e_arg.data_ptr(), int(L), int(seg), int(S),
+            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+            *([x[i].data_ptr() for i in range(4)] if x is not None else [None] * 4), _stream(peaks)), "impb_set_heads")
+    return out[0], out[1], out[2], out[3], x
+
+
+def set_shift(lay: SetLayoutDev, lags, n1, off1, hint_arg, e_max, S, want_groups):
+    """-> shift, lo, hi [S*n]; group-leader views (off, len, shift, lo, hi [int64], max [f64], arg) or None."""
+    torch = _torch()
+    dev = n1.device
+    out = torch.empty((3, S * lay.n), dtype=torch.int64, device=dev)
+    gi = gm = None
+    if want_groups:
+        gi = torch.empty((6, S * lay.n_groups), dtype=torch.int64, device=dev)
+        gm = torch.empty(S * lay.n_groups, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_set_shift(
+            _lib.context(_dev(n1)).handle, C.byref(lay.c), _p(lags), n1.data_ptr(), off1.data_ptr(), hint_arg.data_ptr(),
+            e_max.data_ptr(), int(S), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+            *([gi[i].data_ptr() for i in range(5)] if gi is not None else [None] * 5), _p(gm),
+            gi[5].data_ptr() if gi is not None else None, _stream(n1)), "impb_set_shift")
+    return out[0], out[1], out[2], gi, gm
+
+
+def set_shift2(lay: SetLayoutDev, group_peaks, n1, S, shift, lo, hi):
+    """Composes the group-onset shifts into ``shift / lo / hi`` in place."""
+    torch = _torch()
+    with torch.cuda.device(n1.device):
+        _lib.check(_lib.lib().impb_set_shift2(_lib.context(_dev(n1)).handle, C.byref(lay.c), _p(group_peaks), n1.data_ptr(),
+                                              int(S), shift.data_ptr(), lo.data_ptr(), hi.data_ptr(), _stream(n1)),
+                   "impb_set_shift2")
+
+
+@functools.lru_cache(maxsize=8)
+def _smooth5_host(limit: int):
+    vals = []
+    p2 = 1
+    while p2 <= 2 * limit:
+        p3 = p2
+        while p3 <= 2 * limit:
+            p5 = p3
+            while p5 <= 2 * limit:
+                vals.append(p5)
+                p5 *= 5
+            p3 *= 3
+        p2 *= 2
+    return np.array(sorted(vals), dtype=np.int64)
+
+
+_smooth_cache = {}
+
+
+def set_tails(lay: SetLayoutDev, knee, n1, S, head, fade_out_len, tail_bound, table_limit):
+    """-> tails [S], set_off [S+1], out_len [S*n], dst_off [S*n], flags [1] (all int64, device)."""
+    torch = _torch()
+    dev = n1.device
+    key = (int(table_limit), str(dev))
+    sm = _smooth_cache.get(key)
+    if sm is None:
+        sm = _smooth_cache[key] = torch.as_tensor(_smooth5_host(int(table_limit)), device=dev)
+    B = S * lay.n
+    buf = torch.empty(S + (S + 1) + 2 * B + 1, dtype=torch.int64, device=dev)
+    tails, set_off = buf[:S], buf[S:2 * S + 1]
+    out_len, dst_off, flags = buf[2 * S + 1:2 * S + 1 + B], buf[2 * S + 1 + B:2 * S + 1 + 2 * B], buf[-1:]
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_set_tails(
+            _lib.context(_dev(n1)).handle, C.byref(lay.c), knee.data_ptr(), n1.data_ptr(), int(S), sm.data_ptr(),
+            int(sm.numel()), int(head), int(fade_out_len), int(tail_bound), tails.data_ptr(), set_off.data_ptr(),
+            out_len.data_ptr(), dst_off.data_ptr(), flags.data_ptr(), _stream(n1)), "impb_set_tails")
+    return tails, set_off, out_len, dst_off, flags
+
+
 # ---- K21 --------------------------------------------------------------------------------------------
 def equalize(error, logf, cap, gain_k, half_window, smoothen=True):
     """rows of error curves -> (equalization rows, int32 status per row) — ``impb_equalize`` (K21)."""

@@ -268,6 +268,57 @@ IMPB_API void impb_resample_plan_destroy(impb_resample* plan);
 IMPB_API int32_t impb_resample_execute(impb_resample* plan, const double* src, int64_t ld_src, int64_t n,
                               const double* decay, double* dst, int64_t ld_dst, int64_t batch, void* stream);
 
+/* ---- K22: per-set integer bookkeeping on the device ------------------------------------------------------------
+ * Replaces the per-recording-set Python arithmetic of HRIR.crop_heads (core/hrir.py:573-606: pairwise first peak
+ * minus the speaker delay), align_ipsilateral_all (:936-955: which responses a lag shifts),
+ * align_onset_groups_peak_leftref (:981-1001: group onset against FL-left) and crop_tails (:627-646:
+ * tail = min(min len, next_fast_len(max knee))) for S sets of one layout at once, so that a batch needs no
+ * device->host read between its kernels.  All arrays are device pointers; rows are (set, response) pairs, s * n + r. */
+typedef struct impb_set_layout {
+  int32_t n;                 /* responses per set */
+  int32_t n_spk;             /* speakers: rows left[k] / right[k], crop delay[k] = round(SPEAKER_DELAYS * fs) + head */
+  const int32_t* left;
+  const int32_t* right;
+  const int64_t* delay;
+  const int32_t* spk_of_row; /* [n] speaker index of every row */
+  int32_t n_pairs;           /* ipsilateral pairs: left row of a, right row of b */
+  const int32_t* pa;
+  const int32_t* pb;
+  int32_t n_pos;             /* rows shifted by max(lag, 0) / max(-lag, 0) of pair pos_k / neg_k */
+  const int32_t* pos_rows;
+  const int32_t* pos_k;
+  int32_t n_neg;
+  const int32_t* neg_rows;
+  const int32_t* neg_k;
+  int32_t n_groups;          /* onset groups: leader row gl[g]; g_ref = the group led by FL-left */
+  const int32_t* gl;
+  int32_t g_ref;
+  int32_t n_grows;           /* rows moved by the onset difference of group g_of_row[i] */
+  const int32_t* g_rows;
+  const int32_t* g_of_row;
+} impb_set_layout;
+
+/* crop, n1 = L - crop, off1 = row * L + crop, hint_arg = e_arg - crop per row; segment offsets / lengths (<= seg) of the
+ * ipsilateral pairs for impb_xcorr_lag (xa_*, xb_*: [S, n_pairs], nullable) */
+IMPB_API int32_t impb_set_heads(impb_ctx* ctx, const impb_set_layout* lay, const int64_t* peaks, const int64_t* e_arg,
+                       int64_t L, int64_t seg, int64_t S, int64_t* crop, int64_t* n1, int64_t* off1, int64_t* hint_arg,
+                       int64_t* xa_off, int64_t* xa_len, int64_t* xb_off, int64_t* xb_len, void* stream);
+/* shift / surviving range [lo, hi) per row from the lags ([S, n_pairs], nullable = no pairs); gathered views of the
+ * group leaders for impb_peak_index (g_*: [S, n_groups], nullable) */
+IMPB_API int32_t impb_set_shift(impb_ctx* ctx, const impb_set_layout* lay, const int64_t* lags, const int64_t* n1,
+                       const int64_t* off1, const int64_t* hint_arg, const double* e_max, int64_t S, int64_t* shift,
+                       int64_t* lo, int64_t* hi, int64_t* g_off, int64_t* g_len, int64_t* g_shift, int64_t* g_lo,
+                       int64_t* g_hi, double* g_max, int64_t* g_arg, void* stream);
+/* composes the group-onset shift into shift / lo / hi (in place); group_peaks: [S, n_groups], nullable = none */
+IMPB_API int32_t impb_set_shift2(impb_ctx* ctx, const impb_set_layout* lay, const int64_t* group_peaks, const int64_t* n1,
+                        int64_t S, int64_t* shift, int64_t* lo, int64_t* hi, void* stream);
+/* tails[S], set_off[S + 1] (exclusive sum of tail * n), out_len / dst_off per row; smooth: ascending 5-smooth numbers
+ * (next_fast_len table); flags[0] bits: 1 = a response shorter than the fade-in, 2 = a tail shorter than the fade-out,
+ * 4 = a tail above tail_bound or a knee beyond the table (the caller falls back to an exactly sized gather) */
+IMPB_API int32_t impb_set_tails(impb_ctx* ctx, const impb_set_layout* lay, const int64_t* knee, const int64_t* n1, int64_t S,
+                       const int64_t* smooth, int32_t n_smooth, int64_t head, int64_t fade_out_len, int64_t tail_bound,
+                       int64_t* tails, int64_t* set_off, int64_t* out_len, int64_t* dst_off, int64_t* flags, void* stream);
+
 /* ---- output packing (next-row component) -------------------------------------------------------
  * Replaces the np.vstack / transpose / libsndfile PCM conversion of HRIR.write_wav (core/hrir.py:426-455) and
  * audio_io.write_wav (core/audio_io.py:82-97).  row_offsets: device int64[n_tracks], element offset of each
