@@ -161,3 +161,16 @@ def install(verbose: bool = False):
     if verbose:
         print(f"impulcifer_pip313_b200: installed over the reference ({rebound} bindings replaced)")
     return _installed
+
+
+# ``import impulcifer_pip313_b200 as b200; b200.install()`` must keep working after this submodule has been imported:
+# the import machinery binds the submodule over the package attribute of the same name, so the module itself is callable.
+import types as _types
+
+
+class _CallableModule(_types.ModuleType):
+    def __call__(self, *args, **kwargs):
+        return install(*args, **kwargs)
+
+
+sys.modules[__name__].__class__ = _CallableModule

@@ -39,3 +39,40 @@ def test_install_rebinds_reference_classes():
     from core import parallel_utils
     assert parallel_utils.parallel_map is got['parallel_map']
     assert parallel_utils.parallel_map(abs, [-1, -2, 3], use_threads=True) == [1, 2, 3]
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present")
+def test_copies_keep_the_merged_classes():
+    """ir.copy() / fr.copy() / HRIR.copy() after install() must return the MERGED classes (reference mix-ins such as
+    plot_fr / write_to_csv and the overrides install() adds), not the bare shim classes."""
+    import numpy as np
+    ref_import.load()
+    import impulcifer_pip313_b200 as b200
+    got = b200.install()
+    IR, FR = got['ImpulseResponse'], got['FrequencyResponse']
+    ir = IR(np.linspace(0.0, 1.0, 32), 48000)
+    c = ir.copy()
+    assert type(c) is IR and hasattr(c, 'plot_fr') and np.array_equal(c.data, ir.data) and c.data is not ir.data
+    f = np.geomspace(20.0, 20000.0, 64)
+    fr = FR(name='t', frequency=f, raw=np.zeros(64))
+    fc = fr.copy()
+    assert type(fc) is FR and fc.name == 't_copy' and np.array_equal(fc.frequency, fr.frequency)
+
+
+def test_reference_staging_recipe_is_a_plain_copy(tmp_path):
+    """oracle/make_ref.py stages the reference unmodified: every staged Python file is byte-identical to its source."""
+    import filecmp
+    import os
+    src = os.environ.get("IMPULCIFER_REFERENCE_SRC", "/root/reference")
+    staged = os.path.join(os.path.dirname(os.path.abspath(ref_import.__file__)), "_ref")
+    if not (os.path.isdir(os.path.join(src, "core")) and os.path.isdir(os.path.join(staged, "core"))):
+        pytest.skip("needs both the reference checkout and the staged copy (build container only)")
+    checked = 0
+    for pkg in ("core", "autoeq", "infra"):
+        for base, _dirs, files in os.walk(os.path.join(staged, pkg)):
+            for name in files:
+                if name.endswith(".py"):
+                    rel = os.path.relpath(os.path.join(base, name), staged)
+                    assert filecmp.cmp(os.path.join(staged, rel), os.path.join(src, rel), shallow=False), rel
+                    checked += 1
+    assert checked > 40
