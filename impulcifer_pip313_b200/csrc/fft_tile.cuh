@@ -42,6 +42,18 @@ template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; 
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
   C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
 }
+// FP32: Blackwell's packed FP32x2 instructions (FADD2 / FFMA2 / FMUL2, sm_100+) do the re and im halves of a complex
+// add / subtract in ONE issue slot; the FP32 K1 kernels are issue-bound with FADD as their most frequent instruction
+// (profiles/r02_k1_ncu_full_f32.md).  Same IEEE results as the scalar forms (a - b as fma(b, -1, a) is exact-then-rounded).
+#ifndef IMPB_NO_PACKED_F32
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+#ifdef IMPB_PACKED_F32_CMUL
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
+}
+#endif
+#endif
 template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
 // multiply by -i (forward quarter turn) / +i
 template <typename C> __device__ __forceinline__ C mul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
