@@ -115,14 +115,16 @@ template <typename T> struct Fft2D {
     done.insert(key);
     return IMPB_OK;
   }
+// short sub-FFTs (S <= 192: 15-24 butterflies per column and stage) leave half of a 256-thread CTA idle: 128 threads
 #define IMPB_FXG_CASE(S_, R0_, R1_, R2_)                                                             \
   case S_: {                                                                                         \
-    auto k = INV ? k_fxg_inv<T, TILE, 256, Radix3<R0_, R1_, R2_>, ROW, F>                             \
-                 : k_fxg_fwd<T, TILE, 256, Radix3<R0_, R1_, R2_>, ROW, F>;                            \
+    constexpr int NTX = (S_ <= 192) ? 128 : 256;                                                      \
+    auto k = INV ? k_fxg_inv<T, TILE, NTX, Radix3<R0_, R1_, R2_>, ROW, F>                             \
+                 : k_fxg_fwd<T, TILE, NTX, Radix3<R0_, R1_, R2_>, ROW, F>;                            \
     const size_t smem = fx_tile_elems<S_, TILE>() * sizeof(cx_t<T>);                                  \
     int rc = fxg_prepare(k, smem, device);                                                            \
     if (rc) return rc;                                                                                \
-    k<<<grid, 256, smem, st>>>(tw0, tw1, f);                                                          \
+    k<<<grid, NTX, smem, st>>>(tw0, tw1, f);                                                          \
     IMPB_CUDA(cudaGetLastError());                                                                    \
     return IMPB_OK;                                                                                   \
   }
