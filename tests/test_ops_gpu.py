@@ -408,3 +408,86 @@ def test_equalize_matches_reference(T):
     fr4 = FrequencyResponse(name='t', frequency=f, raw=np.zeros(len(f)), error=np.full(len(f), 3.0))
     fr4.equalize(max_gain=6.0)
     assert np.allclose(fr4.equalization, -3.0, atol=1e-9) and np.allclose(fr4.equalized_raw, -3.0, atol=1e-9)
+
+
+def test_set_bookkeeping_kernels_match_host_arithmetic(T):
+    """K22 (impb_set_heads / _shift / _shift2 / _tails) against the reference's per-set integer arithmetic written out
+    in numpy (core/hrir.py:573-606, 936-955, 981-1001, 627-646) on random integers for the 7.1 layout, including the
+    flag bits (response shorter than the fade-in, tail shorter than the fade-out, tail above the preallocated bound)."""
+    from scipy.fftpack import next_fast_len  # 5-smooth, what core/hrir.py:640 calls (scipy.fft's is 11-smooth)
+    from impulcifer_pip313_b200 import ops
+    from impulcifer_pip313_b200.dispatcher import BatchDispatcher
+    from impulcifer_pip313_b200.estimator import ImpulseResponseEstimator
+    est = ImpulseResponseEstimator(min_duration=0.5, fs=48000)
+    disp = BatchDispatcher(est, ['FL', 'FR', 'FC', 'SL', 'SR', 'BL', 'BR'])
+    L = 2 * 48000 + len(est)
+    n_samples = 96000 + 7 * L
+    lay = disp._prepare(2, n_samples, T.device('cuda'))
+    ld, n = lay['dev'], lay['n']
+    S, seg = 9, 1440
+    rng = np.random.default_rng(3)
+    peaks = rng.integers(0, L - 5000, size=(S, n))
+    peaks[0, :2] = 3            # crop clamps at 0
+    e_arg = rng.integers(0, L, size=(S, n))
+    left, right = np.array(lay['left_h']), np.array(lay['right_h'])
+    delay = lay['delay'].cpu().numpy()
+    crop_sp = np.maximum(np.minimum(peaks[:, left], peaks[:, right]) - delay[None, :], 0)
+    crop = np.zeros((S, n), dtype=np.int64)
+    crop[:, left] = crop_sp
+    crop[:, right] = crop_sp
+    n1 = L - crop
+    rows = np.arange(S * n).reshape(S, n)
+    off1 = rows * L + crop
+    dv = lambda a: T.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).cuda()
+    g_crop, g_n1, g_off1, g_hint, xs = ops.set_heads(ld, dv(peaks.reshape(-1)), dv(e_arg.reshape(-1)), L, seg, S)
+    assert np.array_equal(g_crop.cpu().numpy().reshape(S, n), crop)
+    assert np.array_equal(g_n1.cpu().numpy().reshape(S, n), n1)
+    assert np.array_equal(g_off1.cpu().numpy().reshape(S, n), off1)
+    assert np.array_equal(g_hint.cpu().numpy().reshape(S, n), e_arg - crop)
+    pa, pb = lay['pa'].cpu().numpy(), lay['pb'].cpu().numpy()
+    assert np.array_equal(xs[0].cpu().numpy().reshape(S, -1), off1[:, pa])
+    assert np.array_equal(xs[1].cpu().numpy().reshape(S, -1), np.minimum(n1[:, pa], seg))
+    assert np.array_equal(xs[2].cpu().numpy().reshape(S, -1), off1[:, pb])
+    assert np.array_equal(xs[3].cpu().numpy().reshape(S, -1), np.minimum(n1[:, pb], seg))
+    # lags -> shift, surviving range, gathered group-leader views
+    lags = rng.integers(-40, 40, size=(S, len(pa)))
+    shift = np.zeros((S, n), dtype=np.int64)
+    for r, k in zip(lay['pos_rows'].cpu().numpy(), lay['pos_k'].cpu().numpy()):
+        shift[:, r] += np.maximum(lags[:, k], 0)
+    for r, k in zip(lay['neg_rows'].cpu().numpy(), lay['neg_k'].cpu().numpy()):
+        shift[:, r] += np.maximum(-lags[:, k], 0)
+    lo = np.maximum(shift, 0)
+    hi = np.maximum(np.minimum(n1 + shift, n1), lo)
+    e_max = T.rand(S * n, dtype=T.float64, device='cuda')
+    g_shift, g_lo, g_hi, gi, gm = ops.set_shift(ld, dv(lags.reshape(-1)), g_n1, g_off1, g_hint, e_max, S, True)
+    assert np.array_equal(g_shift.cpu().numpy().reshape(S, n), shift)
+    assert np.array_equal(g_lo.cpu().numpy().reshape(S, n), lo) and np.array_equal(g_hi.cpu().numpy().reshape(S, n), hi)
+    gl = lay['gl'].cpu().numpy()
+    for i, want in enumerate((off1[:, gl], n1[:, gl], shift[:, gl], lo[:, gl], hi[:, gl], (e_arg - crop)[:, gl])):
+        assert np.array_equal(gi[i].cpu().numpy().reshape(S, -1), want), i
+    assert np.array_equal(gm.cpu().numpy().reshape(S, -1), e_max.cpu().numpy().reshape(S, n)[:, gl])
+    # group onset peaks -> composite shift
+    gp = rng.integers(0, 300, size=(S, len(gl)))
+    d = gp - gp[:, lay['g_ref']:lay['g_ref'] + 1]
+    shift2 = np.zeros((S, n), dtype=np.int64)
+    for r, g in zip(lay['g_rows'].cpu().numpy(), lay['g_of_row'].cpu().numpy()):
+        shift2[:, r] += -d[:, g]
+    lo2 = np.maximum(lo + shift2, 0)
+    hi2 = np.maximum(np.minimum(hi + shift2, n1), lo2)
+    ops.set_shift2(ld, dv(gp.reshape(-1)), g_n1, S, g_shift, g_lo, g_hi)
+    assert np.array_equal(g_shift.cpu().numpy().reshape(S, n), shift + shift2)
+    assert np.array_equal(g_lo.cpu().numpy().reshape(S, n), lo2) and np.array_equal(g_hi.cpu().numpy().reshape(S, n), hi2)
+    # knees -> per-set tails and the ragged geometry
+    knee = rng.integers(3000, 90000, size=(S, n))
+    tails = np.minimum(n1.min(axis=1), np.array([next_fast_len(int(k)) for k in knee.max(axis=1)]))
+    t_d, off_d, len_d, dst_d, flags = ops.set_tails(ld, dv(knee.reshape(-1)), g_n1, S, 48, 1892, 104976, L)
+    assert int(flags.item()) == 0
+    assert np.array_equal(t_d.cpu().numpy(), tails)
+    set_off = np.concatenate([[0], np.cumsum(tails * n)])
+    assert np.array_equal(off_d.cpu().numpy(), set_off)
+    assert np.array_equal(len_d.cpu().numpy().reshape(S, n), np.repeat(tails[:, None], n, axis=1))
+    assert np.array_equal(dst_d.cpu().numpy().reshape(S, n), set_off[:-1, None] + np.arange(n)[None, :] * tails[:, None])
+    # flags: fade-out longer than a tail (2), tail above the bound (4), response shorter than the fade-in (1)
+    assert int(ops.set_tails(ld, dv(knee.reshape(-1)), g_n1, S, 48, 200000, 104976, L)[4].item()) & 2
+    assert int(ops.set_tails(ld, dv(knee.reshape(-1)), g_n1, S, 48, 1892, 4096, L)[4].item()) & 4
+    assert int(ops.set_tails(ld, dv(knee.reshape(-1)), g_n1, S, int(n1.min()) + 1, 1892, 104976, L)[4].item()) & 1
