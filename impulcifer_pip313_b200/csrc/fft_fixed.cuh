@@ -90,9 +90,12 @@ __device__ __forceinline__ void fx_twiddles(const cx_t<T>* __restrict__ tw, int 
 // multiplier per OUTPUT element (four-step twiddle); it is fetched at the top of the trip so that its latency
 // hides behind the butterfly instead of sitting in front of the store.
 struct NoPost {};
+struct NoTripHook { __device__ __forceinline__ void operator()(int) const {} };
+// TRIP (optional) is called with the trip number before the trip's loads: the TMA-fed column pass waits there for the
+// box of rows the trip reads, so the butterflies of the first rows overlap the transfer of the rest of the tile.
 template <typename T, int TILE, int NT, int S, int LEN, int R, bool INV, bool ROW, bool PF = false, bool TWFULL = false,
-          class LD, class ST, class POST>
-__device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, ST st, POST post) {
+          class LD, class ST, class POST, class TRIP = NoTripHook>
+__device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, ST st, POST post, TRIP trip = TRIP{}) {
   constexpr int STRIDE = LEN / R;
   constexpr int PER_COL = S / R;
   constexpr int ITEMS = PER_COL * TILE;
@@ -111,6 +114,7 @@ __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, 
   }
 #pragma unroll kTripUnroll
   for (int it = 0; it < TRIPS; ++it) {
+    trip(it);
     const int w = threadIdx.x + it * NT;
     if ((ITEMS % NT) != 0 && w >= ITEMS) break;
     int c, j;
@@ -267,9 +271,10 @@ k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1,
 
 // The column DIT pass.  FROM_SMEM: the tile has already been filled (TMA, see k_fx_inv_tma) and the first stage runs
 // in place on it instead of loading from HBM.
-template <typename T, int TILE, int NT, class RX, class F, bool FROM_SMEM>
+template <typename T, int TILE, int NT, class RX, class F, bool FROM_SMEM, class TRIP = NoTripHook>
 __device__ __forceinline__ void fx_inv_core(unsigned char* smem_raw, const cx_t<T>* __restrict__ tw0,
-                                            const cx_t<T>* __restrict__ tw1, const F& f, const int t, const int b) {
+                                            const cx_t<T>* __restrict__ tw1, const F& f, const int t, const int b,
+                                            TRIP trip = TRIP{}) {
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
   // running max |re|, |im| of what this thread stores: the per-row max|x| the peak search needs comes for free
   T mx_re = (T)0, mx_im = (T)0;
@@ -300,7 +305,7 @@ __device__ __forceinline__ void fx_inv_core(unsigned char* smem_raw, const cx_t<
   };
   auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
-  if constexpr (FROM_SMEM) fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false>(nullptr, sl, ss, NoPost{});
+  if constexpr (FROM_SMEM) fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false>(nullptr, sl, ss, NoPost{}, trip);
   else fx_stage<T, TILE, NT, RX::S, RX::S1, RX::R2, true, false, kPrefetch>(nullptr, gl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, true, false>(tw1, sl, ss, NoPost{});
@@ -395,19 +400,27 @@ __global__ void __launch_bounds__(NT, 2)
 k_fx_inv_tma(const double2* __restrict__ tw0, const double2* __restrict__ tw1, const F f,
              const __grid_constant__ CUtensorMap ws_map) {
   extern __shared__ __align__(1024) unsigned char smem_tma[];
-  __shared__ __align__(8) unsigned long long bar;
+  constexpr int BOXES = RX::S / 256;
+  __shared__ __align__(8) unsigned long long bar[BOXES];
   static_assert(TILE == 8 && RX::S % 256 == 0, "128-byte rows, whole 256-row boxes");
+  // first DIT stage: radix R2 on consecutive rows, NT / TILE butterflies per trip = rows [it, it + 1) * R2 * NT / TILE
+  static_assert(RX::R2 * NT / TILE == 256, "one trip of the first stage reads exactly one 256-row box");
   const int t = blockIdx.x, b = blockIdx.y;
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < BOXES; ++k) mbar_init(&bar[k], 1);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, RX::S * TILE * (unsigned)sizeof(double2));
 #pragma unroll
-    for (int k = 0; k < RX::S / 256; ++k)  // coordinates in doubles (inner) and matrix rows (outer)
-      tma_load_2d(smem_tma + (size_t)k * 256 * TILE * sizeof(double2), &ws_map, t * TILE * 2, b * RX::S + k * 256, &bar);
+    for (int k = 0; k < BOXES; ++k) {  // coordinates in doubles (inner) and matrix rows (outer)
+      mbar_expect_tx(&bar[k], 256 * TILE * (unsigned)sizeof(double2));
+      tma_load_2d(smem_tma + (size_t)k * 256 * TILE * sizeof(double2), &ws_map, t * TILE * 2, b * RX::S + k * 256, &bar[k]);
+    }
   }
-  mbar_wait(&bar, 0);
-  fx_inv_core<double, TILE, NT, RX, F, true>(smem_tma, tw0, tw1, f, t, b);
+  // trip `it` of the first stage touches only box `it`: its butterflies run while the later boxes are still in flight
+  auto wait_box = [&](int it) { if (it < BOXES) mbar_wait(&bar[it], 0); };
+  fx_inv_core<double, TILE, NT, RX, F, true>(smem_tma, tw0, tw1, f, t, b, wait_box);
 }
 
 // row pass: forward, x spectrum, inverse.  tw0r / tw1r are the [p-1][np] (transposed) stage tables.
