@@ -35,6 +35,8 @@ template <typename T> struct DeconvArgs {
   cx_t<T>* ws;
   const cx_t<T>* tw;
   const cx_t<T>* hs;
+  const cx_t<T>* dcol;  // progression steps of the four-step twiddle (Fft2D::dcol / drow)
+  const cx_t<T>* drow;
   int64_t N;
   int N1, N2;
   // input
@@ -87,10 +89,24 @@ template <typename T, int TILE, bool PRE = false> struct DeconvColIn {
     const size_t idx = (size_t)e * a.N2 + n2;
     a.ws[(size_t)b * a.N + idx] = PRE ? v : cmul(v, __ldg(a.tw + idx));
   }
+#ifndef IMPB_NO_TW_PROGRESSION
+  // the specialised kernels fetch post() for output 0 of a butterfly only and multiply up by post_step()^p
+  static constexpr bool post_progression = PRE;
+#else
+  static constexpr bool post_progression = false;
+#endif
+  __device__ __forceinline__ cx_t<T> post_step(int t, int c) const {
+    const int n2 = t * TILE + c;
+    return n2 < a.N2 ? __ldg(a.dcol + n2) : mkc<T>(0, 0);
+  }
   // four-step twiddle of output (e, c), fetched ahead of the butterfly by the specialised kernels
   __device__ __forceinline__ cx_t<T> post(int t, int e, int c) const {
     const int n2 = t * TILE + c;
+#ifdef IMPB_ABL_NO_TABLES
+    return mkc<T>((T)1, (T)0);
+#else
     return n2 < a.N2 ? __ldg(a.tw + (size_t)e * a.N2 + n2) : mkc<T>(0, 0);
+#endif
   }
   // column walk of the staged copy: address of the sample feeding re (which=0) / im (which=1) of element (0, c),
   // the number of leading rows that hold samples (0: the whole column is zero padding) and the row pitch
@@ -123,7 +139,11 @@ template <typename T, int TILE, bool PRE = false> struct DeconvRow {
     return a.ws[(size_t)b * a.N + (size_t)row * a.N2 + e];
   }
   __device__ __forceinline__ cx_t<T> pw(int t, int R, int items, int q, int w) const {
+#ifdef IMPB_ABL_NO_TABLES  // developer ablation (tools/build_variant.sh): what the table loads cost
+    return mkc<T>((T)1, (T)0);
+#else
     return __ldg(a.hs + ((size_t)t * R + q) * items + w);
+#endif
   }
   __device__ __forceinline__ void store(int b, int t, int e, int c, cx_t<T> v) const {
     const int row = t * TILE + c;
@@ -131,9 +151,22 @@ template <typename T, int TILE, bool PRE = false> struct DeconvRow {
     const size_t idx = (size_t)row * a.N2 + e;
     a.ws[(size_t)b * a.N + idx] = PRE ? v : cmul(v, cconj(__ldg(a.tw + idx)));
   }
+#ifndef IMPB_NO_TW_PROGRESSION
+  static constexpr bool post_progression = PRE;
+#else
+  static constexpr bool post_progression = false;
+#endif
+  __device__ __forceinline__ cx_t<T> post_step(int t, int c) const {
+    const int row = t * TILE + c;
+    return row < a.N1 ? cconj(__ldg(a.drow + row)) : mkc<T>(0, 0);
+  }
   __device__ __forceinline__ cx_t<T> post(int t, int e, int c) const {
     const int row = t * TILE + c;
+#ifdef IMPB_ABL_NO_TABLES
+    return mkc<T>((T)1, (T)0);
+#else
     return row < a.N1 ? cconj(__ldg(a.tw + (size_t)row * a.N2 + e)) : mkc<T>(0, 0);
+#endif
   }
 };
 
@@ -311,17 +344,22 @@ template <class K> static int fx_prepare(K kernel, size_t smem, int device) {
   return IMPB_OK;
 }
 
+// threads per CTA of the half-width instantiations (A/B: 128 = four 49 KB CTAs per SM instead of two 256-thread ones)
+#ifndef IMPB_HALF_NT
+#define IMPB_HALF_NT 256
+#endif
 // WIDTHS_: 1 = full-width tiles only, 2 = half-width only (TileOf<T>/2 columns: 88.2 ... 192 kHz plans, whose
 // sub-FFTs do not fit shared memory twice per SM at full width), 3 = both; a kernel is only instantiated for the tile
 // widths its length is planned with
 #define IMPB_FX_CASE(KERNEL, S_, R0_, R1_, R2_, WIDTHS_)                                        \
   case S_: {                                                                                    \
     if constexpr ((TILE == TileOf<T>::value && ((WIDTHS_) & 1)) || (TILE == TileOf<T>::value / 2 && ((WIDTHS_) & 2))) { \
-      auto k = KERNEL<T, TILE, 256, Radix3<R0_, R1_, R2_>, F>;                                   \
+      constexpr int NTX = (TILE == TileOf<T>::value) ? 256 : IMPB_HALF_NT;                        \
+      auto k = KERNEL<T, TILE, NTX, Radix3<R0_, R1_, R2_>, F>;                                   \
       const size_t smem = fx_tile_elems<S_, TILE>() * sizeof(cx_t<T>);                           \
       int rc = fx_prepare(k, smem, device);                                                      \
       if (rc) return rc;                                                                         \
-      k<<<grid, 256, smem, st>>>(tw0, tw1, f);                                                   \
+      k<<<grid, NTX, smem, st>>>(tw0, tw1, f);                                                   \
       IMPB_CUDA(cudaGetLastError());                                                             \
       return IMPB_OK;                                                                            \
     } else {                                                                                     \
@@ -672,7 +710,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
     if (pl->precision == 64) {
       DeconvArgs<double> a{};
       const Plan2D& p = pl->e64.fft.p;
-      a.ws = (double2*)workspace + (size_t)si * slice_pairs * p.N; a.tw = pl->e64.fft.tw; a.hs = pl->e64.hs;
+      a.ws = (double2*)workspace + (size_t)si * slice_pairs * p.N; a.tw = pl->e64.fft.tw; a.hs = pl->e64.hs; a.dcol = pl->e64.fft.dcol; a.drow = pl->e64.fft.drow;
       a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
       a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = 1;
@@ -683,7 +721,7 @@ int32_t impb_deconv_execute(impb_plan* pl, const void* rec, const int64_t* in_of
     } else {
       DeconvArgs<float> a{};
       const Plan2D& p = pl->e32.fft.p;
-      a.ws = (float2*)workspace + (size_t)si * slice_pairs * p.N; a.tw = pl->e32.fft.tw; a.hs = pl->e32.hs;
+      a.ws = (float2*)workspace + (size_t)si * slice_pairs * p.N; a.tw = pl->e32.fft.tw; a.hs = pl->e32.hs; a.dcol = pl->e32.fft.dcol; a.drow = pl->e32.fft.drow;
       a.N = p.N; a.N1 = p.N1; a.N2 = p.N2;
       a.rec = rec; a.in_offsets = in_offsets; a.ld_in = ld_in; a.len = len; a.nrows = batch; a.row0 = 2 * p0; a.in_fmt = in_fmt;
       a.out = out; a.ld_out = ld_out; a.out_start = pl->s + out_offset; a.out_len = out_len; a.out_f64 = out_f64 ? 1 : 0;

@@ -24,6 +24,8 @@ template <typename T> struct Fft2D {
   bool col_fixed = false, row_fixed = false;
   int* perm_col = nullptr;     // device copies of the digit-reversal maps
   int* perm_row = nullptr;
+  cx_t<T>* dcol = nullptr;     // [N2] exp(-2 pi i n2 (N1 / R_last_col) / N): four-step twiddle step of the column pass
+  cx_t<T>* drow = nullptr;     // [N1] exp(-2 pi i k1(p1) (N2 / R_first_row) / N): ... of the row pass (by position p1)
   int* inv_col = nullptr;      // their inverses (natural index -> position): mirror-bin lookups of paired real rows
   int* inv_row = nullptr;
   std::vector<int> h_perm_col, h_perm_row;
@@ -74,6 +76,29 @@ template <typename T> struct Fft2D {
         IMPB_CUDA(cudaMemcpy(*dst, ttf.data(), ttf.size() * sizeof(cx_t<T>), cudaMemcpyHostToDevice));
       }
     }
+    if (col_fixed && row_fixed) {
+      // progression form of the four-step twiddle (fft_fixed.cuh: PostOf): output p of the last column-DIF stage sits
+      // at frequency k_base + p * N1 / R_last, output p of the last row-DIT stage at sample np + p * N2 / R_first
+      int fc[3], frw[3];
+      fixed_radices(p.N1, fc);
+      fixed_radices(p.N2, frw);
+      const int64_t inc_col = p.N1 / fc[2], inc_row = p.N2 / frw[0];
+      std::vector<cx_t<T>> hc((size_t)p.N2), hr((size_t)p.N1);
+      for (int n2 = 0; n2 < p.N2; ++n2) {
+        double re, im;
+        unit_root(((int64_t)n2 * inc_col) % p.N, p.N, &re, &im);
+        hc[(size_t)n2] = mkc<T>((T)re, (T)im);
+      }
+      for (int p1 = 0; p1 < p.N1; ++p1) {
+        double re, im;
+        unit_root(((int64_t)h_perm_col[p1] * inc_row) % p.N, p.N, &re, &im);
+        hr[(size_t)p1] = mkc<T>((T)re, (T)im);
+      }
+      IMPB_CUDA(cudaMalloc(&dcol, p.N2 * sizeof(cx_t<T>)));
+      IMPB_CUDA(cudaMalloc(&drow, p.N1 * sizeof(cx_t<T>)));
+      IMPB_CUDA(cudaMemcpy(dcol, hc.data(), p.N2 * sizeof(cx_t<T>), cudaMemcpyHostToDevice));
+      IMPB_CUDA(cudaMemcpy(drow, hr.data(), p.N1 * sizeof(cx_t<T>), cudaMemcpyHostToDevice));
+    }
     IMPB_CUDA(cudaGetDevice(&device));
     IMPB_CUDA(cudaMalloc(&perm_col, p.N1 * sizeof(int)));
     IMPB_CUDA(cudaMalloc(&perm_row, p.N2 * sizeof(int)));
@@ -91,8 +116,9 @@ template <typename T> struct Fft2D {
 
   void release() {
     cudaFree(tw); cudaFree(tab_col); cudaFree(tab_row); cudaFree(perm_col); cudaFree(perm_row);
-    cudaFree(inv_col); cudaFree(inv_row);
+    cudaFree(inv_col); cudaFree(inv_row); cudaFree(dcol); cudaFree(drow);
     inv_col = inv_row = nullptr;
+    dcol = drow = nullptr;
     for (int s = 0; s < 2; ++s) {
       cudaFree(fx_col[s]); cudaFree(fx_row[s]); cudaFree(fxf_col[s]); cudaFree(fxf_row[s]);
       fx_col[s] = fx_row[s] = fxf_col[s] = fxf_row[s] = nullptr;

@@ -90,6 +90,11 @@ __device__ __forceinline__ void fx_twiddles(const cx_t<T>* __restrict__ tw, int 
 // multiplier per OUTPUT element (four-step twiddle); it is fetched at the top of the trip so that its latency
 // hides behind the butterfly instead of sitting in front of the store.
 struct NoPost {};
+// A POST functor with `static constexpr bool progression = true` supplies first(e, c) = the multiplier of a butterfly's
+// output 0 and step(c) = D with multiplier(output p) = first * D^p (four-step twiddles: the R outputs of the stage sit
+// on an arithmetic progression of frequencies / samples): ONE table load per butterfly instead of R.
+template <class P, class = void> struct is_progression : std::false_type {};
+template <class P> struct is_progression<P, std::enable_if_t<P::progression>> : std::true_type {};
 struct NoTripHook { __device__ __forceinline__ void operator()(int) const {} };
 // TRIP (optional) is called with the trip number before the trip's loads: the TMA-fed column pass waits there for the
 // box of rows the trip reads, so the butterflies of the first rows overlap the transfer of the rest of the tile.
@@ -101,6 +106,16 @@ __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, 
   constexpr int ITEMS = PER_COL * TILE;
   constexpr int TRIPS = (ITEMS + NT - 1) / NT;
   constexpr bool HAS_POST = !std::is_same<POST, NoPost>::value;
+  constexpr bool PROG = is_progression<POST>::value;
+  constexpr int NPOW = (R > 8) ? 4 : (R > 4) ? 3 : (R > 2) ? 2 : 1;
+  cx_t<T> dpow[PROG ? NPOW : 1];
+  if constexpr (PROG && !ROW) {
+    // column pass: a thread keeps its column in every trip (NT is a multiple of TILE), so D is fetched once
+    static_assert(NT % TILE == 0, "per-thread constant column");
+    dpow[0] = post.step(threadIdx.x % TILE);
+#pragma unroll
+    for (int k = 1; k < NPOW; ++k) dpow[k] = cmul(dpow[k - 1], dpow[k - 1]);
+  }
   // PF (stages that read HBM): the operands of trip it+1 are requested before trip it is computed
   cx_t<T> xn[PF ? R : 1];
   if constexpr (PF) {
@@ -121,10 +136,19 @@ __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, 
     fx_decode<ROW, TILE, PER_COL>(w, c, j);
     const int b = j / STRIDE, np = j % STRIDE;
     const int base = b * LEN + np;
-    cx_t<T> m[HAS_POST ? R : 1];
-    if constexpr (HAS_POST) {
+    cx_t<T> m[(HAS_POST && !PROG) ? R : 1];
+    cx_t<T> m0;  // PROG: multiplier of output 0; output p takes m0 * D^p (D, D^2, D^4 ... fetched once per thread)
+    if constexpr (HAS_POST && !PROG) {
 #pragma unroll
       for (int p = 0; p < R; ++p) m[p] = post(base + p * STRIDE, c);
+    }
+    if constexpr (PROG) {
+      m0 = post.first(base, c);
+      if constexpr (ROW) {  // row pass: the row changes from trip to trip, D with it (one more load per butterfly)
+        dpow[0] = post.step(c);
+#pragma unroll
+        for (int k = 1; k < NPOW; ++k) dpow[k] = cmul(dpow[k - 1], dpow[k - 1]);
+      }
     }
     cx_t<T> x[R];
     if constexpr (PF) {
@@ -142,7 +166,11 @@ __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, 
 #pragma unroll
       for (int q = 0; q < R; ++q) x[q] = ld(base + q * STRIDE, c);
     }
+#ifdef IMPB_ABL_NO_MATH  // developer ablation: loads, exchanges and stores only
+    if (false) {
+#else
     if (STRIDE > 1) {
+#endif
       cx_t<T> wv[R];
       fx_twiddles<T, R, ROW, STRIDE, TWFULL>(tw, np, wv);
       if (INV) {
@@ -155,11 +183,27 @@ __device__ __forceinline__ void fx_stage(const cx_t<T>* __restrict__ tw, LD ld, 
         for (int p = 1; p < R; ++p) x[p] = cmul(x[p], wv[p]);
       }
     } else {
+#ifndef IMPB_ABL_NO_MATH
       Dft<T, R, INV>::run(x);
+#endif
     }
-    if constexpr (HAS_POST) {
+    if constexpr (HAS_POST && !PROG) {
 #pragma unroll
       for (int p = 0; p < R; ++p) x[p] = cmul(x[p], m[p]);
+    }
+    if constexpr (PROG) {
+      // m_p = m_(p - hi) * D^hi with hi the largest power of two <= p: every multiplier is a product of at most
+      // log2(R) table-derived factors (the same composition the stage twiddles use)
+      cx_t<T> mp[R];
+      mp[0] = m0;
+#pragma unroll
+      for (int p = 1; p < R; ++p) {
+        const int hi = (p >= 8) ? 8 : (p >= 4) ? 4 : (p >= 2) ? 2 : 1;
+        const int k = (hi == 8) ? 3 : (hi == 4) ? 2 : (hi == 2) ? 1 : 0;
+        mp[p] = cmul(mp[p - hi], dpow[k]);
+      }
+#pragma unroll
+      for (int p = 0; p < R; ++p) x[p] = cmul(x[p], mp[p]);
     }
 #pragma unroll
     for (int p = 0; p < R; ++p) {
@@ -188,17 +232,38 @@ __device__ __forceinline__ void fx_mid(LD ld, ST st, PW pw) {
     cx_t<T> x[R];
 #pragma unroll
     for (int q = 0; q < R; ++q) x[q] = ld(j * R + q, c);
+#ifndef IMPB_ABL_NO_MATH
     Dft<T, R, false>::run(x);
+#endif
 #pragma unroll
     for (int q = 0; q < R; ++q) x[q] = cmul(x[q], h[q]);
+#ifndef IMPB_ABL_NO_MATH
     Dft<T, R, true>::run(x);
+#endif
 #pragma unroll
     for (int q = 0; q < R; ++q) st(j * R + q, c, x[q]);
   }
 }
 
+// adapter: F::post(t, e, c) per output, or (when F offers post_first / post_step) the progression form
+template <class F, class = void> struct has_prog : std::false_type {};
+template <class F> struct has_prog<F, std::enable_if_t<F::post_progression>> : std::true_type {};
+template <typename T, class F, bool = has_prog<F>::value> struct PostOf {
+  const F& f;
+  int t;
+  __device__ __forceinline__ cx_t<T> operator()(int e, int c) const { return f.post(t, e, c); }
+};
+template <typename T, class F> struct PostOf<T, F, true> {
+  static constexpr bool progression = true;
+  const F& f;
+  int t;
+  __device__ __forceinline__ cx_t<T> operator()(int e, int c) const { return f.post(t, e, c); }
+  __device__ __forceinline__ cx_t<T> first(int e, int c) const { return f.post(t, e, c); }
+  __device__ __forceinline__ cx_t<T> step(int c) const { return f.post_step(t, c); }
+};
+
 template <typename T, int TILE, int NT, class RX, class F>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_fx_fwd(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
@@ -207,7 +272,7 @@ k_fx_fwd(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const
   auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
   auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
-  auto post = [&](int e, int c) -> cx_t<T> { return f.post(t, e, c); };
+  PostOf<T, F> post{f, t};
   fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, false>(tw0, gl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false, false>(tw1, sl, ss, NoPost{});
@@ -228,7 +293,7 @@ template <int BYTES> __device__ __forceinline__ void cp_async_n(void* smem_dst, 
 }
 
 template <typename T, int TILE, int NT, class RX, class F>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
@@ -261,7 +326,7 @@ k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1,
   auto gs = [&](int e, int c, cx_t<T> v) { f.store(b, t, e, c, v); };
   auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<false, TILE, RX::S>(e, c)]; };
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<false, TILE, RX::S>(e, c)] = v; };
-  auto post = [&](int e, int c) -> cx_t<T> { return f.post(t, e, c); };
+  PostOf<T, F> post{f, t};
   fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, false>(tw0, sl, ss, NoPost{});
   __syncthreads();
   fx_stage<T, TILE, NT, RX::S, RX::S0, RX::R1, false, false>(tw1, sl, ss, NoPost{});
@@ -350,7 +415,7 @@ __device__ __forceinline__ void fx_inv_core(unsigned char* smem_raw, const cx_t<
 }
 
 template <typename T, int TILE, int NT, class RX, class F>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_fx_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   fx_inv_core<T, TILE, NT, RX, F, false>(smem_raw, tw0, tw1, f, blockIdx.x, blockIdx.y);
@@ -396,7 +461,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 }
 
 template <int TILE, int NT, class RX, class F>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_fx_inv_tma(const double2* __restrict__ tw0, const double2* __restrict__ tw1, const F f,
              const __grid_constant__ CUtensorMap ws_map) {
   extern __shared__ __align__(1024) unsigned char smem_tma[];
@@ -437,7 +502,7 @@ __device__ __forceinline__ void fx_conv_core(unsigned char* smem_raw, const cx_t
   auto sl = [&](int e, int c) -> cx_t<T> { return tile[fx_smem<true, TILE, RX::S>(e, c)]; };
   auto ss = [&](int e, int c, cx_t<T> v) { tile[fx_smem<true, TILE, RX::S>(e, c)] = v; };
   auto pw = [&](int q, int w) -> cx_t<T> { return f.pw(t, RX::R2, ITEMS_MID, q, w); };
-  auto post = [&](int e, int c) -> cx_t<T> { return f.post(t, e, c); };
+  PostOf<T, F> post{f, t};
   if constexpr (FROM_SMEM) fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, true>(tw0r, sl, ss, NoPost{});
   else fx_stage<T, TILE, NT, RX::S, RX::S, RX::R0, false, true, kPrefetch>(tw0r, gl, ss, NoPost{});
   __syncthreads();
@@ -451,7 +516,7 @@ __device__ __forceinline__ void fx_conv_core(unsigned char* smem_raw, const cx_t
 }
 
 template <typename T, int TILE, int NT, class RX, class F>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_fx_conv(const cx_t<T>* __restrict__ tw0r, const cx_t<T>* __restrict__ tw1r, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   fx_conv_core<T, TILE, NT, RX, F, false>(smem_raw, tw0r, tw1r, f, blockIdx.x, blockIdx.y);
@@ -463,7 +528,7 @@ k_fx_conv(const cx_t<T>* __restrict__ tw0r, const cx_t<T>* __restrict__ tw1r, co
 // these whenever their sub-FFT length has a specialised radix sequence, with full-table (exact) stage twiddles.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int TILE, int NT, class RX, bool ROW, class F>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_fxg_fwd(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);
@@ -480,7 +545,7 @@ k_fxg_fwd(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, cons
 }
 
 template <typename T, int TILE, int NT, class RX, bool ROW, class F>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_fxg_inv(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1, const F f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx_t<T>* tile = reinterpret_cast<cx_t<T>*>(smem_raw);

@@ -223,6 +223,9 @@ bool plan_2d(const impb_ctx* ctx, int64_t n_min, bool exact, int elem_bytes, Pla
   // full tile = 128-byte HBM segments; transforms whose sub-FFTs do not fit shared memory at that width
   // (192 kHz sweeps) fall back to half-width tiles (64-byte segments)
   const int tile = 64 / elem_bytes;
+  // A/B switch (tools/): plan the K1 transform on half-width tiles even where full-width ones fit
+  static const bool force_half = getenv("IMPB_FORCE_HALF_TILE") != nullptr;
+  if (force_half && allow_half_tile && plan_2d_tile(ctx, n_min, exact, elem_bytes, tile / 2, out)) return true;
   if (plan_2d_tile(ctx, n_min, exact, elem_bytes, tile, out)) {
     // a full-width plan that leaves room for ONE CTA per SM loses to half-width tiles when both sub-FFT lengths
     // have specialised kernels at that width (192 kHz: 1536 x 1600, two 256-thread CTAs of 98 KB per SM)
