@@ -707,6 +707,25 @@ __global__ void __launch_bounds__(256) k_min_positive_pair(const double2* __rest
   }
 }
 
+// K8, decimated: 20 log10 |X[first + step j]| of real rows 2b (re) and 2b+1 (im) from the position-ordered spectrum of
+// the paired transform.  frequency_response() keeps every step-th bin only (core/impulse_response.py:170-178), so two
+// rows share one complex transform and only the kept bins and their mirrors are read back.
+__global__ void __launch_bounds__(256) k_pair_mag_db(const double2* __restrict__ ws, const Mirror mir, int rows,
+                                                     int64_t first, int64_t step, int64_t n_out, double* __restrict__ out,
+                                                     int64_t ld) {
+  const int b = blockIdx.y;
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n_out) return;
+  const int64_t k = first + step * j, km = k == 0 ? 0 : mir.N - k;
+  const double2* z = ws + (size_t)b * mir.N;
+  const double2 v = z[(size_t)mir.inv1[(int)(k % mir.N1)] * mir.N2 + mir.inv2[(int)(k / mir.N1)]];
+  const double2 vm = z[(size_t)mir.inv1[(int)(km % mir.N1)] * mir.N2 + mir.inv2[(int)(km / mir.N1)]];
+  double2 a, bb;
+  split_pair(v, vm, &a, &bb);
+  out[(size_t)(2 * b) * ld + j] = 20.0 * log10(hypot(a.x, a.y));
+  if (2 * b + 1 < rows) out[(size_t)(2 * b + 1) * ld + j] = 20.0 * log10(hypot(bb.x, bb.y));
+}
+
 __global__ void k_fill_inf(double* __restrict__ p, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = INFINITY;
@@ -1083,6 +1102,38 @@ int32_t impb_magnitude_db(impb_fft* f, const double* x, int64_t ld_x, double* ma
                          MagDbOp{mag_out + (size_t)b0 * ld_out, ld_out, half}};
     if ((rc = f->f.row_fwd<TILE>(ro, nb, st))) return rc;
   }
+  return IMPB_OK;
+}
+
+int32_t impb_magnitude_db_decimated(impb_fft* f, const double* x, int64_t ld_x, int64_t first, int64_t step,
+                                    double* mag_out, int64_t ld_out, int64_t batch, void* workspace, void* stream) {
+  if (!f || !x || !mag_out || !workspace || batch < 0 || ld_x < f->n || first < 0 || step < 1) {
+    set_error("impb_magnitude_db_decimated: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (f->chirp) {
+    set_error("impb_magnitude_db_decimated: chirp-z plans only serve impb_magnitude_db");
+    return IMPB_EUNSUPPORTED;
+  }
+  const int64_t half = (f->n + 1) / 2;
+  const int64_t n_out = half > first ? (half - first + step - 1) / step : 0;
+  if (ld_out < n_out) { set_error("impb_magnitude_db_decimated: ld_out < kept bins"); return IMPB_EINVAL; }
+  if (batch == 0 || n_out == 0) return IMPB_OK;
+  DeviceGuard g(f->ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const Plan2D& p = f->f.p;
+  const Mirror mir{f->f.perm_col, f->f.perm_row, f->f.inv_col, f->f.inv_row, p.N1, p.N2, p.N};
+  double2* ws = (double2*)workspace;
+  for (int64_t b0 = 0; b0 < batch; b0 += 65534) {  // an even number of rows per launch: pairs never straddle
+    const int nr = (int)std::min<int64_t>(65534, batch - b0), np = (nr + 1) / 2;
+    double2* w = ws + (size_t)(b0 / 2) * p.N;
+    int rc = f->f.col_fwd<TILE>(RealColIn2{x + (size_t)b0 * ld_x, ld_x, f->n, nr, w, f->f.tw, p.N, p.N2}, np, st);
+    if (!rc) rc = f->f.row_fwd<TILE>(RowPlain<double, TILE>{w, w, nullptr, p.N, p.N1, p.N2, 0, 0}, np, st);
+    if (rc) return rc;
+    k_pair_mag_db<<<dim3((unsigned)((n_out + 255) / 256), np), 256, 0, st>>>(w, mir, nr, first, step, n_out,
+                                                                              mag_out + (size_t)b0 * ld_out, ld_out);
+  }
+  IMPB_CUDA(cudaGetLastError());
   return IMPB_OK;
 }
 

@@ -253,10 +253,10 @@ def frequency_response_batch(irs, fs):
     f = np.arange(half) * (fs / n)
     pts = (fs / 2) / 4.0
     step = 1 if (pts < 2 or len(f) < 2) else (int(round(len(f) / pts)) or 1)
-    mag = ops.magnitude_db(irs)
     fd = f[1::step]
-    md = mag[:, 1::step]
     if len(fd) == 0:
-        fd, md = f[1:], mag[:, 1:]
+        fd, step = f[1:], 1
+    # step > 1 (any response longer than fs/4 samples): only the kept bins are produced, two rows per transform
+    md = ops.magnitude_db_decimated(irs, 1, step) if step > 1 else ops.magnitude_db(irs)[:, 1:].contiguous()
     grid = FrequencyResponse.generate_frequencies(f_step=1.01, f_min=10, f_max=fs / 2)
-    return ops.loglerp(np.log10(fd), md.contiguous(), np.log10(grid))
+    return ops.loglerp(np.log10(fd), md, np.log10(grid))

@@ -339,6 +339,32 @@ def magnitude_db(x):
     return out
 
 
+def magnitude_db_decimated(x, first, step):
+    """``magnitude_db(x)[:, first::step]`` without the bins in between: rows ride in pairs through one complex
+    transform and only the kept bins are read back (the decimation of ``ImpulseResponse.frequency_response``,
+    reference core/impulse_response.py:170-178).  Lengths that need the chirp-z plan take the full transform."""
+    torch = _torch()
+    if x.dim() == 1:
+        x = x[None, :]
+    x = x.contiguous()
+    batch, n = x.shape
+    first, step = int(first), int(step)
+    half = (n + 1) // 2
+    n_out = max(0, -(-(half - first) // step))
+    plan = fft_plan(n, _dev(x))
+    out = torch.empty((batch, n_out), dtype=torch.float64, device=x.device)
+    if n_out == 0 or batch == 0:
+        return out
+    with torch.cuda.device(x.device):
+        ws = plan.workspace(batch)
+        rc = _lib.lib().impb_magnitude_db_decimated(plan.handle, x.data_ptr(), n, first, step, out.data_ptr(), n_out,
+                                                    batch, ws.data_ptr(), _stream(x))
+    if rc == -4:  # IMPB_EUNSUPPORTED: chirp-z plan
+        return magnitude_db(x)[:, first::step].contiguous()
+    _lib.check(rc, "impb_magnitude_db_decimated")
+    return out
+
+
 def magnitude_lin(x, nfft, n_bins=None):
     """|rfft(x, n=nfft)|[:n_bins] for every row of ``x`` ([batch, n_valid <= nfft] float64 CUDA)."""
     torch = _torch()

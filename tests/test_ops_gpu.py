@@ -258,6 +258,27 @@ def test_magnitude_db_lengths_with_large_prime_factors(T, n):
         assert np.array_equal(fr.frequency, f_o) and np.max(np.abs(fr.raw - raw_o)) < 1e-7
 
 
+@pytest.mark.parametrize("n,step", [(21600, 2), (57600, 5), (84375, 7), (96000, 8), (1000, 3), (1009, 4)])
+def test_magnitude_db_decimated(T, n, step):
+    """The kept bins of frequency_response() (`m[1::step]`, core/impulse_response.py:170-178) from the paired
+    transform: odd row counts, rows 30 dB apart, and a chirp-z length (1009) that takes the full transform."""
+    from impulcifer_pip313_b200 import ops
+    rng = np.random.default_rng(n + step)
+    x = rng.standard_normal((5, n)) * np.exp(-np.arange(n) / (n / 8.0))
+    x[1] *= 0.03
+    x[4] *= 7.0
+    for rows in (5, 2, 1):
+        got = ops.magnitude_db_decimated(T.from_numpy(x[:rows]).cuda(), 1, step).cpu().numpy()
+        for r in range(rows):
+            _, m = O.magnitude_response(x[r], 48000)
+            want = m[1::step]
+            assert got[r].shape == want.shape
+            assert np.max(np.abs(got[r] - want)) < 1e-8
+    full = ops.magnitude_db(T.from_numpy(x).cuda()).cpu().numpy()
+    got0 = ops.magnitude_db_decimated(T.from_numpy(x).cuda(), 0, step).cpu().numpy()
+    assert got0.shape == full[:, 0::step].shape and np.max(np.abs(got0 - full[:, 0::step])) < 1e-8
+
+
 def test_frequency_response_chain_golden(T):
     """magnitude -> decimate -> log-f lerp onto the 783-point grid == reference frequency_response()."""
     from impulcifer_pip313_b200 import ops
