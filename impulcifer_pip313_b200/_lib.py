@@ -55,6 +55,8 @@ SIGNATURES = {
     "impb_add_delayed": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "impb_magnitude_lin": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "impb_loglerp": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp]),
+    "impb_minphase_gain_grid": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_dbl, c_i32, c_vp, c_i64,
+                                        c_i64, c_vp, c_vp]),
     "impb_savgol_blend": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp,
                                   c_vp, c_vp, c_i64, c_i64, c_vp]),
     "impb_minphase_create": (c_i32, [c_vp, c_i64, c_vp, C.POINTER(c_vp)]),

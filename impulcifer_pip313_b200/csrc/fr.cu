@@ -142,22 +142,78 @@ struct MagLinOp {  // |X[k]| for k < nbins (natural order)
   }
 };
 
-__global__ void k_loglerp(const double* __restrict__ lx, const double* __restrict__ y, int64_t n_in, int64_t ld_in,
-                          const double* __restrict__ lxo, int64_t n_out, double* __restrict__ out, int64_t ld_out) {
-  const int b = blockIdx.y;
-  const double* yy = y + (size_t)b * ld_in;
-  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x) {
-    const double xo = lxo[j];
-    // searchsorted(lx, xo, 'right') - 1, clipped to [0, n_in-2]
-    int64_t lo = 0, hi = n_in;
-    while (lo < hi) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (lx[mid] <= xo) lo = mid + 1; else hi = mid;
+// searchsorted(lx, xo, 'right') - 1, clipped to [0, n_in-2]: the knot interval of an output abscissa (the same for every row)
+__device__ __forceinline__ int64_t lerp_interval(const double* __restrict__ lx, int64_t n_in, double xo) {
+  int64_t lo = 0, hi = n_in;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (lx[mid] <= xo) lo = mid + 1; else hi = mid;
+  }
+  return max((int64_t)0, min(lo - 1, n_in - 2));
+}
+__device__ __forceinline__ double lerp_eval(double y0, double y1, double x0, double x1, double xo) {
+  return (y0 * (x1 - xo) + y1 * (xo - x0)) / (x1 - x0);
+}
+
+constexpr int LERP_ROWS = 16;  // rows per block: one interval search per output abscissa serves all of them
+
+__global__ void __launch_bounds__(256) k_loglerp(const double* __restrict__ lx, const double* __restrict__ y, int64_t n_in,
+                                                 int64_t ld_in, const double* __restrict__ lxo, int64_t n_out,
+                                                 double* __restrict__ out, int64_t ld_out, int64_t batch) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n_out) return;
+  const double xo = lxo[j];
+  const int64_t i = lerp_interval(lx, n_in, xo);
+  const double x0 = lx[i], x1 = lx[i + 1];
+  const int64_t b1 = min(batch, ((int64_t)blockIdx.y + 1) * LERP_ROWS);
+  for (int64_t b = (int64_t)blockIdx.y * LERP_ROWS; b < b1; ++b) {
+    const double* yy = y + (size_t)b * ld_in;
+    out[(size_t)b * ld_out + j] = lerp_eval(yy[i], yy[i + 1], x0, x1, xo);
+  }
+}
+
+// ---- gain grid of minimum_phase_impulse_response (autoeq/frequency_response.py:653-676) ----------------------------------
+// dB curve on the log-f grid -> linear gain on linspace(0, fs//2, n): k=1 interpolation, the value at f_min for every
+// f <= f_min (a prefix of n_below points), [normalize: - max - 0.5 dB], * 2, 10^(./20), last point 0.  Two launches:
+// the interpolation (+ per-row maximum when normalising) and the shaping; arithmetic in the order the reference applies it.
+__device__ __forceinline__ unsigned long long order_key(double v) {  // monotone map of doubles onto unsigned integers
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double order_value(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+__global__ void __launch_bounds__(256) k_gain_lerp(const double* __restrict__ lx, const double* __restrict__ y, int64_t n_in,
+                                                   int64_t ld_in, const double* __restrict__ lxo, int64_t n_out,
+                                                   int64_t n_below, double lx_min, double* __restrict__ out, int64_t ld_out,
+                                                   int64_t batch, unsigned long long* __restrict__ rowmax) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool live = j < n_out;
+  const double xo = live ? (j < n_below ? lx_min : lxo[j]) : lx_min;
+  const int64_t i = lerp_interval(lx, n_in, xo);
+  const double x0 = lx[i], x1 = lx[i + 1];
+  const int64_t b1 = min(batch, ((int64_t)blockIdx.y + 1) * LERP_ROWS);
+  for (int64_t b = (int64_t)blockIdx.y * LERP_ROWS; b < b1; ++b) {
+    const double* yy = y + (size_t)b * ld_in;
+    const double v = lerp_eval(yy[i], yy[i + 1], x0, x1, xo);
+    if (live) out[(size_t)b * ld_out + j] = v;
+    if (rowmax) {
+      unsigned long long k = live ? order_key(v) : 0ull;
+      for (int o = 16; o; o >>= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, o));
+      if ((threadIdx.x & 31) == 0) atomicMax(rowmax + b, k);
     }
-    int64_t i = lo - 1;
-    i = max((int64_t)0, min(i, n_in - 2));
-    const double x0 = lx[i], x1 = lx[i + 1];
-    out[(size_t)b * ld_out + j] = (yy[i] * (x1 - xo) + yy[i + 1] * (xo - x0)) / (x1 - x0);
+  }
+}
+__global__ void __launch_bounds__(256) k_gain_shape(double* __restrict__ g, int64_t n, int64_t ld,
+                                                    const unsigned long long* __restrict__ rowmax) {
+  const int64_t b = blockIdx.y;
+  double* row = g + (size_t)b * ld;
+  const double mx = rowmax ? order_value(rowmax[b]) : 0.0;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    double v = row[j];
+    if (rowmax) { v -= mx; v -= 0.5; }
+    v *= 2.0;
+    row[j] = j == n - 1 ? 0.0 : pow(10.0, v / 20.0);
   }
 }
 
@@ -1172,11 +1228,37 @@ int32_t impb_loglerp(impb_ctx* ctx, const double* logf_in, const double* y_in, i
   if (batch == 0 || n_out == 0) return IMPB_OK;
   DeviceGuard g(ctx->device);
   const int thr = 256;
-  const unsigned bx = (unsigned)std::min<int64_t>((n_out + thr - 1) / thr, 64);
+  const unsigned bx = (unsigned)((n_out + thr - 1) / thr);
+  const int64_t chunk = 65535 * (int64_t)LERP_ROWS;
+  for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+    const int64_t nb = std::min<int64_t>(chunk, batch - b0);
+    k_loglerp<<<dim3(bx, (unsigned)((nb + LERP_ROWS - 1) / LERP_ROWS)), thr, 0, (cudaStream_t)stream>>>(
+        logf_in, y_in + (size_t)b0 * ld_in, n_in, ld_in, logf_out, n_out, y_out + (size_t)b0 * ld_out, ld_out, nb);
+  }
+  IMPB_CUDA(cudaGetLastError());
+  return IMPB_OK;
+}
+
+int32_t impb_minphase_gain_grid(impb_ctx* ctx, const double* logf_in, const double* eq_db, int64_t n_in, int64_t ld_in,
+                                const double* logf_out, int64_t n_out, int64_t n_below, double logf_min, int32_t normalize,
+                                double* gain_out, int64_t ld_out, int64_t batch, void* row_scratch, void* stream) {
+  if (!ctx || !logf_in || !eq_db || !logf_out || !gain_out || n_in < 2 || n_out < 1 || batch < 0 || ld_in < n_in ||
+      ld_out < n_out || n_below < 0 || n_below > n_out || (normalize && !row_scratch) || batch > 65535 * (int64_t)LERP_ROWS) {
+    set_error("impb_minphase_gain_grid: bad argument");
+    return IMPB_EINVAL;
+  }
+  if (batch == 0) return IMPB_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* rowmax = normalize ? (unsigned long long*)row_scratch : nullptr;
+  if (rowmax) IMPB_CUDA(cudaMemsetAsync(rowmax, 0, sizeof(unsigned long long) * batch, st));  // key 0 < key(any double)
+  const unsigned bx = (unsigned)((n_out + 255) / 256);
+  k_gain_lerp<<<dim3(bx, (unsigned)((batch + LERP_ROWS - 1) / LERP_ROWS)), 256, 0, st>>>(
+      logf_in, eq_db, n_in, ld_in, logf_out, n_out, n_below, logf_min, gain_out, ld_out, batch, rowmax);
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = (int)std::min<int64_t>(65535, batch - b0);
-    k_loglerp<<<dim3(bx, nb), thr, 0, (cudaStream_t)stream>>>(logf_in, y_in + (size_t)b0 * ld_in, n_in, ld_in, logf_out,
-                                                            n_out, y_out + (size_t)b0 * ld_out, ld_out);
+    k_gain_shape<<<dim3(std::min(bx, 16u), nb), 256, 0, st>>>(gain_out + (size_t)b0 * ld_out, n_out, ld_out,
+                                                              rowmax ? rowmax + b0 : nullptr);
   }
   IMPB_CUDA(cudaGetLastError());
   return IMPB_OK;

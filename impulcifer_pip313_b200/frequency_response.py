@@ -152,18 +152,10 @@ def minphase_gain_grid(frequency, equalization, fs, f_res, normalize):
     if fq[0] == 0:
         fq[0] = 0.001
     eq = equalization if isinstance(equalization, torch.Tensor) else _to_dev(np.atleast_2d(equalization))
-    lf = np.log10(frequency)
-    g = ops.loglerp(lf, eq, np.log10(fq))
-    g_min = ops.loglerp(lf, eq, np.log10(np.array([f_min])))
-    below = torch.as_tensor(f <= f_min, device=g.device)
-    g = torch.where(below[None, :], g_min, g)
-    if normalize:
-        g = g - g.max(dim=1, keepdim=True).values
-        g = g - 0.5
-    g = g * 2
-    g = 10 ** (g / 20)
-    g[:, -1] = 0.0
-    return g
+    # f ascends, so "f <= f_min" is a prefix; the interpolation, the prefix fill, [normalize: - max - 0.5], * 2,
+    # 10^(./20) and the zero at Nyquist run as one pair of launches for all rows
+    n_below = int(np.count_nonzero(f <= f_min))
+    return ops.minphase_gain_grid(np.log10(frequency), eq, np.log10(fq), n_below, np.log10(f_min), normalize)
 
 
 def minimum_phase_batch(frequency, equalization, fs=DEFAULT_FS, f_res=DEFAULT_F_RES, normalize=True):

@@ -401,6 +401,27 @@ def loglerp(logf_in, y, logf_out):
     return out
 
 
+def minphase_gain_grid(logf_in, eq_db, logf_out, n_below, logf_min, normalize):
+    """Rows of equalization curves (dB, CUDA [B, F] on the log10 grid ``logf_in``) -> the linear gain grid that
+    ``minphase_fir`` takes: interpolation, the f <= f_min prefix, [normalize], * 2, 10^(./20), last point 0
+    (reference autoeq/frequency_response.py:653-676) in two launches."""
+    torch = _torch()
+    y = (eq_db if eq_db.dim() == 2 else eq_db[None, :]).contiguous()
+    dev = y.device
+    lx = torch.as_tensor(np.asarray(logf_in, np.float64), device=dev)
+    lo = torch.as_tensor(np.asarray(logf_out, np.float64), device=dev)
+    batch, n_in = y.shape
+    n = lo.numel()
+    out = torch.empty((batch, n), dtype=torch.float64, device=dev)
+    scratch = torch.empty(max(batch, 1), dtype=torch.int64, device=dev) if normalize else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().impb_minphase_gain_grid(
+            _lib.context(_dev(y)).handle, lx.data_ptr(), y.data_ptr(), n_in, n_in, lo.data_ptr(), n, int(n_below),
+            float(logf_min), 1 if normalize else 0, out.data_ptr(), n, batch,
+            scratch.data_ptr() if normalize else None, _stream(y)), "impb_minphase_gain_grid")
+    return out
+
+
 # ---- K11 ------------------------------------------------------------------------------------------
 @functools.lru_cache(maxsize=64)
 def savgol_tables(window: int, order: int = 2):

@@ -218,6 +218,15 @@ IMPB_API int32_t impb_loglerp(impb_ctx* ctx, const double* logf_in, const double
                      const double* logf_out, int64_t n_out, double* y_out, int64_t ld_out, int64_t batch,
                      void* stream);
 
+/* The gain grid of FrequencyResponse.minimum_phase_impulse_response(), autoeq/frequency_response.py:653-676, for rows of
+ * equalization curves (dB on the log10-frequency grid logf_in): k=1 interpolation onto logf_out (log10 of
+ * linspace(0, fs//2, n_out) with 0 Hz moved to 0.001), the value at logf_min for the n_below leading points (f <= f_min),
+ * [normalize: - max - 0.5 dB], * 2, 10^(./20), last point 0.  gain_out: [batch, ld_out] linear gains, the input of
+ * impb_minphase_fir.  row_scratch: batch * 8 bytes (only read when normalize != 0). */
+IMPB_API int32_t impb_minphase_gain_grid(impb_ctx* ctx, const double* logf_in, const double* eq_db, int64_t n_in, int64_t ld_in,
+                                const double* logf_out, int64_t n_out, int64_t n_below, double logf_min, int32_t normalize,
+                                double* gain_out, int64_t ld_out, int64_t batch, void* row_scratch, void* stream);
+
 /* ---- K11: fractional-octave smoothing -------------------------------------------------------------------
  * Replaces FrequencyResponse._smoothen_fractional_octave, autoeq/frequency_response.py:1060-1105:
  * `it_normal` passes of savgol_filter(y, w_normal, 2) and `it_treble` passes of savgol_filter(y, w_treble, 2)

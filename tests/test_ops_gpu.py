@@ -279,6 +279,41 @@ def test_magnitude_db_decimated(T, n, step):
     assert got0.shape == full[:, 0::step].shape and np.max(np.abs(got0 - full[:, 0::step])) < 1e-8
 
 
+@pytest.mark.parametrize("normalize", [True, False])
+@pytest.mark.parametrize("f_res", [5, 10])
+def test_minphase_gain_grid_matches_reference_arithmetic(T, normalize, f_res):
+    """The host part of minimum_phase_impulse_response (autoeq/frequency_response.py:653-676) as two launches:
+    k=1 spline on log10 f, f <= f_min prefix, [normalize], * 2, 10^(./20), zero at Nyquist."""
+    from scipy.fft import next_fast_len
+    from scipy.interpolate import InterpolatedUnivariateSpline
+    from impulcifer_pip313_b200.frequency_response import minphase_gain_grid
+    fs = 48000
+    freq = O.generate_frequencies(10, fs / 2, 1.01)
+    rng = np.random.default_rng(5 + f_res)
+    eq = np.cumsum(rng.standard_normal((37, len(freq))), axis=1) * 0.3
+    eq[3] = 0.0
+    eq[4] -= 40.0
+    got = minphase_gain_grid(freq, T.from_numpy(eq).cuda(), fs, f_res, normalize).cpu().numpy()
+    fr2 = f_res / 2
+    f_min = np.max([freq[0], fr2])
+    n = next_fast_len(round(fs // 2 / fr2))
+    f = np.linspace(0.0, fs // 2, n)
+    fq = f.copy()
+    fq[0] = 0.001
+    assert got.shape == (37, n)
+    for r in range(37):
+        sp = InterpolatedUnivariateSpline(np.log10(freq), eq[r], k=1)
+        raw = sp(np.log10(fq))
+        raw[f <= f_min] = sp(np.log10(f_min))
+        if normalize:
+            raw -= np.max(raw)
+            raw -= 0.5
+        raw *= 2
+        raw = 10 ** (raw / 20)
+        raw[-1] = 0.0
+        assert np.max(np.abs(got[r] - raw) / np.maximum(raw, 1e-300)) < 1e-12
+
+
 def test_frequency_response_chain_golden(T):
     """magnitude -> decimate -> log-f lerp onto the 783-point grid == reference frequency_response()."""
     from impulcifer_pip313_b200 import ops
