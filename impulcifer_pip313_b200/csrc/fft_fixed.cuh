@@ -59,6 +59,12 @@ template <bool ROW, int TILE, int S> __device__ __forceinline__ int fx_smem(int 
 #ifndef IMPB_TW_LOADS
 #define IMPB_TW_LOADS 1  // how many of the power-of-two entries are loaded; the rest are squared from the last one
 #endif
+// FP32 tiles are issue-bound, not load-bound (profiles/r02_k1_ncu_full_f32.md: complex multiplies are a third of the
+// issued instructions of the row pass), so they load all the power-of-two entries and compose only the rest:
+// K1 FP32 6.92 -> 6.73 ms per 1792 IRs; the same switch costs FP64 (load-bound) 2 %.
+#ifndef IMPB_TW_LOADS_F32
+#define IMPB_TW_LOADS_F32 4
+#endif
 // FULL: every w_p is its own correctly rounded table entry (tw[np][p-1] / tw[p-1][np]).  Used by the frequency-
 // response transforms: the cepstral minimum-phase chain takes logs of spectra next to their nulls and amplifies
 // each extra ulp of transform noise (min-phase tolerance), so no composed twiddles there.
@@ -70,7 +76,8 @@ __device__ __forceinline__ void fx_twiddles(const cx_t<T>* __restrict__ tw, int 
     return;
   }
   constexpr int NB = (R > 8) ? 4 : (R > 4) ? 3 : (R > 2) ? 2 : 1;
-  constexpr int NL = NB < IMPB_TW_LOADS ? NB : IMPB_TW_LOADS;
+  constexpr int WANT = sizeof(T) == 4 ? IMPB_TW_LOADS_F32 : IMPB_TW_LOADS;
+  constexpr int NL = NB < WANT ? NB : WANT;
   const cx_t<T>* twp = ROW ? tw + np : tw + np * NB;
   constexpr int TWS = ROW ? STRIDE : 1;
 #pragma unroll
