@@ -938,14 +938,24 @@ __global__ void k_homomorphic_window(double* __restrict__ w, int64_t n_fft) {
 // system with Givens rotations — agreement is to rounding (tests: <= 1e-9 dB against the reference golden).
 constexpr int EQ_MAXF = 2048;
 
+// Shared-memory layout of one curve, sized by its length (783 points: 47 KB, four curves per SM): seven double
+// arrays of P = n + 4 entries and the clip flags.
 struct EqShared {
-  double x[EQ_MAXF];    // kept sites (log10 f)
-  double y[EQ_MAXF];    // kept values, then spline coefficients
-  double eq[EQ_MAXF];   // clipped gain at every point
-  double t[EQ_MAXF + 3];
-  double cp[EQ_MAXF];   // Thomas scratch
-  int keep[EQ_MAXF];
-  int m;
+  double *x, *y;   // kept sites (log10 f) / kept values, then spline coefficients
+  double *eq;      // clipped gain at every point; after the compaction: B-spline value h0 of every collocation row
+  double *t;       // knots
+  double *cp;      // keep flags, then the modified upper diagonal of the Thomas elimination
+  double *h1, *h2;
+  int* keep;
+  int* wsum;       // per-warp counts of the ordered compaction
+  __device__ EqShared(unsigned char* raw, int n) {
+    const int P = (n + 4) & ~1;
+    double* d = reinterpret_cast<double*>(raw);
+    x = d; y = d + P; eq = d + 2 * P; t = d + 3 * P; cp = d + 4 * P; h1 = d + 5 * P; h2 = d + 6 * P;
+    keep = reinterpret_cast<int*>(d + 7 * P);
+    wsum = keep + P;
+  }
+  static size_t bytes(int n) { const size_t P = (n + 4) & ~1; return 7 * P * sizeof(double) + (P + 8) * sizeof(int); }
 };
 
 // quadratic B-spline values N_{l-2}, N_{l-1}, N_l at x inside knot interval [t_l, t_{l+1})  (de Boor recursion, fpbspl)
@@ -971,7 +981,7 @@ __global__ void __launch_bounds__(256) k_equalize(const double* __restrict__ err
                                                   const double* __restrict__ gain_k, int n, int half, int smoothen,
                                                   double* __restrict__ out, int64_t ld_out, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char eq_raw[];
-  EqShared& sh = *reinterpret_cast<EqShared*>(eq_raw);
+  const EqShared sh(eq_raw, n);
   const int b = blockIdx.x;
   const double* err = error + (size_t)b * ld_err;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -995,14 +1005,29 @@ __global__ void __launch_bounds__(256) k_equalize(const double* __restrict__ err
     sh.cp[i] = doomed ? 0.0 : 1.0;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int m = 0;
-    for (int i = 0; i < n; ++i)
-      if (sh.cp[i] != 0.0) { sh.x[m] = logf[i]; sh.y[m] = sh.eq[i]; ++m; }
-    sh.m = m;
+  // ordered compaction of the kept points, 256 at a time (ballot ranks inside a warp, warp counts through shared memory)
+  int m = 0;
+  for (int i0 = 0; i0 < n; i0 += 256) {
+    const int i = i0 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool kept = i < n && sh.cp[i] != 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, kept);
+    if (lane == 0) sh.wsum[w] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int cnt = sh.wsum[q];
+      before += q < w ? cnt : 0;
+      total += cnt;
+    }
+    if (kept) {
+      const int pos = m + before + __popc(bal & ((1u << lane) - 1u));
+      sh.x[pos] = logf[i];
+      sh.y[pos] = sh.eq[i];
+    }
+    m += total;
+    __syncthreads();
   }
-  __syncthreads();
-  const int m = sh.m;
   if (m < 3) {  // dfitpack raises for m <= k; the host turns the status into the same kind of error
     if (threadIdx.x == 0 && status) status[b] = 1;
     for (int i = threadIdx.x; i < n; i += blockDim.x) out[(size_t)b * ld_out + i] = sh.eq[i];
@@ -1016,17 +1041,25 @@ __global__ void __launch_bounds__(256) k_equalize(const double* __restrict__ err
     sh.t[j] = v;
   }
   __syncthreads();
+  // the three B-spline values of every collocation row, by all threads (eq is free after the compaction): the serial
+  // elimination below is then one multiply-add and two divisions per row instead of seven divisions
+  double* h0 = sh.eq;
+  for (int i = 1 + threadIdx.x; i <= m - 2; i += blockDim.x) {
+    double h[3];
+    bspl2(sh.t, i + 1, sh.x[i], h);
+    h0[i] = h[0]; sh.h1[i] = h[1]; sh.h2[i] = h[2];
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     // tridiagonal collocation system: row i (1 <= i <= m-2): a_i c_{i-1} + d_i c_i + u_i c_{i+1} = y_i
     double* c = sh.y;
     double* cpp = sh.cp;  // modified upper diagonal
     cpp[0] = 0.0;         // row 0: c_0 = y_0
     for (int i = 1; i <= m - 2; ++i) {
-      double h[3];
-      bspl2(sh.t, i + 1, sh.x[i], h);
-      const double den = h[1] - h[0] * cpp[i - 1];
-      cpp[i] = h[2] / den;
-      c[i] = (c[i] - h[0] * c[i - 1]) / den;
+      const double a = h0[i];
+      const double den = sh.h1[i] - a * cpp[i - 1];
+      cpp[i] = sh.h2[i] / den;
+      c[i] = (c[i] - a * c[i - 1]) / den;
     }
     // row m-1: c_{m-1} = y_{m-1}; back substitution
     for (int i = m - 2; i >= 1; --i) c[i] -= cpp[i] * c[i + 1];
@@ -1456,9 +1489,10 @@ int32_t impb_equalize(impb_ctx* ctx, const double* error, int64_t ld_err, const 
   }
   if (batch == 0) return IMPB_OK;
   DeviceGuard g(ctx->device);
-  IMPB_CUDA(cudaFuncSetAttribute(k_equalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EqShared)));
-  k_equalize<<<(unsigned)batch, 256, sizeof(EqShared), (cudaStream_t)stream>>>(error, ld_err, logf, cap, gain_k, (int)n,
-                                                                             half_window, smoothen, out, ld_out, status);
+  const size_t smem = EqShared::bytes((int)n);
+  IMPB_CUDA(cudaFuncSetAttribute(k_equalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EqShared::bytes(EQ_MAXF)));
+  k_equalize<<<(unsigned)batch, 256, smem, (cudaStream_t)stream>>>(error, ld_err, logf, cap, gain_k, (int)n, half_window,
+                                                                 smoothen, out, ld_out, status);
   IMPB_CUDA(cudaGetLastError());
   return IMPB_OK;
 }

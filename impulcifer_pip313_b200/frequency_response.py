@@ -12,6 +12,7 @@ run every (speaker, side) curve of many recordings in one launch; the methods ca
 """
 from __future__ import annotations
 
+import functools
 import math
 import warnings
 
@@ -50,11 +51,31 @@ def _to_dev(a):
 
 
 # ---- host-side scalar helpers (reference :1033-1058) ----------------------------------------------------
-def window_size(frequency, octaves) -> int:
-    steps = [frequency[i] / frequency[i - 1] for i in range(1, len(frequency))]
-    step_size = sum(steps) / len(steps)
+@functools.lru_cache(maxsize=64)
+def _frequency_grid(f_min, f_max, f_step):
+    """The geometric grid of ``generate_frequencies`` (running product, as the reference builds it), built once."""
+    freq = []
+    f = f_min
+    while f <= f_max:
+        freq.append(f)
+        f *= f_step
+    return np.array(freq)
+
+
+@functools.lru_cache(maxsize=256)
+def _window_size_cached(grid_bytes, octaves) -> int:
+    frequency = np.frombuffer(grid_bytes, dtype=np.float64)
+    # the reference adds the ratios one by one (Python sum); cumsum accumulates in the same order, unlike np.sum
+    steps = frequency[1:] / frequency[:-1]
+    step_size = float(np.cumsum(steps)[-1]) / len(steps)
     w = round(math.log(2 ** octaves) / math.log(step_size))
     return w if w % 2 else w + 1
+
+
+def window_size(frequency, octaves) -> int:
+    """Savitzky-Golay window of ``octaves`` on this grid (reference ``_window_size``, :1033-1049); the 783-iteration
+    Python loop of the reference ran twice per smoothing call, on the host, in front of a 10 us kernel."""
+    return _window_size_cached(np.ascontiguousarray(frequency, dtype=np.float64).tobytes(), float(octaves))
 
 
 def sigmoid(frequency, f_lower, f_upper, a_normal=0.0, a_treble=1.0):
@@ -227,12 +248,7 @@ class FrequencyResponse:
 
     @staticmethod
     def generate_frequencies(f_min=DEFAULT_F_MIN, f_max=DEFAULT_F_MAX, f_step=DEFAULT_STEP):
-        freq = []
-        f = f_min
-        while f <= f_max:
-            freq.append(f)
-            f *= f_step
-        return np.array(freq)
+        return _frequency_grid(f_min, f_max, f_step).copy()
 
     # ---- K10 -----------------------------------------------------------------------------------------
     def interpolate(self, f=None, f_step=DEFAULT_STEP, pol_order=1, f_min=DEFAULT_F_MIN, f_max=DEFAULT_F_MAX):

@@ -59,10 +59,20 @@ def _dev_window(win, device):
     with _win_lock:  # dispatcher threads of different GPUs share this cache
         t = _win_cache.get(key)
         if t is None:
-            if len(_win_cache) > 64:
+            if len(_win_cache) > 256:
                 _win_cache.clear()
             t = _win_cache[key] = torch.as_tensor(arr, device=device)
     return t
+
+
+def _dev_const(values, device):
+    """Host-built grid / table (frequency grids, sigmoid weights ...) -> cached device tensor.  A fresh
+    ``torch.as_tensor(..., device=...)`` per call is a pageable copy that synchronises the stream: the launches of the
+    frequency-response chain would stop queueing behind each other."""
+    torch = _torch()
+    if isinstance(values, torch.Tensor):
+        return values
+    return _dev_window(np.asarray(values, dtype=np.float64), device)
 
 
 def make_view(device, shift=None, valid_lo=None, valid_hi=None, fade_in=None, hint_max=None, hint_argmax=None,
@@ -390,8 +400,7 @@ def loglerp(logf_in, y, logf_out):
         y = y[None, :]
     y = y.contiguous()
     dev = y.device
-    lx = torch.as_tensor(np.asarray(logf_in, np.float64), device=dev) if not isinstance(logf_in, torch.Tensor) else logf_in
-    lo = torch.as_tensor(np.asarray(logf_out, np.float64), device=dev) if not isinstance(logf_out, torch.Tensor) else logf_out
+    lx, lo = _dev_const(logf_in, dev), _dev_const(logf_out, dev)
     batch, n_in = y.shape
     out = torch.empty((batch, lo.numel()), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
@@ -408,8 +417,7 @@ def minphase_gain_grid(logf_in, eq_db, logf_out, n_below, logf_min, normalize):
     torch = _torch()
     y = (eq_db if eq_db.dim() == 2 else eq_db[None, :]).contiguous()
     dev = y.device
-    lx = torch.as_tensor(np.asarray(logf_in, np.float64), device=dev)
-    lo = torch.as_tensor(np.asarray(logf_out, np.float64), device=dev)
+    lx, lo = _dev_const(logf_in, dev), _dev_const(logf_out, dev)
     batch, n_in = y.shape
     n = lo.numel()
     out = torch.empty((batch, n), dtype=torch.float64, device=dev)
@@ -465,7 +473,7 @@ def savgol_blend(y, w_normal, it_normal, w_treble, it_treble, k_treble):
         raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")
     cn, en = _savgol_dev(int(w_normal), dev)
     ct, et = _savgol_dev(int(w_treble), dev)
-    kt = k_treble if isinstance(k_treble, torch.Tensor) else torch.as_tensor(np.asarray(k_treble, np.float64), device=dev)
+    kt = _dev_const(k_treble, dev)
     out = torch.empty_like(y)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().impb_savgol_blend(_lib.context(_dev(y)).handle, y.data_ptr(), n, n, int(w_normal),
@@ -594,8 +602,7 @@ def equalize(error, logf, cap, gain_k, half_window, smoothen=True):
     error = error.contiguous()
     dev = error.device
     batch, n = error.shape
-    tabs = [t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t, np.float64), device=dev)
-            for t in (logf, cap, gain_k)]
+    tabs = [_dev_const(t, dev) for t in (logf, cap, gain_k)]
     out = torch.empty_like(error)
     status = torch.zeros(batch, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):

@@ -8,7 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from impulcifer_pip313_b200.frequency_response import FrequencyResponse, minimum_phase_batch, smoothen_batch
+from impulcifer_pip313_b200.frequency_response import (FrequencyResponse, equalize_batch, minimum_phase_batch,
+                                                       smoothen_batch)
+from impulcifer_pip313_b200.dispatcher import equalization_worker_batch
 from impulcifer_pip313_b200.impulse_response import frequency_response_batch
 from impulcifer_pip313_b200 import ops
 
@@ -42,3 +44,13 @@ for tail in (84375, 96000, 57600, 21600):
     t_mp, _ = timed(lambda: minimum_phase_batch(grid, eq, fs=fs, f_res=5, normalize=False))
     print(f"tail {tail:6d} rows {rows}: magnitude_db (all bins) {t_full:.3f} ms | frequency_response {t_fr:.3f} ms | "
           f"smoothing {t_sm:.3f} ms | minimum phase {t_mp:.3f} ms", flush=True)
+
+
+# the EQ-worker arithmetic (core/parallel_workers.py:98-131) on the last raw curves
+err = raw - raw.mean(dim=1, keepdim=True)
+t_hl, err_s = timed(lambda: smoothen_batch(grid, torch.maximum(smoothen_batch(grid, err, 1 / 6, 1, 1 / 3, 1, 100, 10000),
+                                                                smoothen_batch(grid, err, 1 / 3, 1, 1.3, 1, 1000, 6000)),
+                                           1 / 3, 1, 1 / 3, 1, 100, 10000))
+t_eq, _ = timed(lambda: equalize_batch(grid, err_s, max_gain=40, treble_f_lower=10000, treble_f_upper=fs / 2))
+t_all, _ = timed(lambda: equalization_worker_batch(grid, raw, fs, f_res=5))
+print(f"EQ worker rows {rows}: smoothen_heavy_light {t_hl:.3f} ms | equalize {t_eq:.3f} ms | whole worker {t_all:.3f} ms", flush=True)
