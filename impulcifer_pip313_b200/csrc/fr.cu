@@ -717,11 +717,15 @@ struct RealColIn2 {  // rows 2b (re) and 2b+1 (im) in, column DIF
   const double2* tw;
   int64_t N;
   int N2;
+  const int64_t* offs = nullptr;  // optional start of every row (elements from x) instead of row * ld
   __device__ __forceinline__ double2 load(int b, int t, int e, int c) const {
     const int n2 = t * TILE + c;
     const int64_t i = (int64_t)e * N2 + n2;
     if (n2 >= N2 || i >= n) return make_double2(0.0, 0.0);
-    return make_double2(x[(size_t)(2 * b) * ld + i], 2 * b + 1 < rows ? x[(size_t)(2 * b + 1) * ld + i] : 0.0);
+    const bool two = 2 * b + 1 < rows;
+    const int64_t o0 = offs ? offs[2 * b] : (int64_t)(2 * b) * ld;
+    const int64_t o1 = two ? (offs ? offs[2 * b + 1] : (int64_t)(2 * b + 1) * ld) : 0;
+    return make_double2(x[o0 + i], two ? x[o1 + i] : 0.0);
   }
   __device__ __forceinline__ void store(int b, int t, int e, int c, double2 v) const {
     const int n2 = t * TILE + c;
@@ -1195,9 +1199,10 @@ int32_t impb_magnitude_db(impb_fft* f, const double* x, int64_t ld_x, double* ma
   return IMPB_OK;
 }
 
-int32_t impb_magnitude_db_decimated(impb_fft* f, const double* x, int64_t ld_x, int64_t first, int64_t step,
-                                    double* mag_out, int64_t ld_out, int64_t batch, void* workspace, void* stream) {
-  if (!f || !x || !mag_out || !workspace || batch < 0 || ld_x < f->n || first < 0 || step < 1) {
+int32_t impb_magnitude_db_decimated(impb_fft* f, const double* x, int64_t ld_x, const int64_t* row_offsets, int64_t first,
+                                    int64_t step, double* mag_out, int64_t ld_out, int64_t batch, void* workspace,
+                                    void* stream) {
+  if (!f || !x || !mag_out || !workspace || batch < 0 || (!row_offsets && ld_x < f->n) || first < 0 || step < 1) {
     set_error("impb_magnitude_db_decimated: bad argument");
     return IMPB_EINVAL;
   }
@@ -1217,7 +1222,9 @@ int32_t impb_magnitude_db_decimated(impb_fft* f, const double* x, int64_t ld_x, 
   for (int64_t b0 = 0; b0 < batch; b0 += 65534) {  // an even number of rows per launch: pairs never straddle
     const int nr = (int)std::min<int64_t>(65534, batch - b0), np = (nr + 1) / 2;
     double2* w = ws + (size_t)(b0 / 2) * p.N;
-    int rc = f->f.col_fwd<TILE>(RealColIn2{x + (size_t)b0 * ld_x, ld_x, f->n, nr, w, f->f.tw, p.N, p.N2}, np, st);
+    const RealColIn2 ci{row_offsets ? x : x + (size_t)b0 * ld_x, ld_x, f->n, nr, w, f->f.tw, p.N, p.N2,
+                        row_offsets ? row_offsets + b0 : nullptr};
+    int rc = f->f.col_fwd<TILE>(ci, np, st);
     if (!rc) rc = f->f.row_fwd<TILE>(RowPlain<double, TILE>{w, w, nullptr, p.N, p.N1, p.N2, 0, 0}, np, st);
     if (rc) return rc;
     k_pair_mag_db<<<dim3((unsigned)((n_out + 255) / 256), np), 256, 0, st>>>(w, mir, nr, first, step, n_out,

@@ -427,8 +427,15 @@ class BatchDispatcher:
         for i, r in enumerate(results):
             by_tail.setdefault(r.tail_ind, []).append(i)
         for tail, idxs in by_tail.items():
-            data = torch.cat([results[i].data for i in idxs]) if len(idxs) > 1 else results[idxs[0]].data
-            raw = frequency_response_batch(data, self.fs)
+            flat = results[idxs[0]]._flat
+            if flat is not None and all(results[i]._flat is flat for i in idxs):
+                # the sets of one process() call are slices of one flat buffer: hand K8 the row offsets, no gather copy
+                n_rows = len(results[idxs[0]].names)
+                offs = np.concatenate([results[i]._off + np.arange(n_rows, dtype=np.int64) * tail for i in idxs])
+                raw = frequency_response_batch(flat, self.fs, row_offsets=ops._dev_index_const(offs, flat.device), n=tail)
+            else:
+                data = torch.cat([results[i].data for i in idxs]) if len(idxs) > 1 else results[idxs[0]].data
+                raw = frequency_response_batch(data, self.fs)
             if worker:  # the whole EQ-worker arithmetic, equalize() included (core/parallel_workers.py:98-131)
                 sm, _eq, fir = equalization_worker_batch(grid, raw, self.fs, f_res=f_res)
             else:

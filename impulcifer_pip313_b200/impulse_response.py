@@ -246,9 +246,11 @@ def decay_times_batch(irs, params=None):
     return [tuple(None if np.isnan(v) else float(v) for v in row) for row in out]
 
 
-def frequency_response_batch(irs, fs):
-    """rows of equal-length IRs (CUDA [B, n]) -> raw dB on the 1.01-step grid 10 Hz..fs/2 (CUDA [B, F])."""
-    n = irs.shape[1]
+def frequency_response_batch(irs, fs, row_offsets=None, n=None):
+    """rows of equal-length IRs (CUDA [B, n]) -> raw dB on the 1.01-step grid 10 Hz..fs/2 (CUDA [B, F]).
+    With ``row_offsets`` (int64 CUDA tensor) and ``n`` the rows are slices ``irs.reshape(-1)[o : o + n]`` of one flat
+    buffer (the dispatcher's cropped responses): no gather copy in front of the transform."""
+    n = irs.shape[1] if row_offsets is None else int(n)
     half = int(np.ceil(n / 2))
     f = np.arange(half) * (fs / n)
     pts = (fs / 2) / 4.0
@@ -256,7 +258,12 @@ def frequency_response_batch(irs, fs):
     fd = f[1::step]
     if len(fd) == 0:
         fd, step = f[1:], 1
-    # step > 1 (any response longer than fs/4 samples): only the kept bins are produced, two rows per transform
-    md = ops.magnitude_db_decimated(irs, 1, step) if step > 1 else ops.magnitude_db(irs)[:, 1:].contiguous()
+    if step > 1:  # any response longer than fs/4 samples: only the kept bins are produced, two rows per transform
+        md = ops.magnitude_db_decimated(irs, 1, step, row_offsets, n)
+    else:
+        if row_offsets is not None:
+            import torch
+            irs = torch.stack([irs.reshape(-1).narrow(0, int(o), n) for o in row_offsets.tolist()])
+        md = ops.magnitude_db(irs)[:, 1:].contiguous()
     grid = FrequencyResponse.generate_frequencies(f_step=1.01, f_min=10, f_max=fs / 2)
     return ops.loglerp(np.log10(fd), md, np.log10(grid))

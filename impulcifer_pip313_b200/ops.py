@@ -75,6 +75,20 @@ def _dev_const(values, device):
     return _dev_window(np.asarray(values, dtype=np.float64), device)
 
 
+def _dev_index_const(values, device):
+    """int64 twin of ``_dev_const`` (row offsets of a batch geometry that repeats from step to step)."""
+    torch = _torch()
+    arr = np.ascontiguousarray(values, dtype=np.int64)
+    key = (arr.tobytes(), 'i8', str(device))
+    with _win_lock:
+        t = _win_cache.get(key)
+        if t is None:
+            if len(_win_cache) > 256:
+                _win_cache.clear()
+            t = _win_cache[key] = torch.as_tensor(arr, device=device)
+    return t
+
+
 def make_view(device, shift=None, valid_lo=None, valid_hi=None, fade_in=None, hint_max=None, hint_argmax=None,
               blocks=None):
     """(ctypes impb_view or None, keep-alive tensors).  See include/impb.h.  ``hint_max`` / ``hint_argmax``: float64 /
@@ -349,15 +363,21 @@ def magnitude_db(x):
     return out
 
 
-def magnitude_db_decimated(x, first, step):
+def magnitude_db_decimated(x, first, step, row_offsets=None, n=None):
     """``magnitude_db(x)[:, first::step]`` without the bins in between: rows ride in pairs through one complex
     transform and only the kept bins are read back (the decimation of ``ImpulseResponse.frequency_response``,
-    reference core/impulse_response.py:170-178).  Lengths that need the chirp-z plan take the full transform."""
+    reference core/impulse_response.py:170-178).  Lengths that need the chirp-z plan take the full transform.
+    ``row_offsets`` (int64 CUDA tensor) + ``n``: the rows are ``x.reshape(-1)[o : o + n]`` for every offset ``o``
+    (slices of one flat buffer, no gather copy)."""
     torch = _torch()
-    if x.dim() == 1:
-        x = x[None, :]
-    x = x.contiguous()
-    batch, n = x.shape
+    if row_offsets is None:
+        if x.dim() == 1:
+            x = x[None, :]
+        x = x.contiguous()
+        batch, n = x.shape
+    else:
+        x = x.reshape(-1)
+        batch, n = int(row_offsets.numel()), int(n)
     first, step = int(first), int(step)
     half = (n + 1) // 2
     n_out = max(0, -(-(half - first) // step))
@@ -367,9 +387,12 @@ def magnitude_db_decimated(x, first, step):
         return out
     with torch.cuda.device(x.device):
         ws = plan.workspace(batch)
-        rc = _lib.lib().impb_magnitude_db_decimated(plan.handle, x.data_ptr(), n, first, step, out.data_ptr(), n_out,
-                                                    batch, ws.data_ptr(), _stream(x))
+        rc = _lib.lib().impb_magnitude_db_decimated(plan.handle, x.data_ptr(), n,
+                                                    None if row_offsets is None else row_offsets.data_ptr(), first, step,
+                                                    out.data_ptr(), n_out, batch, ws.data_ptr(), _stream(x))
     if rc == -4:  # IMPB_EUNSUPPORTED: chirp-z plan
+        if row_offsets is not None:
+            x = torch.stack([x.narrow(0, int(o), n) for o in row_offsets.tolist()])
         return magnitude_db(x)[:, first::step].contiguous()
     _lib.check(rc, "impb_magnitude_db_decimated")
     return out

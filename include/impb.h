@@ -201,9 +201,12 @@ IMPB_API int64_t impb_fft_workspace_bytes(const impb_fft* fft, int64_t batch);
 /* The same bins after the decimation of ImpulseResponse.frequency_response(), core/impulse_response.py:170-178
  * (`f[1::step]`, `m[1::step]`): mag_out[b][j] = 20*log10(|rfft(x_b)[first + step*j]|) for first + step*j < ceil(n/2).
  * Two rows ride one complex transform and only the kept bins are read back; workspace as for impb_magnitude_db.
+ * row_offsets (nullable, device, [batch]): start of every row in elements from x, for rows that are slices of one
+ * buffer (the cropped responses of many recording sets); ld_x is ignored then.
  * IMPB_EUNSUPPORTED for chirp-z plans (lengths with large prime factors): use impb_magnitude_db and slice. */
-IMPB_API int32_t impb_magnitude_db_decimated(impb_fft* fft, const double* x, int64_t ld_x, int64_t first, int64_t step,
-                                    double* mag_out, int64_t ld_out, int64_t batch, void* workspace, void* stream);
+IMPB_API int32_t impb_magnitude_db_decimated(impb_fft* fft, const double* x, int64_t ld_x, const int64_t* row_offsets,
+                                    int64_t first, int64_t step, double* mag_out, int64_t ld_out, int64_t batch,
+                                    void* workspace, void* stream);
 /* Linear twin used by the interaural microphone-mismatch estimator (next row): replaces
  * np.abs(scipy.fft.rfft(seg, n=nfft)) in MicrophoneMatchingCorrector._windowed_power,
  * core/microphone_deviation_correction.py:130-133.  Rows hold n_valid <= n samples (zero-padded to the

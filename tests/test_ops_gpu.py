@@ -277,6 +277,12 @@ def test_magnitude_db_decimated(T, n, step):
     full = ops.magnitude_db(T.from_numpy(x).cuda()).cpu().numpy()
     got0 = ops.magnitude_db_decimated(T.from_numpy(x).cuda(), 0, step).cpu().numpy()
     assert got0.shape == full[:, 0::step].shape and np.max(np.abs(got0 - full[:, 0::step])) < 1e-8
+    # rows as slices of one flat buffer (the dispatcher's cropped responses): same bits as the matrix form
+    flat = np.concatenate([np.zeros(3), x[2], np.zeros(5), x[0], x[4], np.zeros(1)])
+    offs = np.array([3 + n + 5, 3, 3 + n + 5 + n], dtype=np.int64)
+    sl = ops.magnitude_db_decimated(T.from_numpy(flat).cuda(), 1, step, T.from_numpy(offs).cuda(), n).cpu().numpy()
+    mat = ops.magnitude_db_decimated(T.from_numpy(x[[0, 2, 4]]).cuda(), 1, step).cpu().numpy()
+    assert np.array_equal(sl, mat)
 
 
 @pytest.mark.parametrize("normalize", [True, False])
