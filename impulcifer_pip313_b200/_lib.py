@@ -48,6 +48,7 @@ SIGNATURES = {
     "impb_fft_workspace_bytes": (c_i64, [c_vp, c_i64]),
     "impb_magnitude_db": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "impb_magnitude_db_decimated": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "impb_magnitude_db_folded": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "impb_decay_times_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "impb_decay_times": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "impb_segment_energy": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp]),

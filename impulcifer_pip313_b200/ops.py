@@ -364,9 +364,10 @@ def magnitude_db(x):
 
 
 def magnitude_db_decimated(x, first, step, row_offsets=None, n=None):
-    """``magnitude_db(x)[:, first::step]`` without the bins in between: rows ride in pairs through one complex
-    transform and only the kept bins are read back (the decimation of ``ImpulseResponse.frequency_response``,
-    reference core/impulse_response.py:170-178).  Lengths that need the chirp-z plan take the full transform.
+    """``magnitude_db(x)[:, first::step]`` without the bins in between (the decimation of
+    ``ImpulseResponse.frequency_response``, reference core/impulse_response.py:170-178).  When ``step`` divides the row
+    length the kept bins are one (n / step)-point transform of the folded row; otherwise rows ride in pairs through one
+    complex transform and only the kept bins are read back.  Lengths that need the chirp-z plan take the full transform.
     ``row_offsets`` (int64 CUDA tensor) + ``n``: the rows are ``x.reshape(-1)[o : o + n]`` for every offset ``o``
     (slices of one flat buffer, no gather copy)."""
     torch = _torch()
@@ -381,14 +382,24 @@ def magnitude_db_decimated(x, first, step, row_offsets=None, n=None):
     first, step = int(first), int(step)
     half = (n + 1) // 2
     n_out = max(0, -(-(half - first) // step))
-    plan = fft_plan(n, _dev(x))
     out = torch.empty((batch, n_out), dtype=torch.float64, device=x.device)
     if n_out == 0 or batch == 0:
         return out
+    offs_ptr = None if row_offsets is None else row_offsets.data_ptr()
+    if 2 <= step <= 64 and first < step and n % step == 0 and n // step >= 4:
+        # step divides the row: the kept bins are the (n / step)-point DFT of the folded, modulated row
+        small = fft_plan(n // step, _dev(x))
+        with torch.cuda.device(x.device):
+            ws = small.workspace(batch)
+            rc = _lib.lib().impb_magnitude_db_folded(small.handle, x.data_ptr(), n, offs_ptr, first, step,
+                                                     out.data_ptr(), n_out, batch, ws.data_ptr(), _stream(x))
+        if rc != -4:  # IMPB_EUNSUPPORTED: no specialised plan for n / step -> the paired transform of the full row
+            _lib.check(rc, "impb_magnitude_db_folded")
+            return out
+    plan = fft_plan(n, _dev(x))
     with torch.cuda.device(x.device):
         ws = plan.workspace(batch)
-        rc = _lib.lib().impb_magnitude_db_decimated(plan.handle, x.data_ptr(), n,
-                                                    None if row_offsets is None else row_offsets.data_ptr(), first, step,
+        rc = _lib.lib().impb_magnitude_db_decimated(plan.handle, x.data_ptr(), n, offs_ptr, first, step,
                                                     out.data_ptr(), n_out, batch, ws.data_ptr(), _stream(x))
     if rc == -4:  # IMPB_EUNSUPPORTED: chirp-z plan
         if row_offsets is not None:

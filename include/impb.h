@@ -207,6 +207,14 @@ IMPB_API int64_t impb_fft_workspace_bytes(const impb_fft* fft, int64_t batch);
 IMPB_API int32_t impb_magnitude_db_decimated(impb_fft* fft, const double* x, int64_t ld_x, const int64_t* row_offsets,
                                     int64_t first, int64_t step, double* mag_out, int64_t ld_out, int64_t batch,
                                     void* workspace, void* stream);
+/* The same kept bins when `step` divides the row length: bins first + step*j of an (M*step)-point DFT are the M-point DFT
+ * of the folded, modulated row y[m] = W^(first*m) * sum_r x[m + M*r] * exp(-2*pi*i*first*r/step), so the transform is
+ * `step` times smaller.  `fft` is a plan of length M = n / step (impb_fft_create(ctx, M, ...)); rows hold M*step samples;
+ * first < step <= 64; workspace: impb_fft_workspace_bytes(fft, batch).  IMPB_EUNSUPPORTED if M needs a chirp-z plan or
+ * sub-FFT lengths outside the specialised menu (the paired transform of the full row is faster then). */
+IMPB_API int32_t impb_magnitude_db_folded(impb_fft* fft, const double* x, int64_t ld_x, const int64_t* row_offsets,
+                                 int64_t first, int64_t step, double* mag_out, int64_t ld_out, int64_t batch,
+                                 void* workspace, void* stream);
 /* Linear twin used by the interaural microphone-mismatch estimator (next row): replaces
  * np.abs(scipy.fft.rfft(seg, n=nfft)) in MicrophoneMatchingCorrector._windowed_power,
  * core/microphone_deviation_correction.py:130-133.  Rows hold n_valid <= n samples (zero-padded to the

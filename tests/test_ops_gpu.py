@@ -258,10 +258,13 @@ def test_magnitude_db_lengths_with_large_prime_factors(T, n):
         assert np.array_equal(fr.frequency, f_o) and np.max(np.abs(fr.raw - raw_o)) < 1e-7
 
 
-@pytest.mark.parametrize("n,step", [(21600, 2), (57600, 5), (84375, 7), (96000, 8), (1000, 3), (1009, 4)])
+@pytest.mark.parametrize("n,step", [(21600, 2), (57600, 5), (84375, 7), (96000, 8), (90000, 8), (1000, 3), (1009, 4),
+                                    (2 * 7 * 11 * 13, 2)])
 def test_magnitude_db_decimated(T, n, step):
-    """The kept bins of frequency_response() (`m[1::step]`, core/impulse_response.py:170-178) from the paired
-    transform: odd row counts, rows 30 dB apart, and a chirp-z length (1009) that takes the full transform."""
+    """The kept bins of frequency_response() (`m[1::step]`, core/impulse_response.py:170-178): the folded transform
+    when step divides n (21 600 / 2, 57 600 / 5, 96 000 / 8, 90 000 / 8), the paired transform otherwise (84 375 / 7,
+    1000 / 3, and 2002 / 2 whose folded length 1001 is not 5-smooth), the full chirp-z transform for 1009; odd row
+    counts and rows 30 dB apart."""
     from impulcifer_pip313_b200 import ops
     rng = np.random.default_rng(n + step)
     x = rng.standard_normal((5, n)) * np.exp(-np.arange(n) / (n / 8.0))
