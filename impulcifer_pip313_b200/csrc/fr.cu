@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -30,9 +31,9 @@ struct impb_fft {
   int64_t M = 0;
   double2* w = nullptr;   // [n]  exp(+i pi m^2 / n)
   double2* Hs = nullptr;  // [M]  spectrum of the circularly extended chirp, in position order
-  // folded transforms (impb_magnitude_db_folded): tables of the last (first, step) served by this plan
-  int64_t fold_first = -1, fold_step = 0;
-  double2* fold_w = nullptr;  // [n] exp(-2 pi i first m / (n step)) then [step] exp(-2 pi i first r / step)
+  // folded transforms (impb_magnitude_db_folded): per (first, step) served by this plan,
+  // [n] exp(-2 pi i first m / (n step)) followed by [step] exp(-2 pi i first r / step); built once, freed with the plan
+  std::map<std::pair<int64_t, int64_t>, double2*> fold_w;
   std::mutex fold_mu;
 };
 
@@ -1192,7 +1193,7 @@ void impb_fft_destroy(impb_fft* f) {
   f->f.release();
   cudaFree(f->w);
   cudaFree(f->Hs);
-  cudaFree(f->fold_w);
+  for (auto& kv : f->fold_w) cudaFree(kv.second);
   delete f;
 }
 
@@ -1298,9 +1299,11 @@ int32_t impb_magnitude_db_folded(impb_fft* f, const double* x, int64_t ld_x, con
   if (batch == 0 || n_out == 0) return IMPB_OK;
   DeviceGuard g(f->ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
+  double2* fold_w = nullptr;
   {
     std::lock_guard<std::mutex> lk(f->fold_mu);
-    if (f->fold_first != first || f->fold_step != step) {
+    auto it = f->fold_w.find({first, step});
+    if (it == f->fold_w.end()) {
       std::vector<double2> w((size_t)(M + step));
       const long double tau = -2.0L * 3.141592653589793238462643383279502884L;
       for (int64_t m = 0; m < M; ++m) {  // first * m < step * M = n_full: the angle stays inside one turn
@@ -1311,18 +1314,13 @@ int32_t impb_magnitude_db_folded(impb_fft* f, const double* x, int64_t ld_x, con
         const long double a = tau * (long double)((first * r) % step) / (long double)step;
         w[(size_t)(M + r)] = make_double2((double)cosl(a), (double)sinl(a));
       }
-      if (!f->fold_w || f->fold_step != step) {
-        IMPB_CUDA(cudaStreamSynchronize(st));  // launches still reading the old tables
-        cudaFree(f->fold_w);
-        f->fold_w = nullptr;
-        IMPB_CUDA(cudaMalloc(&f->fold_w, sizeof(double2) * (size_t)(M + step)));
-      } else {
-        IMPB_CUDA(cudaStreamSynchronize(st));
-      }
-      IMPB_CUDA(cudaMemcpy(f->fold_w, w.data(), sizeof(double2) * (size_t)(M + step), cudaMemcpyHostToDevice));
-      f->fold_first = first;
-      f->fold_step = step;
+      double2* d = nullptr;
+      IMPB_CUDA(cudaMalloc(&d, sizeof(double2) * (size_t)(M + step)));
+      cudaError_t e = cudaMemcpy(d, w.data(), sizeof(double2) * (size_t)(M + step), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "fold tables"); }
+      it = f->fold_w.emplace(std::make_pair(first, step), d).first;
     }
+    fold_w = it->second;
   }
   const Plan2D& p = f->f.p;
   double2* ws = (double2*)workspace;
@@ -1330,7 +1328,7 @@ int32_t impb_magnitude_db_folded(impb_fft* f, const double* x, int64_t ld_x, con
     const int nb = (int)std::min<int64_t>(32768, batch - b0);
     double2* w = ws + (size_t)b0 * p.N;
     const FoldColIn ci{row_offsets ? x : x + (size_t)b0 * ld_x, ld_x, row_offsets ? row_offsets + b0 : nullptr, M, (int)step,
-                       f->fold_w, f->fold_w + M, w, f->f.tw, p.N, p.N2};
+                       fold_w, fold_w + M, w, f->f.tw, p.N, p.N2};
     int rc = f->f.col_fwd<TILE>(ci, nb, st);
     if (rc) return rc;
     RowFwdOp<MagDbOp> ro{w, p.N, p.N1, p.N2, f->f.perm_col, f->f.perm_row,
