@@ -16,6 +16,7 @@ needs ONE host synchronisation: reading the knee indices that fix each set's out
 """
 from __future__ import annotations
 
+import os
 import threading
 import time
 import warnings
@@ -119,6 +120,7 @@ class BatchDispatcher:
         self._layout = None
         self.launches = 0
         self.phase_timing = False   # developer hook: record device time per phase of process() into phase_ms
+        self._read_state = {}       # device index -> (side stream, pinned int64 buffer) of the step's host read
         self.phase_ms = []
 
     # ---- static layout of one set ---------------------------------------------------------------------
@@ -291,12 +293,17 @@ class BatchDispatcher:
             tail_bound = min(int(L), next_fast_len(int(2 * fs) + 8192))
             tails_d, set_off_d, out_len_d, dst_off_d, flags_d = ops.set_tails(ld, knee, n1, S, head, len(window_out),
                                                                               tail_bound, L)
+            # ---- the ONE host read of the step: integers the results report.  They are final before the gather is
+            # launched, so they travel on a side stream while the gather (the step's last and longest crop kernel) runs:
+            # the host's bookkeeping and the caller's next launches no longer wait for it.
+            ints_d = torch.cat([knee, n1, peaks, crop, tails_d, set_off_d, flags_d])
+            ready = torch.cuda.Event()
+            ready.record()
             flat = ops.gather_rows(flatE, off1, out_len_d, dst_off_d, S * n * tail_bound, tail_bound, shift=shift,
                                    valid_lo=lo, valid_hi=hi, fade_in=window_in, fade_out=window_out)
             launches += 2
             mark('tail gather launch')
-            # ---- the ONE host read of the step, after its last launch: integers the results report -----------------
-            ints = torch.cat([knee, n1, peaks, crop, tails_d, set_off_d, flags_d]).cpu().numpy()
+            ints = self._read_ints(ints_d, ready)
             mark('host sync')
             B4 = 4 * B
             knees_h, n1_h, peaks_h, crop_h = (ints[i * B:(i + 1) * B].reshape(S, n) for i in range(4))
@@ -332,6 +339,26 @@ class BatchDispatcher:
             self.phase_host_ms = [(b[0], (b[2] - a[2]) * 1e3) for a, b in zip(marks[:-1], marks[1:])]
         self.launches = launches
         return results
+
+    def _read_ints(self, ints_d, ready):
+        """Device int64 vector -> numpy, through a pinned buffer on a side stream that only waits for ``ready`` (not for
+        what the calling stream was given afterwards)."""
+        import torch
+        if os.environ.get("IMPULCIFER_B200_SYNC_READ"):  # A/B: the read waits for everything launched so far
+            return ints_d.cpu().numpy()
+        dev = ints_d.device
+        st = self._read_state.get(dev.index)
+        if st is None or st[1].numel() < ints_d.numel():
+            st = self._read_state[dev.index] = (st[0] if st else torch.cuda.Stream(dev),
+                                                torch.empty(max(ints_d.numel(), 1 << 14), dtype=torch.int64).pin_memory())
+        side, pinned = st
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            host = pinned[:ints_d.numel()]
+            host.copy_(ints_d, non_blocking=True)
+        ints_d.record_stream(side)
+        side.synchronize()
+        return host.numpy().copy()
 
     # ---- host buffers in, host buffers out ------------------------------------------------------------------
     def process_host(self, recordings, out=None, chunk_sets=None, precision=None, out_sets=None):
