@@ -260,7 +260,10 @@ int run_peak_index(impb_ctx* ctx, const double* x, const ViewArgs& va, double he
 // ------------------------------------------------------------------------------------------------
 // Lundeby: one CTA per impulse response
 // ------------------------------------------------------------------------------------------------
-constexpr int LB_THREADS = 512;
+#ifndef IMPB_LB_THREADS
+#define IMPB_LB_THREADS 256  // two CTAs per SM at 512 threads (registers): 256 keeps three responses per SM in flight (-6 %)
+#endif
+constexpr int LB_THREADS = IMPB_LB_THREADS;
 constexpr int LB_MAXWIN = 4096;  // >= the 4000-window upper bound of the refined pass (proof at its use)
 
 constexpr int LB_MAXBLK = 3072;  // partial sums of the squared window: blocks of bs = 32, 64, ... samples
@@ -677,16 +680,20 @@ __global__ void __launch_bounds__(256) k_xcorr(const double* __restrict__ x, con
   extern __shared__ double smx[];
   const int r = blockIdx.x;
   const int na = (int)a_len[r], nb = (int)b_len[r];
+  // Sample i lives at slot i + i/8: consecutive threads own lags XR = 8 apart, so at every step their a / b indices are
+  // 8 apart too -- unskewed that is a 64-byte stride, a 16-way bank conflict on every load (ncu: LSU wavefronts 82 % of
+  // peak, FP64 pipe 26 %); with the skew the stride is 9 doubles and a warp's load touches every bank once.
+  auto slot = [](int i) { return i + (i >> 3); };
   double* a = smx;
-  double* b = smx + na;
+  double* b = smx + slot(na) + 1;
   // segments start at the head of a cropped response: the fade-in of crop_heads applies to their first samples
   for (int i = threadIdx.x; i < na; i += blockDim.x) {
     double v = x[a_off[r] + i];
-    a[i] = (fade && i < fade_len) ? __dmul_rn(v, fade[i]) : v;
+    a[slot(i)] = (fade && i < fade_len) ? __dmul_rn(v, fade[i]) : v;
   }
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
     double v = x[b_off[r] + i];
-    b[i] = (fade && i < fade_len) ? __dmul_rn(v, fade[i]) : v;
+    b[slot(i)] = (fade && i < fade_len) ? __dmul_rn(v, fade[i]) : v;
   }
   __syncthreads();
   // z[k] = sum_l a[l] * b[l - k + nb - 1],  k in [0, na + nb - 1).  Every thread owns XR consecutive lags and slides a
@@ -697,7 +704,7 @@ __global__ void __launch_bounds__(256) k_xcorr(const double* __restrict__ x, con
   double best = -DBL_MAX;
   int best_k = 0x7fffffff;
   const int nk = na + nb - 1;
-  auto b_at = [&](int i) -> double { return (i >= 0 && i < nb) ? b[i] : 0.0; };
+  auto b_at = [&](int i) -> double { return (i >= 0 && i < nb) ? b[slot(i)] : 0.0; };
   for (int k0 = threadIdx.x * XR; k0 < nk; k0 += blockDim.x * XR) {
     const int shift0 = k0 - (nb - 1);  // lag k0 + r pairs a[l] with b[l - shift0 - r]
     const int lo = max(0, shift0), hi = min(na, nb + shift0 + XR - 1);
@@ -709,7 +716,7 @@ __global__ void __launch_bounds__(256) k_xcorr(const double* __restrict__ x, con
 #pragma unroll
       for (int u = 0; u < XR; ++u) {
         // at step l + u the window slot of lag r is w[(r - u) mod XR]
-        const double av = a[l + u];
+        const double av = a[slot(l + u)];
 #pragma unroll
         for (int r = 0; r < XR; ++r) acc[r] = fma(av, w[(r - u + XR) % XR], acc[r]);
         // slot (XR - 1 - u + XR) % XR ... the oldest value (lag XR-1) is replaced by the next b for lag 0
@@ -717,7 +724,7 @@ __global__ void __launch_bounds__(256) k_xcorr(const double* __restrict__ x, con
       }
     }
     for (; l < hi; ++l) {  // tail: plain rotation
-      const double av = a[l];
+      const double av = a[slot(l)];
 #pragma unroll
       for (int r = 0; r < XR; ++r) acc[r] = fma(av, w[r], acc[r]);
 #pragma unroll
@@ -874,7 +881,7 @@ int32_t impb_xcorr_lag(impb_ctx* ctx, const double* x, const int64_t* a_offsets,
     return IMPB_EINVAL;
   }
   if (batch == 0) return IMPB_OK;
-  const size_t smem = 2 * (size_t)max_seg_len * sizeof(double);
+  const size_t smem = 2 * ((size_t)max_seg_len + (size_t)max_seg_len / 8 + 2) * sizeof(double);  // skewed slots
   if (smem > ctx->smem_optin) {
     set_error("impb_xcorr_lag: segments of %lld samples do not fit shared memory", (long long)max_seg_len);
     return IMPB_EUNSUPPORTED;
