@@ -854,9 +854,13 @@ int32_t impb_lundeby(impb_ctx* ctx, const double* x, const int64_t* offsets, con
     double* blk = nullptr;
     if (e == cudaSuccess) e = cudaMallocAsync(&segmax, sizeof(unsigned long long) * rows_per, st);
     if (e == cudaSuccess) e = cudaMallocAsync(&blk, sizeof(double) * LB_MAXBLK * rows_per, st);
-    const unsigned chunks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((2 * (int64_t)fs + 4095) / 4096, 256));
+    // CTAs per row of the two streaming passes: 4096 samples each when few rows must fill the GPU (one recording set),
+    // 16 384 when the rows alone do (a CTA of 4096 samples lives ~5 us, a third of it prologue: 43 008 CTAs per step)
+    const int64_t fine = std::max<int64_t>(1, std::min<int64_t>((2 * (int64_t)fs + 4095) / 4096, 256));
+    const int64_t coarse = std::max<int64_t>(1, (2 * (int64_t)fs + 16383) / 16384);
     for (int64_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += rows_per) {
       const int64_t nb = std::min<int64_t>(rows_per, batch - b0);
+      const unsigned chunks = (unsigned)std::min<int64_t>(fine, std::max<int64_t>(coarse, (1184 + nb - 1) / nb));
       e = cudaMemsetAsync(segmax, 0, sizeof(unsigned long long) * nb, st);
       k_lb_segmax<<<dim3((unsigned)nb, chunks), 256, 0, st>>>(x, va, b0, fs, peaks + b0, segmax);
       k_lb_blocksums<<<dim3((unsigned)nb, chunks), 256, 0, st>>>(x, va, b0, fs, peaks + b0, segmax, blk);
