@@ -15,6 +15,13 @@
 //   BC row pass   : ws row -> DIF over n2 -> x H (inverse-sweep spectrum, pre-permuted, pre-scaled)
 //                   -> DIT over k2 -> x conj(W_N^(n2 k1)) -> ws           (in place)
 //   D  column pass: ws -> DIT over k1 -> write the wanted slice of re / im to the two output rows
+// Trips of a radix stage unrolled in pairs in the K1 kernels (fft_fixed.cuh: kTripUnroll): the loads of the second trip are
+// issued under the butterflies of the first.  FP64 A / BC / D 3.51 / 4.29 / 2.65 -> 3.36 / 4.24 / 2.63 ms per 1792 IRs
+// (BC spills 40 bytes and still gains), FP32 6.76 -> 6.45 ms; unrolling all three trips costs 40 % (registers).
+// The frequency-response transforms (fr.cu) keep the rolled loops.
+#ifndef IMPB_TRIP_UNROLL
+#define IMPB_TRIP_UNROLL 2
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 
