@@ -17,6 +17,10 @@
 namespace impb {
 
 constexpr int kTripUnroll = IMPB_TRIP_UNROLL;
+#ifndef IMPB_STAGE_UNROLL
+#define IMPB_STAGE_UNROLL 4  // copies of the cp.async staging loop of pass A issued back to back
+#endif
+constexpr int kStageUnroll = IMPB_STAGE_UNROLL;
 #ifndef IMPB_PREFETCH
 #define IMPB_PREFETCH 0
 #endif
@@ -321,7 +325,7 @@ k_fx_fwd_async(const cx_t<T>* __restrict__ tw0, const cx_t<T>* __restrict__ tw1,
     const T* col = f.src_column(b, t, c, which, &e_lim, &e_pitch);
     const T* src = col + (int64_t)e0 * e_pitch;
     const int64_t step = (int64_t)ESTEP * e_pitch;
-#pragma unroll 4
+#pragma unroll kStageUnroll
     for (int e = e0; e < RX::S; e += ESTEP, src += step) {
       T* dst = reinterpret_cast<T*>(&tile[fx_smem<false, TILE, RX::S>(e, c)]) + which;
       if (e < e_lim) cp_async_n<sizeof(T)>(dst, src); else *dst = (T)0;
