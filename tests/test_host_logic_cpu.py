@@ -67,6 +67,33 @@ def test_window_arithmetic_and_tables():
         assert np.allclose(c, O.savgol_coeffs(w), atol=1e-15) and np.allclose(e, O.savgol_edge_matrix(w), atol=1e-13)
 
 
+def test_window_size_is_the_reference_loop_and_grids_are_fresh_copies():
+    """window_size is vectorised and cached: it must still be the reference's loop (ratios added one by one,
+    autoeq/frequency_response.py:1033-1049) on any grid, and a caller that edits a generated grid must not poison the
+    cache behind generate_frequencies."""
+    import math
+    from impulcifer_pip313_b200 import frequency_response as FR
+
+    def loop(frequency, octaves):
+        steps = [frequency[i] / frequency[i - 1] for i in range(1, len(frequency))]
+        step_size = sum(steps) / len(steps)
+        w = round(math.log(2 ** octaves) / math.log(step_size))
+        return w if w % 2 else w + 1
+
+    rng = np.random.default_rng(3)
+    grids = [FR.FrequencyResponse.generate_frequencies(f_min=10, f_max=fm, f_step=st)
+             for fm in (22050, 24000, 96000) for st in (1.01, 1.007, 1.03)]
+    grids.append(np.sort(rng.uniform(10, 20000, 400)))
+    for f in grids:
+        for octv in (1 / 3, 1 / 6, 1 / 12, 1.3, 2):
+            assert FR.window_size(f, octv) == loop(f, octv)
+            assert FR.window_size(list(f), octv) == loop(f, octv)
+    a = FR.FrequencyResponse.generate_frequencies(f_min=10, f_max=24000, f_step=1.01)
+    a[:] = 0.0
+    b = FR.FrequencyResponse.generate_frequencies(f_min=10, f_max=24000, f_step=1.01)
+    assert b[0] == 10 and np.array_equal(b, O.generate_frequencies(10, 24000, 1.01))
+
+
 def test_resample_taps_match_port():
     from impulcifer_pip313_b200.impulse_response import resample_taps
     for new, old in ((44100, 48000), (48000, 192000), (96000, 48000)):
