@@ -174,3 +174,21 @@ def default_device() -> int:
 def current_stream_ptr(device) -> int:
     import torch
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class StreamWorkspace:
+    """Scratch memory of a plan, one buffer per CUDA stream that launches it: executes issued from two streams must not
+    share scratch (nothing orders them), and on one stream the caching allocator already orders a grown buffer after
+    the launches that used the old one."""
+
+    def __init__(self, device: int):
+        self.device = int(device)
+        self._by_stream = {}
+
+    def get(self, need: int):
+        import torch
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._by_stream.get(key)
+        if ws is None or ws.numel() < need:
+            ws = self._by_stream[key] = torch.empty(int(need), dtype=torch.uint8, device=f"cuda:{self.device}")
+        return ws

@@ -47,7 +47,7 @@ class DeconvPlan:
         n, n1, n2 = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.lib().impb_deconv_plan_info(h, C.byref(n), C.byref(n1), C.byref(n2))
         self.nfft, self.n1, self.n2 = n.value, n1.value, n2.value
-        self._ws = None
+        self._ws = _lib.StreamWorkspace(self.device)
         self._lock = threading.Lock()
 
     def __del__(self):
@@ -58,11 +58,7 @@ class DeconvPlan:
             pass
 
     def workspace(self, batch: int):
-        import torch
-        need = _lib.lib().impb_deconv_workspace_bytes(self.handle, int(batch))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
-        return self._ws
+        return self._ws.get(_lib.lib().impb_deconv_workspace_bytes(self.handle, int(batch)))
 
     def launches(self, batch: int) -> int:
         return int(_lib.lib().impb_deconv_launches_per_execute(self.handle, int(batch)))

@@ -316,7 +316,7 @@ class FftPlan:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().impb_fft_create(self.ctx.handle, self.n, 64, C.byref(h)), "impb_fft_create")
         self.handle = h
-        self._ws = None
+        self._ws = _lib.StreamWorkspace(self.device)
 
     def __del__(self):
         try:
@@ -326,11 +326,7 @@ class FftPlan:
             pass
 
     def workspace(self, batch):
-        torch = _torch()
-        need = _lib.lib().impb_fft_workspace_bytes(self.handle, int(batch))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
-        return self._ws
+        return self._ws.get(_lib.lib().impb_fft_workspace_bytes(self.handle, int(batch)))
 
 
 _plan_lock = threading.Lock()
@@ -660,7 +656,7 @@ class MinPhasePlan:
             _lib.check(_lib.lib().impb_minphase_create(self.ctx.handle, self.n, ham.ctypes.data, C.byref(h)),
                        "impb_minphase_create")
         self.handle = h
-        self._ws = None
+        self._ws = _lib.StreamWorkspace(self.device)
 
     def __del__(self):
         try:
@@ -670,11 +666,7 @@ class MinPhasePlan:
             pass
 
     def workspace(self, batch):
-        torch = _torch()
-        need = _lib.lib().impb_minphase_workspace_bytes(self.handle, int(batch))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device}")
-        return self._ws
+        return self._ws.get(_lib.lib().impb_minphase_workspace_bytes(self.handle, int(batch)))
 
 
 def minphase_plan(n, device=0) -> MinPhasePlan:
