@@ -72,7 +72,10 @@ def _dev_const(values, device):
     torch = _torch()
     if isinstance(values, torch.Tensor):
         return values
-    return _dev_window(np.asarray(values, dtype=np.float64), device)
+    arr = np.asarray(values, dtype=np.float64)
+    if arr.size == 0:
+        return torch.empty(0, dtype=torch.float64, device=device)
+    return _dev_window(arr, device)
 
 
 def _dev_index_const(values, device):
